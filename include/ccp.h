@@ -1,0 +1,178 @@
+/*
+ * ccp.h -- C ABI of the B200 conjugate-point engine (libccp_b200.so).
+ *
+ * Drop-in boundary for ONE hot path of JCJaquette/Computing-Conjugate-Points:
+ *   propagateManifold::frameDet            (reference propagateManifold.cpp:125-188)
+ *     -> computeTotalTrajectory x n        (propagateManifold.cpp:84-121)
+ *     -> getTotalTrajectory                (utils.cpp:175-263)
+ *     -> topFrame::initialize / countZeros / getLastFrame / getFirstFrame
+ *                                          (topFrame.cpp:4-108, 193-351)
+ * The reference has no FFI layer (everything is CAPD value types passed between C++
+ * member functions), so the boundary is drawn around "n trajectories + topFrame" and
+ * expressed as plain-old-data descriptors in / result records out.  One descriptor is
+ * exactly the data propagateManifold::construct_InitCondU / construct_A_lin
+ * (propagateManifold.cpp:6-81) assemble for one parameter value; one result record is
+ * what frameDet consumes afterwards (countZeros output, last/first frame for the L_+ test).
+ *
+ * No C++ or torch types cross this boundary.  All functions return 0 on success or a
+ * negative CCP_E_* code; numerical failures of a single front are reported per front in
+ * ccp_front_result.status and never abort the batch (mirrors the per-parameter try/catch
+ * of SampleParameters, heteroclinic.cpp:456-467).
+ */
+#ifndef CCP_H
+#define CCP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CCP_MAX_N      4      /* coupled PDE components n (reference: 2 or 3; 4 = chain extension) */
+#define CCP_MAX_DIM    8      /* 2n: phase-space dimension of the front ODE                          */
+#define CCP_MAX_ORDER  20     /* Taylor order p (reference: order = 20, heteroclinic.cpp:63)         */
+#define CCP_MAX_GRID   16     /* sub-intervals per step (reference: grid = 14, heteroclinic.cpp:66)  */
+#define CCP_MAX_CONJ   8      /* recorded conjugate-point time intervals per front                   */
+
+/* closed interval [lo,hi] of doubles (CAPD `interval` restricted to double end points) */
+typedef struct { double lo, hi; } ccp_interval;
+
+/* ---- input: one standing front (one parameter value, or one sub-box of its initial set) ---- */
+typedef struct {
+    int32_t n;            /* number of components; dimension = 2n, coupled system d = 4n                 */
+    int32_t order;        /* Taylor order p          (propagateManifold.h:63 `order`)                   */
+    int32_t step_log2;    /* fixed step h = 2^-step_log2 (propagateManifold.cpp:92 `step_size`)         */
+    int32_t grid;         /* sub-intervals per step  (frameDet argument `grid`)                          */
+    double  L_minus;      /* integration time L_- as an exact double (heteroclinic.cpp:324)             */
+    ccp_interval b[CCP_MAX_N];        /* b_1..b_n  (n=2: a,b)  ODE_functions.cpp:257-273                */
+    ccp_interval c[CCP_MAX_N - 1];    /* c_12, c_23, ... chain couplings (n=2: c)                       */
+    double  A_u[CCP_MAX_DIM * CCP_MAX_DIM];   /* row-major, leading dim CCP_MAX_DIM: eigenbasis at (0,..,0),
+                                                 columns 0..n-1 unstable, n..2n-1 stable (point matrix;
+                                                 heteroclinic.cpp:116-117, construct_A_lin)               */
+    ccp_interval p_i[CCP_MAX_DIM];    /* phi(-L_-) in global coords (localManifold::getPointNbd [0])    */
+    ccp_interval Uxy[CCP_MAX_DIM];    /* its error box in local eigen-coords (getPointNbd [1])          */
+    ccp_interval Eu_err[CCP_MAX_N * CCP_MAX_N]; /* row-major ld CCP_MAX_N: Eu_m_Error_Final[j][k] =
+                                                 error of eigen-direction k along stable coordinate j
+                                                 (localManifold.cpp:673-681)                             */
+} ccp_front_desc;
+
+/* per-front status */
+enum {
+    CCP_OK              = 0,
+    CCP_ST_BAD_DESC     = 1,   /* n/order/grid out of range, L_minus <= 0, non-finite input            */
+    CCP_ST_ENCLOSURE    = 2,   /* a-priori (rough) enclosure of a step could not be verified            */
+    CCP_ST_NONFINITE    = 3    /* NaN/inf appeared in an enclosure                                     */
+};
+
+/* ---- output: what frameDet / topFrame hand back for one front ---- */
+typedef struct {
+    int32_t status;           /* CCP_OK or CCP_ST_*                                                     */
+    int32_t zero_count;       /* certified sign changes of det(top frame)  (countZeros output[0])      */
+    int32_t failure_count;    /* sub-intervals that could not be certified (countZeros output[1])      */
+    int32_t series_length;    /* steps * grid                                                          */
+    int32_t steps;            /* integrator steps taken (last one may be partial, utils.cpp:258)       */
+    int32_t n_conj;           /* min(zero_count, CCP_MAX_CONJ) entries valid below                      */
+    int32_t first_failure;    /* sub-interval index of first failure, -1 if none                       */
+    int32_t reserved;
+    ccp_interval conj_time[CCP_MAX_CONJ];   /* time label (prevTime+sub) of each certified crossing     */
+    int32_t      conj_index[CCP_MAX_CONJ];  /* its sub-interval index                                   */
+    /* topFrame::getLastFrame (topFrame.cpp:265-299): rows 0..2n-1, row-major ld = CCP_MAX_N+2.
+       cols 0..n-1: (U,V) of trajectory k at the right end of the last sub-interval;
+       col n: phi' over the whole last sub-interval; col n+1: phi at the right end.                    */
+    ccp_interval last_frame[CCP_MAX_DIM * (CCP_MAX_N + 2)];
+    /* data for topFrame::getFirstFrame (topFrame.cpp:301-331), row-major ld = CCP_MAX_N+1.
+       cols 0..n-1: (U,V) of trajectory k at the left end of the first sub-interval;
+       col n: phi' over the whole first sub-interval.                                                  */
+    ccp_interval first_frame[CCP_MAX_DIM * (CCP_MAX_N + 1)];
+    ccp_interval det_first;   /* det range enclosure on the first sub-interval                          */
+    ccp_interval det_last;    /* det range enclosure on the last sub-interval                           */
+} ccp_front_result;
+
+/* optional per-sub-interval series (topFrame::time_series / det_series, makePlot) */
+typedef struct {
+    ccp_interval time;    /* prevTime + sub                 (utils.cpp:242)  */
+    ccp_interval det_L;   /* det of left-end frame          det_series[i][0] */
+    ccp_interval det_R;   /* det of right-end frame         det_series[i][1] */
+    ccp_interval det_V;   /* det of range frame             det_series[i][2] (what plot_det.txt holds) */
+    ccp_interval det_D;   /* d/dt det, Jacobi formula       calculateDerivative (topFrame.cpp:110-122) */
+} ccp_series_rec;
+
+/* error codes of the API itself */
+enum {
+    CCP_E_CUDA      = -100,   /* CUDA runtime error (see ccp_last_error)            */
+    CCP_E_NO_DEVICE = -101,   /* no CUDA device: there is NO CPU fallback           */
+    CCP_E_ARG       = -102,
+    CCP_E_NOT_INIT  = -103
+};
+
+/* ---------------- engine life cycle ---------------- */
+int  ccp_device_count(void);
+int  ccp_init(int device);            /* binds this process to one GPU, creates stream + scratch       */
+void ccp_shutdown(void);
+const char* ccp_last_error(void);
+const char* ccp_version(void);
+
+/* ---------------- the hot path ---------------- */
+/* Replaces the call `E_u.frameDet(L_minus,grid,endPoint_LPlus-p_s)` (heteroclinic.cpp:334) for a
+   batch of fronts: host buffers in, host buffers out (H2D + kernel + D2H inside). */
+int ccp_frame_count_batch(const ccp_front_desc* fronts, size_t n_fronts, ccp_front_result* results);
+
+/* Same, device-resident: `d_fronts`/`d_results` are device pointers, `stream` a cudaStream_t (or NULL
+   for the engine stream).  Asynchronous: returns after enqueueing.  */
+int ccp_frame_count_batch_device(const void* d_fronts, size_t n_fronts, void* d_results, void* stream);
+
+/* One front with the full per-sub-interval series (topFrame::makePlot equivalent).  `cap` records
+   available in `series`; *len receives steps*grid.  */
+int ccp_frame_count_series(const ccp_front_desc* front, ccp_front_result* result,
+                           ccp_series_rec* series, size_t cap, size_t* len);
+
+/* kernel launch accounting + last kernel time for bench.py */
+uint64_t ccp_kernel_launches(void);
+float    ccp_last_kernel_ms(void);
+
+/* FP64 DFMA-chain peak of the bound device in TFLOP/s (roofline denominator) */
+int ccp_measure_fp64_peak(int iters, double* tflops);
+
+/* FP64 work of one front under the implemented algorithm: flop (1 DFMA = 2) */
+double ccp_front_flops(int n, int order, int grid, int steps);
+
+/* ---------------- host-side setup of descriptors (non-rigorous float shooting) ----------------
+   Re-states stage (i) of computeFrontAndConjugatePoints (heteroclinic.cpp:96-191, 324) in plain
+   doubles so that synthetic sweeps can be generated without CAPD.  Not part of the timed path. */
+typedef struct {
+    double xy_nbd;        /* +- radius of the validated BVP neighbourhood in x (local coords)           */
+    double cone_L;        /* cone constant L (heteroclinic.cpp:80-87); <=0 -> reference default per n   */
+    double eig_err;       /* +- magnitude of Eu_m_Error_Final entries; <0 -> 2e-4 (n=2) / 2e-5 (n>=3)   */
+    double scale;         /* manifold scale; <=0 -> reference default per n                             */
+    double L_minus_percent; /* <=0 -> 0.84 (heteroclinic.cpp:72)                                        */
+    double L_minus_override; /* >0 -> use this L_minus instead of sup(2*T*percent)                      */
+    int32_t order, step_log2, grid;   /* <=0 -> 20, 5, 14                                               */
+    int32_t newton_steps;             /* <=0 -> 20                                                      */
+} ccp_setup_opts;
+
+typedef struct {
+    double T;             /* shooting time after FindTime (boundaryValueProblem.cpp:118)                */
+    double L_minus;
+    double newton_residual;
+    double eig_unstable[CCP_MAX_N];
+    double x_local[CCP_MAX_N];
+    double y_local[CCP_MAX_N];
+    int32_t converged;
+    int32_t reserved;
+} ccp_setup_info;
+
+/* params = (b_1..b_n, c_12..c_{n-1,n}) as doubles */
+int ccp_setup_front(int n, const double* params, const ccp_setup_opts* opts,
+                    ccp_front_desc* out, ccp_setup_info* info);
+/* n_fronts parameter vectors, each 2n-1 doubles, `threads` host threads (<=0: all cores) */
+int ccp_setup_sweep(int n, const double* params, size_t n_fronts, const ccp_setup_opts* opts,
+                    ccp_front_desc* out, ccp_setup_info* info, int threads);
+/* the reference's own sweep generator, Construct_ParameterList (heteroclinic.cpp:386-427):
+   writes N_c*N_r vectors (b1,b2,b3,c12,c23) */
+int ccp_parameter_list(int N_c, int N_r, double r_min, double r_max, const double* b3, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CCP_H */
