@@ -8,7 +8,7 @@ import ctypes as C
 CCP_MAX_N = 4
 CCP_MAX_DIM = 8
 CCP_MAX_ORDER = 20
-CCP_MAX_GRID = 16
+CCP_MAX_GRID = 15
 CCP_MAX_CONJ = 8
 
 CCP_OK, CCP_ST_BAD_DESC, CCP_ST_ENCLOSURE, CCP_ST_NONFINITE = 0, 1, 2, 3
@@ -25,7 +25,7 @@ class Interval(C.Structure):
 class FrontDesc(C.Structure):
     _fields_ = [
         ("n", C.c_int32), ("order", C.c_int32), ("step_log2", C.c_int32), ("grid", C.c_int32),
-        ("L_minus", C.c_double),
+        ("L_minus", C.c_double), ("reserved", C.c_double),
         ("b", Interval * CCP_MAX_N),
         ("c", Interval * (CCP_MAX_N - 1)),
         ("A_u", C.c_double * (CCP_MAX_DIM * CCP_MAX_DIM)),
@@ -89,6 +89,7 @@ SYMBOLS = {
     "ccp_frame_count_series": (C.c_int, [C.POINTER(FrontDesc), C.POINTER(FrontResult), C.POINTER(SeriesRec), C.c_size_t, C.POINTER(C.c_size_t)]),
     "ccp_kernel_launches": (C.c_uint64, []),
     "ccp_last_kernel_ms": (C.c_float, []),
+    "ccp_debug_primitives": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_size_t]),
     "ccp_measure_fp64_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
     "ccp_front_flops": (C.c_double, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "ccp_setup_front": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(SetupOpts), C.POINTER(FrontDesc), C.POINTER(SetupInfo)]),

@@ -1,0 +1,314 @@
+// ccp_engine.cu -- C ABI of libccp_b200.so (include/ccp.h): engine life cycle, batched launches,
+// FP64 peak microbenchmark.  There is NO CPU fallback: without a CUDA device every compute entry
+// point returns CCP_E_NO_DEVICE.
+#include "ccp_kernel.cuh"
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <vector>
+#include <mutex>
+#include <string>
+
+namespace {
+
+struct Engine {
+    bool ready = false;
+    int device = -1;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    void* d_desc = nullptr;  size_t desc_cap = 0;
+    void* d_res = nullptr;   size_t res_cap = 0;
+    int*  d_index = nullptr; size_t index_cap = 0;
+    void* d_series = nullptr; size_t series_cap = 0;
+    int grid_limit[CCP_MAX_N + 1] = {0, 0, 0, 0, 0};
+    unsigned long long launches = 0;
+    float last_ms = 0.f;
+    std::string err;
+    std::mutex mu;
+};
+Engine E;
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { E.err = std::string(#call) + ": " + cudaGetErrorString(e_); return CCP_E_CUDA; } } while (0)
+
+template <int N> int prepare_kernel() {
+    const size_t smem = sizeof(ccp::FrontSmem<N>);
+    CK(cudaFuncSetAttribute(ccp::front_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ccp::front_kernel<N>, 32, smem));
+    if (per_sm < 1) { E.err = "kernel does not fit on an SM"; return CCP_E_CUDA; }
+    E.grid_limit[N] = per_sm * E.sm_count;
+    return 0;
+}
+
+template <int N> int launch(const ccp_front_desc* d_desc, ccp_front_result* d_res, const int* d_index, int count,
+                            ccp_series_rec* series, int series_cap, cudaStream_t st) {
+    if (count <= 0) return 0;
+    // one warp (= one CTA) per front; the grid is sized to the number of CTAs that are resident at once
+    // (multiple of the SM count) and strides over the batch.
+    int grid = count < E.grid_limit[N] ? count : E.grid_limit[N];
+    ccp::front_kernel<N><<<grid, 32, sizeof(ccp::FrontSmem<N>), st>>>(d_desc, d_res, d_index, count, series, series_cap);
+    E.launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int ensure(void** p, size_t* cap, size_t bytes) {
+    if (*cap >= bytes) return 0;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    CK(cudaMalloc(p, bytes));
+    *cap = bytes;
+    return 0;
+}
+
+// launches the per-n kernels for a device-resident batch; `h_n` = host copy of the n field of every descriptor
+int run_device(const ccp_front_desc* d_desc, ccp_front_result* d_res, const std::vector<int>& h_n, cudaStream_t st) {
+    const size_t nf = h_n.size();
+    bool uniform = true;
+    for (size_t i = 1; i < nf; i++) if (h_n[i] != h_n[0]) { uniform = false; break; }
+    if (uniform) {
+        switch (h_n[0]) {
+            case 2: return launch<2>(d_desc, d_res, nullptr, (int)nf, nullptr, 0, st);
+            case 3: return launch<3>(d_desc, d_res, nullptr, (int)nf, nullptr, 0, st);
+            case 4: return launch<4>(d_desc, d_res, nullptr, (int)nf, nullptr, 0, st);
+            default: break;
+        }
+    }
+    // mixed batch: one index list per n; anything else is answered by the n=2 kernel with CCP_ST_BAD_DESC
+    std::vector<int> idx[3];
+    for (size_t i = 0; i < nf; i++) { int n = h_n[i]; idx[(n == 3) ? 1 : (n == 4) ? 2 : 0].push_back((int)i); }
+    int rc = ensure((void**)&E.d_index, &E.index_cap, nf * sizeof(int)); if (rc) return rc;
+    size_t off = 0;
+    for (int k = 0; k < 3; k++) {
+        if (idx[k].empty()) continue;
+        CK(cudaMemcpyAsync(E.d_index + off, idx[k].data(), idx[k].size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));   // idx[k] is a stack-owned vector
+        if (k == 0) rc = launch<2>(d_desc, d_res, E.d_index + off, (int)idx[k].size(), nullptr, 0, st);
+        if (k == 1) rc = launch<3>(d_desc, d_res, E.d_index + off, (int)idx[k].size(), nullptr, 0, st);
+        if (k == 2) rc = launch<4>(d_desc, d_res, E.d_index + off, (int)idx[k].size(), nullptr, 0, st);
+        if (rc) return rc;
+        off += idx[k].size();
+    }
+    return 0;
+}
+
+// ---- FP64 peak: independent DFMA chains, 8 per thread ----
+__global__ void dfma_peak_kernel(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x * 1e-9, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            x0 = __fma_ru(x0, a, b); x1 = __fma_rd(x1, a, b); x2 = __fma_ru(x2, a, b); x3 = __fma_rd(x3, a, b);
+            x4 = __fma_ru(x4, a, b); x5 = __fma_rd(x5, a, b); x6 = __fma_ru(x6, a, b); x7 = __fma_rd(x7, a, b);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+// ---- primitive probe: one op per element, 8 inputs -> 4 outputs (unit tests compare with the oracle bit for bit) ----
+__global__ void debug_prim_kernel(int op, const double* in, double* out, int n) {
+    using namespace ccp;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double* x = in + 8 * (size_t)i; double* o = out + 4 * (size_t)i;
+    o[0] = o[1] = o[2] = o[3] = 0.0;
+    switch (op) {
+        case 0: o[0] = __dadd_rd(x[0], x[1]); break;
+        case 1: o[0] = __dadd_ru(x[0], x[1]); break;
+        case 2: o[0] = __dmul_rd(x[0], x[1]); break;
+        case 3: o[0] = __dmul_ru(x[0], x[1]); break;
+        case 4: o[0] = __fma_rd(x[0], x[1], x[2]); break;
+        case 5: o[0] = __fma_ru(x[0], x[1], x[2]); break;
+        case 6: o[0] = __ddiv_rd(x[0], x[1]); break;
+        case 7: o[0] = __ddiv_ru(x[0], x[1]); break;
+        case 10: { ival r = imul(mk(x[0], x[1]), mk(x[2], x[3])); o[0] = r.lo; o[1] = r.hi; break; }
+        case 11: { mt r = iv2mt(mk(x[0], x[1])); o[0] = r.m; o[1] = r.t; break; }
+        case 12: { mt a; a.m = x[0]; a.t = x[1]; ival r = mt2iv(a); o[0] = r.lo; o[1] = r.hi; break; }
+        case 13: { acc4 a = acc_zero(); mt p, q; p.m = x[0]; p.t = x[1]; q.m = x[2]; q.t = x[3]; acc_term(a, p, q);
+                   p.m = x[4]; p.t = x[5]; q.m = x[6]; q.t = x[7]; acc_term_neg(a, p, q); ival r = acc_finish(a); o[0] = r.lo; o[1] = r.hi; break; }
+        case 14: { ival r = idivk(mk(x[0], x[1]), (int)x[2]); o[0] = r.lo; o[1] = r.hi; break; }
+        case 15: { ival r = horner_rg(mk(x[0], x[1]), x[2], x[3], mk(x[4], x[5])); o[0] = r.lo; o[1] = r.hi; break; }
+        case 16: { ival r = isub(mk(x[0], x[1]), mk(x[2], x[3])); o[0] = r.lo; o[1] = r.hi; break; }
+        case 17: { ival r = iadd(mk(x[0], x[1]), mk(x[2], x[3])); o[0] = r.lo; o[1] = r.hi; break; }
+        case 18: { ival r = imulk(mk(x[0], x[1]), (int)x[2]); o[0] = r.lo; o[1] = r.hi; break; }
+        case 19: { ival r = horner_pt(mk(x[0], x[1]), x[2], mk(x[4], x[5])); o[0] = r.lo; o[1] = r.hi; break; }
+        case 20: { ival m[3][3]; for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) { int q = (a * 3 + b) % 7; m[a][b] = mk(dmin(x[q], x[q + 1]), dmax(x[q], x[q + 1])); }
+                   ival r = Det<3>::det(m); o[0] = r.lo; o[1] = r.hi; break; }
+        default: break;
+    }
+}
+
+} // namespace
+
+extern "C" {
+
+int ccp_debug_primitives(int op, const double* in, double* out, size_t n) {
+    if (!E.ready) { E.err = "ccp_init not called (or no device)"; return CCP_E_NOT_INIT; }
+    double *d_in = nullptr, *d_out = nullptr;
+    CK(cudaMalloc(&d_in, n * 8 * sizeof(double)));
+    CK(cudaMalloc(&d_out, n * 4 * sizeof(double)));
+    CK(cudaMemcpyAsync(d_in, in, n * 8 * sizeof(double), cudaMemcpyHostToDevice, E.stream));
+    debug_prim_kernel<<<(unsigned)((n + 127) / 128), 128, 0, E.stream>>>(op, d_in, d_out, (int)n);
+    E.launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, d_out, n * 4 * sizeof(double), cudaMemcpyDeviceToHost, E.stream));
+    CK(cudaStreamSynchronize(E.stream));
+    cudaFree(d_in); cudaFree(d_out);
+    return 0;
+}
+
+const char* ccp_version(void) { return "ccp_b200 0.1 (sm_100a, c1-structured interval Taylor kernel)"; }
+const char* ccp_last_error(void) { return E.err.c_str(); }
+
+int ccp_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int ccp_init(int device) {
+    std::lock_guard<std::mutex> lk(E.mu);
+    if (E.ready) return 0;
+    int n = ccp_device_count();
+    if (n <= 0) { E.err = "no CUDA device visible: libccp_b200 has no CPU fallback"; return CCP_E_NO_DEVICE; }
+    if (device < 0 || device >= n) { E.err = "bad device index"; return CCP_E_ARG; }
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    E.device = device; E.sm_count = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&E.stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&E.ev0));
+    CK(cudaEventCreate(&E.ev1));
+    int rc;
+    if ((rc = prepare_kernel<2>())) return rc;
+    if ((rc = prepare_kernel<3>())) return rc;
+    if ((rc = prepare_kernel<4>())) return rc;
+    E.ready = true;
+    return 0;
+}
+
+void ccp_shutdown(void) {
+    std::lock_guard<std::mutex> lk(E.mu);
+    if (!E.ready) return;
+    cudaStreamSynchronize(E.stream);
+    if (E.d_desc) cudaFree(E.d_desc);
+    if (E.d_res) cudaFree(E.d_res);
+    if (E.d_index) cudaFree(E.d_index);
+    if (E.d_series) cudaFree(E.d_series);
+    E.d_desc = E.d_res = E.d_series = nullptr; E.d_index = nullptr;
+    E.desc_cap = E.res_cap = E.index_cap = E.series_cap = 0;
+    cudaEventDestroy(E.ev0); cudaEventDestroy(E.ev1);
+    cudaStreamDestroy(E.stream);
+    E.stream = nullptr; E.ready = false;
+}
+
+int ccp_frame_count_batch(const ccp_front_desc* fronts, size_t n_fronts, ccp_front_result* results) {
+    if (!E.ready) { E.err = "ccp_init not called (or no device)"; return CCP_E_NOT_INIT; }
+    if (n_fronts == 0) return 0;
+    if (!fronts || !results) return CCP_E_ARG;
+    std::lock_guard<std::mutex> lk(E.mu);
+    int rc;
+    if ((rc = ensure(&E.d_desc, &E.desc_cap, n_fronts * sizeof(ccp_front_desc)))) return rc;
+    if ((rc = ensure(&E.d_res, &E.res_cap, n_fronts * sizeof(ccp_front_result)))) return rc;
+    std::vector<int> h_n(n_fronts);
+    for (size_t i = 0; i < n_fronts; i++) h_n[i] = fronts[i].n;
+    CK(cudaMemcpyAsync(E.d_desc, fronts, n_fronts * sizeof(ccp_front_desc), cudaMemcpyHostToDevice, E.stream));
+    CK(cudaEventRecord(E.ev0, E.stream));
+    if ((rc = run_device((const ccp_front_desc*)E.d_desc, (ccp_front_result*)E.d_res, h_n, E.stream))) return rc;
+    CK(cudaEventRecord(E.ev1, E.stream));
+    CK(cudaMemcpyAsync(results, E.d_res, n_fronts * sizeof(ccp_front_result), cudaMemcpyDeviceToHost, E.stream));
+    CK(cudaStreamSynchronize(E.stream));
+    CK(cudaEventElapsedTime(&E.last_ms, E.ev0, E.ev1));
+    return 0;
+}
+
+int ccp_frame_count_batch_device(const void* d_fronts, size_t n_fronts, void* d_results, void* stream) {
+    if (!E.ready) { E.err = "ccp_init not called (or no device)"; return CCP_E_NOT_INIT; }
+    if (n_fronts == 0) return 0;
+    if (!d_fronts || !d_results) return CCP_E_ARG;
+    std::lock_guard<std::mutex> lk(E.mu);
+    cudaStream_t st = stream ? (cudaStream_t)stream : E.stream;
+    // the n field is needed on the host to pick the kernel instantiation: read the first descriptor's header
+    // and assume a uniform batch when called device-resident (mixed batches go through ccp_frame_count_batch).
+    int n0 = 0;
+    CK(cudaMemcpyAsync(&n0, d_fronts, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    switch (n0) {
+        case 2: return launch<2>((const ccp_front_desc*)d_fronts, (ccp_front_result*)d_results, nullptr, (int)n_fronts, nullptr, 0, st);
+        case 3: return launch<3>((const ccp_front_desc*)d_fronts, (ccp_front_result*)d_results, nullptr, (int)n_fronts, nullptr, 0, st);
+        case 4: return launch<4>((const ccp_front_desc*)d_fronts, (ccp_front_result*)d_results, nullptr, (int)n_fronts, nullptr, 0, st);
+        default: E.err = "device batch: unsupported n in first descriptor"; return CCP_E_ARG;
+    }
+}
+
+int ccp_frame_count_series(const ccp_front_desc* front, ccp_front_result* result, ccp_series_rec* series, size_t cap, size_t* len) {
+    if (!E.ready) { E.err = "ccp_init not called (or no device)"; return CCP_E_NOT_INIT; }
+    if (!front || !result) return CCP_E_ARG;
+    std::lock_guard<std::mutex> lk(E.mu);
+    int rc;
+    if ((rc = ensure(&E.d_desc, &E.desc_cap, sizeof(ccp_front_desc)))) return rc;
+    if ((rc = ensure(&E.d_res, &E.res_cap, sizeof(ccp_front_result)))) return rc;
+    size_t want = 0;
+    if (front->step_log2 >= 1 && front->step_log2 <= 20 && front->L_minus > 0 && std::isfinite(front->L_minus) && front->grid >= 1 && front->grid <= CCP_MAX_GRID)
+        want = (size_t)ccp::step_count(front->L_minus, std::ldexp(1.0, -front->step_log2)) * front->grid;
+    if (len) *len = want;
+    size_t ncap = (series && cap) ? (want < cap ? want : cap) : 0;
+    if (ncap) { if ((rc = ensure(&E.d_series, &E.series_cap, ncap * sizeof(ccp_series_rec)))) return rc; }
+    CK(cudaMemcpyAsync(E.d_desc, front, sizeof(ccp_front_desc), cudaMemcpyHostToDevice, E.stream));
+    ccp_series_rec* ds = ncap ? (ccp_series_rec*)E.d_series : nullptr;
+    switch (front->n) {
+        case 3: rc = launch<3>((const ccp_front_desc*)E.d_desc, (ccp_front_result*)E.d_res, nullptr, 1, ds, (int)ncap, E.stream); break;
+        case 4: rc = launch<4>((const ccp_front_desc*)E.d_desc, (ccp_front_result*)E.d_res, nullptr, 1, ds, (int)ncap, E.stream); break;
+        default: rc = launch<2>((const ccp_front_desc*)E.d_desc, (ccp_front_result*)E.d_res, nullptr, 1, ds, (int)ncap, E.stream); break;
+    }
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(result, E.d_res, sizeof(ccp_front_result), cudaMemcpyDeviceToHost, E.stream));
+    if (ncap) CK(cudaMemcpyAsync(series, E.d_series, ncap * sizeof(ccp_series_rec), cudaMemcpyDeviceToHost, E.stream));
+    CK(cudaStreamSynchronize(E.stream));
+    return 0;
+}
+
+uint64_t ccp_kernel_launches(void) { return E.launches; }
+float ccp_last_kernel_ms(void) { return E.last_ms; }
+
+int ccp_measure_fp64_peak(int iters, double* tflops) {
+    if (!E.ready) { E.err = "ccp_init not called (or no device)"; return CCP_E_NOT_INIT; }
+    if (!tflops) return CCP_E_ARG;
+    if (iters < 1) iters = 4096;
+    const int threads = 256, blocks = E.sm_count * 8;
+    double* d_out = nullptr;
+    CK(cudaMalloc(&d_out, sizeof(double) * threads * blocks));
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {
+        CK(cudaEventRecord(E.ev0, E.stream));
+        dfma_peak_kernel<<<blocks, threads, 0, E.stream>>>(d_out, iters, 0.999999, 1e-7);
+        CK(cudaEventRecord(E.ev1, E.stream));
+        CK(cudaStreamSynchronize(E.stream));
+        float ms = 0; CK(cudaEventElapsedTime(&ms, E.ev0, E.ev1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaFree(d_out);
+    const double flop = 2.0 * 64.0 * (double)iters * threads * blocks;     // 64 DFMA per thread per iteration
+    *tflops = flop / (best * 1e-3) / 1e12;
+    return 0;
+}
+
+// FP64 work of one front under the implemented algorithm: DFMA = 2 flop, DADD/DMUL = 1.
+double ccp_front_flops(int n, int order, int grid, int steps) {
+    const double p = order, g = grid, N = n, D = 2.0 * n;
+    const double P2 = p * (p + 1) / 2;                                      // sum_{k<p} (k+1) Cauchy terms per product
+    const double products = 2 * (5 * N - 3) + D * (3 * N - 2);              // centre + hull phi tables, Psi tables
+    const double terms = products * P2 + (p + 1) * N * N * D;               // + frame tables
+    const double dfma_cauchy = 4 * terms;
+    const double horner_fma = 2 * ((g + 1) * N * N * p + g * N * N * p + g * N * N * (p - 1) + (D + D * D) * p);
+    const double horner_mul = 2 * g * N * N * (p - 1);
+    const double linalg = 2 * D * D * D * 10 + 4 * D * D * 10;             // J*C, J*P (8 DMUL + 2 DADD per interval MAC), hull, r update
+    const double conv = 10 * (2 * (4 * N - 1) + 2 * N * D + (2 * N - 1)) * p; // iv2mt / mt2iv / divisions per stored coefficient
+    const double det3 = (N == 2 ? 17 : N == 3 ? 82 : 360), jac = (N == 2 ? 50 : N == 3 ? 252 : 1500);
+    const double dets = g * (3 * det3 + jac);
+    const double per_step = 2 * (dfma_cauchy + horner_fma) + horner_mul + linalg + conv + dets;
+    return per_step * steps;
+}
+
+} // extern "C"

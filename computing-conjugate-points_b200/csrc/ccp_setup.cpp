@@ -286,28 +286,64 @@ static int setup_one(int n, const double* params, const ccp_setup_opts* o, ccp_f
         if (d0_first < d0) T = T0;
     }
 
-    // zero-width Newton on (x,y), last equation |x|^2 = r_u^2 (boundaryValueProblem.cpp:237-353)
+    // zero-width Newton on (x,y), last equation |x|^2 = r_u^2 (boundaryValueProblem.cpp:237-353).
+    // The reference takes 20 plain Newton steps; for weak couplings the phase-locking directions are soft and
+    // plain Newton from the uncoupled guess can overshoot, so the step is damped by backtracking on |G|.
     double resid = 0; int converged = 0;
-    for (int it = 0; it < newton; it++) {
-        double Gx[MAXD], Gy[MAXD], Px[MAXD * MAXD], Py[MAXD * MAXD];
-        endpoints(T, Gx, Gy, Px, Py);
-        double G[MAXD], DG[MAXD * MAXD];
+    auto residual = [&](const double* xx, const double* yy, double* G, double* Px, double* Py) {
+        double Gx[MAXD], Gy[MAXD];
+        for (int r = 0; r < D; r++) { double a = 0, bq = 0; for (int i = 0; i < n; i++) { a += Au[r][i] * xx[i]; bq += As[r][n + i] * yy[i]; } Gx[r] = a; Gy[r] = bq + (r < n ? 1.0 : 0.0); }
+        flow(s, Gx, Px, T);
+        flow(s, Gy, Py, -T);
         for (int r = 0; r < D; r++) G[r] = Gx[r] - Gy[r];
-        double xr = 0; for (int i = 0; i < n; i++) xr += x[i] * x[i];
-        G[D - 1] = xr - r_u_sqr;
+        double xr = 0; for (int i = 0; i < n; i++) xr += xx[i] * xx[i];
+        G[D - 1] = (xr - r_u_sqr) / r_u_sqr;          // relative radius defect (same zero set as the reference's row)
+        double nn = 0; for (int r = 0; r < D; r++) nn += G[r] * G[r];
+        return std::sqrt(nn);
+    };
+    // Levenberg-Marquardt in scaled variables z = (x,y)/scale: the weak-coupling phase modes make DG nearly
+    // singular away from the solution, where a pure Newton direction is dominated by the null vector.
+    const int max_it = std::max(newton, 400);
+    double G[MAXD], Px[MAXD * MAXD], Py[MAXD * MAXD];
+    double gn = residual(x, y, G, Px, Py);
+    double mu = 1e-2;
+    for (int it = 0; it < max_it && std::isfinite(gn); it++) {
+        double DG[MAXD * MAXD];
         for (int r = 0; r < D; r++) for (int j = 0; j < D; j++) {
             double a = 0;
             if (j < n) { for (int k = 0; k < D; k++) a += Px[r * D + k] * Au[k][j]; }
             else       { for (int k = 0; k < D; k++) a -= Py[r * D + k] * As[k][j]; }
-            DG[r * D + j] = a;
+            DG[r * D + j] = a * scale;
         }
-        for (int j = 0; j < D; j++) DG[(D - 1) * D + j] = (j < n) ? 2.0 * x[j] : 0.0;
-        resid = 0; for (int r = 0; r < D; r++) resid = std::max(resid, std::fabs(G[r]));
-        if (!solve_linear(D, DG, G)) break;
-        double stepn = 0;
-        for (int i = 0; i < n; i++) { x[i] -= G[i]; y[i] -= G[n + i]; stepn = std::max(stepn, std::fabs(G[i]) / scale); stepn = std::max(stepn, std::fabs(G[n + i]) / scale); }
-        if (stepn < 1e-11) { if (converged) break; converged = 1; }   // reference runs a fixed 20; the iterates no longer move
+        for (int j = 0; j < D; j++) DG[(D - 1) * D + j] = (j < n) ? 2.0 * x[j] / r_u_sqr * scale : 0.0;
+        double JtJ[MAXD * MAXD], Jtg[MAXD];
+        for (int i = 0; i < D; i++) {
+            double a = 0; for (int r = 0; r < D; r++) a += DG[r * D + i] * G[r];
+            Jtg[i] = a;
+            for (int j = 0; j < D; j++) { double b2 = 0; for (int r = 0; r < D; r++) b2 += DG[r * D + i] * DG[r * D + j]; JtJ[i * D + j] = b2; }
+        }
+        bool accepted = false; double stepn = 0;
+        for (int tries = 0; tries < 30 && !accepted; tries++) {
+            double Mx[MAXD * MAXD], st[MAXD];
+            for (int i = 0; i < D * D; i++) Mx[i] = JtJ[i];
+            for (int i = 0; i < D; i++) { Mx[i * D + i] += mu * (JtJ[i * D + i] + 1e-30); st[i] = Jtg[i]; }
+            if (!solve_linear(D, Mx, st)) { mu *= 10; continue; }
+            double xn[MAXN], yn[MAXN], Gn[MAXD], Pxn[MAXD * MAXD], Pyn[MAXD * MAXD];
+            for (int i = 0; i < n; i++) { xn[i] = x[i] - scale * st[i]; yn[i] = y[i] - scale * st[n + i]; }
+            double gnew = residual(xn, yn, Gn, Pxn, Pyn);
+            if (std::isfinite(gnew) && gnew < gn) {
+                stepn = 0; for (int i = 0; i < D; i++) stepn = std::max(stepn, std::fabs(st[i]));
+                for (int i = 0; i < n; i++) { x[i] = xn[i]; y[i] = yn[i]; }
+                for (int r = 0; r < D; r++) G[r] = Gn[r];
+                for (int i = 0; i < D * D; i++) { Px[i] = Pxn[i]; Py[i] = Pyn[i]; }
+                gn = gnew; mu = std::max(mu * 0.2, 1e-12); accepted = true;
+            } else mu *= 5;
+        }
+        if (!accepted) break;                     // noise floor
+        if (gn < 1e-9 && stepn < 1e-9) break;
     }
+    resid = gn;
+    converged = (std::isfinite(gn) && gn < 1e-8) ? 1 : 0;
 
     // ---- assemble the descriptor ----
     std::memset(out, 0, sizeof(*out));

@@ -32,7 +32,7 @@ extern "C" {
 #define CCP_MAX_N      4      /* coupled PDE components n (reference: 2 or 3; 4 = chain extension) */
 #define CCP_MAX_DIM    8      /* 2n: phase-space dimension of the front ODE                          */
 #define CCP_MAX_ORDER  20     /* Taylor order p (reference: order = 20, heteroclinic.cpp:63)         */
-#define CCP_MAX_GRID   16     /* sub-intervals per step (reference: grid = 14, heteroclinic.cpp:66)  */
+#define CCP_MAX_GRID   15     /* sub-intervals per step (reference: grid = 14, heteroclinic.cpp:66)  */
 #define CCP_MAX_CONJ   8      /* recorded conjugate-point time intervals per front                   */
 
 /* closed interval [lo,hi] of doubles (CAPD `interval` restricted to double end points) */
@@ -45,6 +45,7 @@ typedef struct {
     int32_t step_log2;    /* fixed step h = 2^-step_log2 (propagateManifold.cpp:92 `step_size`)         */
     int32_t grid;         /* sub-intervals per step  (frameDet argument `grid`)                          */
     double  L_minus;      /* integration time L_- as an exact double (heteroclinic.cpp:324)             */
+    double  reserved;     /* keeps sizeof(ccp_front_desc) a multiple of 16 (coalesced 16-byte staging)  */
     ccp_interval b[CCP_MAX_N];        /* b_1..b_n  (n=2: a,b)  ODE_functions.cpp:257-273                */
     ccp_interval c[CCP_MAX_N - 1];    /* c_12, c_23, ... chain couplings (n=2: c)                       */
     double  A_u[CCP_MAX_DIM * CCP_MAX_DIM];   /* row-major, leading dim CCP_MAX_DIM: eigenbasis at (0,..,0),
@@ -130,6 +131,10 @@ int ccp_frame_count_series(const ccp_front_desc* front, ccp_front_result* result
 /* kernel launch accounting + last kernel time for bench.py */
 uint64_t ccp_kernel_launches(void);
 float    ccp_last_kernel_ms(void);
+
+/* Unit-test probe: applies primitive `op` of csrc/ccp_interval.cuh element-wise on the device
+   (8 input doubles -> 4 output doubles per element); tests compare with the oracle bit for bit. */
+int ccp_debug_primitives(int op, const double* in, double* out, size_t n);
 
 /* FP64 DFMA-chain peak of the bound device in TFLOP/s (roofline denominator) */
 int ccp_measure_fp64_peak(int iters, double* tflops);

@@ -213,6 +213,8 @@ static inline void run_front(const ccp_front_desc& d, ccp_front_result& res, std
     ival b[MAXN], c[MAXN];
     for (int i = 0; i < n; i++) b[i] = fromc(d.b[i]);
     for (int i = 0; i < n - 1; i++) c[i] = fromc(d.c[i]);
+    const int S = step_count(d.L_minus, h);
+    res.steps = S; res.series_length = S * g;
     Majorant mj = c1_majorant(n, b, c, p, h);
     if (!mj.ok) { res.status = CCP_ST_ENCLOSURE; return; }
 
@@ -226,8 +228,6 @@ static inline void run_front(const ccp_front_desc& d, ccp_front_result& res, std
     }
     for (int j = 0; j < n; j++) for (int k = 0; k < n; k++) Err[j][k] = fromc(d.Eu_err[j * CCP_MAX_N + k]);
 
-    const int S = step_count(d.L_minus, h);
-    res.steps = S; res.series_length = S * g;
     Counter cnt;
     ival tprev(0.0);
     static thread_local PhiTables ct, ht;
@@ -305,6 +305,7 @@ static inline void run_front(const ccp_front_desc& d, ccp_front_result& res, std
             if (idx == S * g - 1) res.det_last = toc(dV);
             if (!(finite(dL) && finite(dR) && finite(dV) && finite(dD))) res.status = CCP_ST_NONFINITE;
         }
+        if (res.status != CCP_OK) break;
         // first-frame data (topFrame::getFirstFrame, topFrame.cpp:301-331)
         if (s == 0) {
             for (int rr = 0; rr < D; rr++) for (int k = 0; k < n; k++) res.first_frame[rr * (CCP_MAX_N + 1) + k] = toc(Ws[rr][k]);

@@ -84,6 +84,39 @@ int orc_mt_dot(const double* xm, const double* xt, const double* ym, const doubl
     out[0] = r.lo; out[1] = r.hi;
     return 0;
 }
+// same op codes as ccp_debug_primitives (csrc/ccp_engine.cu)
+int orc_debug_primitives(int op, const double* in, double* out, size_t n) {
+    RoundUpGuard guard;
+    using namespace c1;
+    for (size_t i = 0; i < n; i++) {
+        const double* x = in + 8 * i; double* o = out + 4 * i;
+        o[0] = o[1] = o[2] = o[3] = 0.0;
+        switch (op) {
+            case 0: o[0] = add_rd(x[0], x[1]); break;
+            case 1: o[0] = add_ru(x[0], x[1]); break;
+            case 2: o[0] = mul_rd(x[0], x[1]); break;
+            case 3: o[0] = mul_ru(x[0], x[1]); break;
+            case 4: o[0] = fma_rd(x[0], x[1], x[2]); break;
+            case 5: o[0] = fma_ru(x[0], x[1], x[2]); break;
+            case 6: o[0] = div_rd(x[0], x[1]); break;
+            case 7: o[0] = div_ru(x[0], x[1]); break;
+            case 10: { ival r = ival(x[0], x[1]) * ival(x[2], x[3]); o[0] = r.lo; o[1] = r.hi; break; }
+            case 11: { mt r = iv2mt(ival(x[0], x[1])); o[0] = r.m; o[1] = r.t; break; }
+            case 12: { ival r = mt2iv(mt{x[0], x[1]}); o[0] = r.lo; o[1] = r.hi; break; }
+            case 13: { acc4 a; acc_term(a, mt{x[0], x[1]}, mt{x[2], x[3]}); acc_term_neg(a, mt{x[4], x[5]}, mt{x[6], x[7]}); ival r = acc_finish(a); o[0] = r.lo; o[1] = r.hi; break; }
+            case 14: { ival r = divk(ival(x[0], x[1]), (int)x[2]); o[0] = r.lo; o[1] = r.hi; break; }
+            case 15: { ival r = horner_rg(ival(x[0], x[1]), x[2], x[3], ival(x[4], x[5])); o[0] = r.lo; o[1] = r.hi; break; }
+            case 16: { ival r = ival(x[0], x[1]) - ival(x[2], x[3]); o[0] = r.lo; o[1] = r.hi; break; }
+            case 17: { ival r = ival(x[0], x[1]) + ival(x[2], x[3]); o[0] = r.lo; o[1] = r.hi; break; }
+            case 18: { ival r = mulk(ival(x[0], x[1]), (int)x[2]); o[0] = r.lo; o[1] = r.hi; break; }
+            case 19: { ival r = horner_pt(ival(x[0], x[1]), x[2], ival(x[4], x[5])); o[0] = r.lo; o[1] = r.hi; break; }
+            case 20: { Frame m; for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) { int q = (a * 3 + b) % 7; m[a][b] = ival(std::min(x[q], x[q + 1]), std::max(x[q], x[q + 1])); }
+                       ival r = detN(m, 3); o[0] = r.lo; o[1] = r.hi; break; }
+            default: return -1;
+        }
+    }
+    return 0;
+}
 int orc_iv2mt(double lo, double hi, double* out) { RoundUpGuard guard; c1::mt m = c1::iv2mt(ival(lo, hi)); out[0] = m.m; out[1] = m.t; return 0; }
 int orc_mt2iv(double m, double t, double* out) { RoundUpGuard guard; ival r = c1::mt2iv(c1::mt{m, t}); out[0] = r.lo; out[1] = r.hi; return 0; }
 int orc_det(const double* lo, const double* hi, int n, double* out) {

@@ -36,7 +36,14 @@ static inline double mul_rd(double a, double b) { return -((-a) * b); }
 static inline double div_ru(double a, double b) { return a / b; }
 static inline double div_rd(double a, double b) { return -((-a) / b); }
 static inline double fma_ru(double a, double b, double c) { return std::fma(a, b, c); }
-static inline double fma_rd(double a, double b, double c) { return -std::fma(-a, b, -c); }
+// The empty asm is an optimisation barrier: without it GCC folds -fma(-a,b,-c) into fma(a,b,c) (one vfmadd)
+// even under -frounding-math, which silently rounds the LOWER bound UP.  Caught by the bit-for-bit
+// comparison with __fma_rd on the GPU (tests/test_gpu_primitives.py).
+static inline double fma_rd(double a, double b, double c) {
+    double t = std::fma(-a, b, -c);
+    __asm__ volatile("" : "+x"(t));
+    return -t;
+}
 static inline double sqrt_ru(double a) { return std::sqrt(a); }
 
 struct ival {

@@ -1,0 +1,61 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN_L_MINUS = 33.84706312634513          # last t_mid + t_rad of the reference's plot_det.txt
+CONFIG1 = [1.0, 0.98, 0.96, 0.04, 0.02]      # heteroclinic.cpp:524-529
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def ge():
+    import __graft_entry__ as g
+    return g
+
+
+@pytest.fixture(scope="session")
+def pkg(ge):
+    p = ge.load_package()
+    if not os.path.exists(p.LIB_PATH):
+        p.build()
+    return p
+
+
+@pytest.fixture(scope="session")
+def orc(ge, pkg):
+    o = ge.load_oracle()
+    o.lib(pkg.abi)
+    return o
+
+
+@pytest.fixture(scope="session")
+def engine(pkg):
+    return pkg.Engine(0)
+
+
+@pytest.fixture(scope="session")
+def config1_desc(pkg):
+    """n=3 reference defaults, L_- pinned to the value recorded in plot_det.txt, decimal-string parameters."""
+    opts = pkg.abi.SetupOpts.default(L_minus_override=GOLDEN_L_MINUS)
+    desc, info = pkg.setup_front(3, CONFIG1, opts)
+    pkg.decimal_params(desc)
+    return desc, info
+
+
+@pytest.fixture(scope="session")
+def config1_ref(pkg, orc, config1_desc):
+    """One full reference-structured oracle run of config 1 (a few seconds, shared by the session)."""
+    return orc.run_front(pkg.abi, config1_desc[0], orc.MODE_REF, series=True, threads=3)
+
+
+@pytest.fixture(scope="session")
+def config1_c1(pkg, orc, config1_desc):
+    return orc.run_front(pkg.abi, config1_desc[0], orc.MODE_C1, series=True)

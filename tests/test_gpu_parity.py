@@ -1,0 +1,209 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Everything goes through the C ABI of libccp_b200.so.
+
+Bar (BASELINE.json north_star): conjugate-point counts and pass/fail exact; every GPU enclosure contains the
+oracle's point values; widths of the pinned quantities within 2x.  Because the kernel performs the same
+directed-rounding operations in the same order as oracle mode c1, GPU == c1 is checked BIT FOR BIT, and
+c1 <-> ref <-> plot_det.txt is checked by tests/test_oracle_golden.py on the CPU.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "plot_det_golden.npz"))
+
+
+def _raw(res):
+    return np.frombuffer(bytes(res), dtype=np.float64)
+
+
+def _same_bits(a, b):
+    return bool(np.all((a == b) | (np.isnan(a) & np.isnan(b))))
+
+
+PRIM_KINDS = {0: 'r', 1: 'r', 2: 'r', 3: 'r', 4: 'r', 5: 'r', 6: 'r', 7: 'r', 10: 'ival', 11: 'ival', 12: 'mt', 13: 'mt',
+              14: 'k', 15: 'horner', 16: 'ival', 17: 'ival', 18: 'k', 19: 'horner', 20: 'r'}
+
+
+def _gen(rng, kind, n):
+    x = rng.standard_normal((n, 8)) * np.exp(rng.uniform(-20, 20, (n, 8)))
+    pairs = {'ival': (0, 2, 4, 6), 'k': (0,), 'horner': (0, 4)}.get(kind, ())
+    for a in pairs:
+        lo, hi = np.minimum(x[:, a], x[:, a + 1]), np.maximum(x[:, a], x[:, a + 1])
+        x[:, a], x[:, a + 1] = lo, hi
+    if kind == 'mt':
+        for a in (0, 2, 4, 6):
+            x[:, a + 1] = np.abs(x[:, a]) * (1 + np.abs(rng.standard_normal(n)) * 1e-10)
+    if kind == 'k':
+        x[:, 2] = rng.integers(1, 21, n)
+    if kind == 'horner':
+        t = np.abs(rng.standard_normal((n, 2))) * 0.03
+        x[:, 2], x[:, 3] = t.min(1), t.max(1)
+    return np.ascontiguousarray(x)
+
+
+def test_interval_primitives_bit_identical_and_exact(engine, orc, pkg):
+    """Device intrinsics vs the oracle's host primitives (bit for bit) and vs exact rational arithmetic."""
+    from fractions import Fraction
+    OL = orc.lib(pkg.abi)
+    OL.orc_debug_primitives.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_size_t]
+    rng = np.random.default_rng(7)
+    n = 20000
+    dp = C.POINTER(C.c_double)
+    for op, kind in PRIM_KINDS.items():
+        x = _gen(rng, kind, n)
+        og, oc = np.zeros((n, 4)), np.zeros((n, 4))
+        assert engine.L.ccp_debug_primitives(op, x.ctypes.data_as(dp), og.ctypes.data_as(dp), n) == 0
+        assert OL.orc_debug_primitives(op, x.ctypes.data_as(dp), oc.ctypes.data_as(dp), n) == 0
+        assert np.array_equal(og, oc), "primitive %d differs between GPU and oracle" % op
+        if op < 8:   # directed rounding is correct: result bounds the exact value and is within 1 ulp of it
+            for i in range(200):
+                a, b, c = (Fraction(float(v)) for v in x[i, :3])
+                exact = {0: a + b, 1: a + b, 2: a * b, 3: a * b, 4: a * b + c, 5: a * b + c, 6: a / b, 7: a / b}[op]
+                r = float(og[i, 0])
+                if op % 2 == 0:
+                    assert Fraction(r) <= exact < Fraction(float(np.nextafter(r, np.inf)))
+                else:
+                    assert Fraction(float(np.nextafter(r, -np.inf))) < exact <= Fraction(r)
+
+
+def test_smoke(ge):
+    ge.smoke()
+
+
+def test_config1_gpu_bit_identical_to_c1_and_pinned_to_reference(engine, pkg, orc, config1_desc, config1_c1, config1_ref):
+    desc, _ = config1_desc
+    res, ser = engine.frame_count_series(desc)
+    cr, cs = config1_c1
+    assert ser.shape == cs.shape == (15176, 10)
+    assert _same_bits(ser, cs), "per-sub-interval series differ from oracle c1"
+    assert _same_bits(_raw(res), _raw(cr)), "result record differs from oracle c1"
+    # counts / pass-fail exact against the reference-structured oracle
+    rr, rs = config1_ref
+    assert (res.status, res.zero_count, res.failure_count, res.steps) == (rr.status, rr.zero_count, rr.failure_count, rr.steps) == (0, 2, 0, 1084)
+    assert [res.conj_index[i] for i in range(res.n_conj)] == [rr.conj_index[i] for i in range(rr.n_conj)] == [10993, 11463]
+    # GPU enclosures contain the oracle's point values; pinned widths within 2x
+    for col in (2, 4, 6, 8):
+        mid = (rs[:, col] + rs[:, col + 1]) / 2
+        assert np.all((mid >= ser[:, col]) & (mid <= ser[:, col + 1]))
+    for col in (6, 8):
+        ratio = (ser[:, col + 1] - ser[:, col]) / (rs[:, col + 1] - rs[:, col])
+        assert 0.5 <= ratio.min() and ratio.max() <= 2.0
+    # and the reference's own recorded enclosures (plot_det.txt)
+    lo, hi = ser[:, 6], ser[:, 7]
+    assert np.all((G["det_mid"] >= lo) & (G["det_mid"] <= hi))
+    ratio = ((hi - lo) / 2) / G["det_rad"]
+    assert ratio.max() <= 2.0
+    assert np.max(np.abs((ser[:, 0] + ser[:, 1]) / 2 - G["t_mid"])) < 1e-11
+
+
+def test_batch_equals_series_path(engine, pkg, config1_desc):
+    desc, _ = config1_desc
+    batch = engine.frame_count_batch((pkg.abi.FrontDesc * 1)(desc))
+    single, _ = engine.frame_count_series(desc)
+    assert _same_bits(_raw(batch[0]), _raw(single))
+
+
+def test_reference_sweep_gpu_bit_identical_to_c1(engine, pkg, orc):
+    """The reference's own 96-point sweep (SampleParameters, heteroclinic.cpp:437-443)."""
+    params = pkg.parameter_list(24, 4)
+    descs, infos = pkg.setup_sweep(3, params)
+    gpu = engine.frame_count_batch(descs)
+    cpu, _ = orc.run_batch(pkg.abi, descs, orc.MODE_C1)
+    a = np.frombuffer(gpu, dtype=np.float64).reshape(96, -1)
+    b = np.frombuffer(cpu, dtype=np.float64).reshape(96, -1)
+    assert _same_bits(a, b)
+    codes = np.array([pkg.frame_det_code(r) for r in gpu])
+    # expected by quadrant of (c12,c23) [float-probe, SURVEY.md 4]: (+,+) 2, (-,+) 1, (-,-) 0, (+,-) 1
+    exp = np.where((params[:, 3] > 0) & (params[:, 4] > 0), 2, np.where((params[:, 3] < 0) & (params[:, 4] < 0), 0, 1))
+    ok = codes >= 0
+    assert ok.sum() >= 90
+    assert np.array_equal(codes[ok], exp[ok])
+
+
+def test_counts_match_reference_structured_oracle_on_sweep_sample(engine, pkg, orc):
+    params = pkg.parameter_list(24, 4)[[0, 13, 30, 47, 63, 70, 88]]
+    descs, _ = pkg.setup_sweep(3, params)
+    gpu = engine.frame_count_batch(descs)
+    ref, _ = orc.run_batch(pkg.abi, descs, orc.MODE_REF)
+    for g, r in zip(gpu, ref):
+        assert pkg.frame_det_code(g) == pkg.frame_det_code(r)            # counts and pass/fail exact
+        if g.failure_count == 0:
+            assert [g.conj_index[i] for i in range(g.n_conj)] == [r.conj_index[i] for i in range(r.n_conj)]
+        for row in range(6):                                             # last frame enclosures of both contain the truth
+            for col in range(5):
+                x, y = g.last_frame[row * 6 + col], r.last_frame[row * 6 + col]
+                assert max(x.lo, y.lo) <= min(x.hi, y.hi)
+                assert x.lo <= 0.5 * (y.lo + y.hi) <= x.hi
+
+
+@pytest.mark.parametrize("n,params,expected", [
+    (2, [1.0, .97, .05], 1), (2, [1.0, .97, -.05], 0),
+    (3, [1.0, .98, .96, .04, -.02], 1), (3, [1.0, .98, .96, -.04, -.02], 0),
+    (4, [1.0, .98, .96, .94, .04, .02, .03], 3),
+])
+def test_other_dimensions_bit_identical(engine, pkg, orc, n, params, expected):
+    desc, _ = pkg.setup_front(n, params)
+    g, gs = engine.frame_count_series(desc)
+    c, cs = orc.run_front(pkg.abi, desc, orc.MODE_C1, series=True)
+    assert _same_bits(gs, cs) and _same_bits(_raw(g), _raw(c))
+    assert (g.status, g.failure_count, g.zero_count) == (0, 0, expected)
+
+
+def test_mixed_batch_and_edge_cases(engine, pkg, orc):
+    abi = pkg.abi
+    d2, _ = pkg.setup_front(2, [1.0, .97, .05], abi.SetupOpts.default(L_minus_override=1.5))
+    d3, _ = pkg.setup_front(3, [1.0, .98, .96, .04, .02], abi.SetupOpts.default(L_minus_override=0.01))   # one partial step
+    d4, _ = pkg.setup_front(4, [1.0, .98, .96, .94, .04, .02, .03], abi.SetupOpts.default(L_minus_override=1.0))
+    bad = abi.FrontDesc.from_buffer_copy(bytes(d3)); bad.grid = 99
+    far = abi.FrontDesc.from_buffer_copy(bytes(d3)); far.L_minus = 2.0
+    for i in range(3):
+        far.p_i[i].lo, far.p_i[i].hi = 3.0, 3.0
+    batch = (abi.FrontDesc * 6)(d3, d2, d4, bad, far, d2)
+    gpu = engine.frame_count_batch(batch)
+    cpu, _ = orc.run_batch(abi, batch, orc.MODE_C1, threads=2)
+    assert [r.status for r in gpu] == [0, 0, 0, abi.CCP_ST_BAD_DESC, abi.CCP_ST_ENCLOSURE, 0]
+    for g, c in zip(gpu, cpu):
+        assert _same_bits(_raw(g), _raw(c))
+    assert (gpu[0].steps, gpu[0].series_length) == (1, 14)
+    assert len(engine.frame_count_batch((abi.FrontDesc * 0)())) == 0          # empty batch
+
+
+def test_device_resident_entry_point_and_determinism(engine, pkg):
+    import torch
+    from ccp_b200 import sweep
+    params = pkg.parameter_list(8, 2)
+    descs, _ = pkg.setup_sweep(3, params, pkg.abi.SetupOpts.default(L_minus_override=4.0))
+    host = engine.frame_count_batch(descs)
+    d_in = sweep.desc_array_to_tensor(descs, device="cuda:0")
+    d_out = torch.zeros(len(descs) * C.sizeof(pkg.abi.FrontResult), dtype=torch.uint8, device="cuda:0")
+    st = torch.cuda.Stream()          # a NULL stream argument means "the engine's own stream"
+    torch.cuda.synchronize()
+    for _ in range(2):
+        d_out.zero_(); torch.cuda.synchronize()
+        engine.frame_count_batch_device(d_in.data_ptr(), len(descs), d_out.data_ptr(), st.cuda_stream)
+        st.synchronize()
+        dev = sweep.tensor_to_results(d_out)
+        assert _same_bits(np.frombuffer(dev, dtype=np.float64), np.frombuffer(host, dtype=np.float64))
+
+
+def test_full_size_sweep_properties(engine, pkg):
+    """BASELINE config 2 (1,024 parameter values): size-independent properties -- sharding invariance
+    (the union of 4 interleaved shards is bit-identical to the single run) and counts by quadrant."""
+    params = pkg.parameter_list(128, 8)
+    descs, infos = pkg.setup_sweep(3, params)
+    full = engine.frame_count_batch(descs)
+    a = np.frombuffer(full, dtype=np.float64).reshape(1024, -1)
+    for rank in range(4):
+        idx = pkg.shard(1024, rank, 4)
+        part = engine.frame_count_batch((pkg.abi.FrontDesc * len(idx))(*[descs[i] for i in idx]))
+        assert _same_bits(np.frombuffer(part, dtype=np.float64).reshape(len(idx), -1), a[idx])
+    codes = np.array([pkg.frame_det_code(r) for r in full])
+    exp = np.where((params[:, 3] > 0) & (params[:, 4] > 0), 2, np.where((params[:, 3] < 0) & (params[:, 4] < 0), 0, 1))
+    ok = codes >= 0
+    assert ok.mean() > 0.9
+    assert np.array_equal(codes[ok], exp[ok])
+    assert all(r.status == 0 for r in full)
