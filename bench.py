@@ -1,0 +1,266 @@
+#!/usr/bin/env python
+"""bench.py -- certified fronts/sec on the bifurcation-diagram parameter sweep.
+
+One "step" = one pass of the hot path (frame propagation + conjugate-point count, the reference's
+E_u.frameDet call, heteroclinic.cpp:334) over this rank's shard of the sweep.  Workload at N GPUs =
+BASELINE.json configs[1] per GPU: the reference's Construct_ParameterList sweep (heteroclinic.cpp:386-427)
+with 128*N angles x 8 radii = 1,024*N parameter values, sharded front_id mod N (weak scaling), one
+NCCL all-gather of the result records per step when N > 1.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--fronts-per-gpu M]
+  (N > 1: launched by torchrun, one rank per GPU)
+
+`--impl reference` times the CPU restatement of the reference's own path (oracle mode "ref"; the reference
+itself needs CAPD and cannot be built here) on the box's host cores.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "certified fronts/sec (param sweep)"
+UNIT = "fronts/s"
+
+
+def sweep_params(pkg, n_total):
+    """Construct_ParameterList with N_c*N_r = n_total (N_r = 8 radii as in config 2 = 128 x 8)."""
+    n_r = 8 if n_total % 8 == 0 else 1
+    return pkg.parameter_list(n_total // n_r, n_r, 0.02, 0.06)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.stop = False
+        self.th = None
+
+    def _run(self):
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.splitlines()[0].split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def __enter__(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.th.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(float(r[1]) for r in self.rows)
+        reasons = []
+        for name, col in (("hw_slowdown", 4), ("hw_thermal_slowdown", 5), ("sw_thermal_slowdown", 6), ("sw_power_cap", 7)):
+            if any(r[col].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][2]), "power_w_max": max(float(r[3]) for r in self.rows),
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def cpu_reference_sample(pkg, orc, n_fronts_total, cores, steps=1, warmup=0):
+    """Times the oracle's reference-structured mode (n separate 4n-dim validated integrations + topFrame) on
+    `cores` fronts taken evenly from the sweep, one front per host thread."""
+    import numpy as np
+    params = sweep_params(pkg, n_fronts_total)
+    take = np.linspace(0, len(params) - 1, cores).round().astype(int)
+    descs, _ = pkg.setup_sweep(3, params[take])
+    times, certified = [], 0
+    for it in range(warmup + steps):
+        res, sec = orc.run_batch(pkg.abi, descs, orc.MODE_REF, threads=cores)
+        if it >= warmup:
+            times.append(sec)
+            certified = sum(1 for r in res if pkg.frame_det_code(r) >= 0)
+    sec = sum(times) / len(times)
+    return {"fronts": int(cores), "certified": int(certified), "seconds": sec, "value": certified / sec, "all_times": times}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--fronts-per-gpu", type=int, default=1024)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    K, W = max(1, args.steps), max(0, args.warmup)
+    n_total = args.fronts_per_gpu * world
+    cores = os.cpu_count() or 1
+
+    import __graft_entry__ as ge
+    pkg = ge.load_package()
+    config = {"workload": "bifurcation-diagram sweep, Construct_ParameterList %dx8 = %d parameter values (BASELINE configs[1] x n_gpus), n=3, b=(1,.975,.95), order 20, step 2^-5, grid 14"
+              % (n_total // 8, n_total), "fronts_per_gpu": args.fronts_per_gpu, "parallelism": "front_id mod %d shards, 1 NCCL all-gather of result records per step" % world if world > 1 else "single GPU",
+              "l2": "256 MiB written between timed steps (untimed); inputs are ~1.2 MB and the kernel is FP64-compute bound"}
+
+    # ------------------------------------------------------------------ reference arm (CPU, rank 0 only)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        orc = ge.load_oracle()
+        s = cpu_reference_sample(pkg, orc, n_total, cores, steps=K, warmup=min(W, 1))
+        line = {"metric": METRIC, "value": s["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": min(W, 1),
+                "ms_per_step": s["seconds"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64 interval (directed rounding)", "data": "synthetic", "impl": "reference", "config": config,
+                "cpu_baseline": {"value": s["value"], "unit": UNIT, "cores": cores, "kind": "port",
+                                 "sample": "%d fronts of the sweep (evenly strided), one per host thread, oracle mode ref; reference binary needs CAPD 5.0.59 (unbuildable here)" % s["fronts"]},
+                "e2e": {"value": s["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm (GPU)
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from ccp_b200 import sweep
+    abi = pkg.abi
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    eng = pkg.Engine(local_rank)
+
+    params = sweep_params(pkg, n_total)
+    mine = sweep.local_indices(n_total, rank, world)
+    descs, infos = pkg.setup_sweep(3, params[mine])
+    m = len(descs)
+    rb, db = C.sizeof(abi.FrontResult), C.sizeof(abi.FrontDesc)
+    d_in = sweep.desc_array_to_tensor(descs, device=dev)
+    d_out = torch.zeros(m * rb, dtype=torch.uint8, device=dev)
+    h_in = sweep.desc_array_to_tensor(descs, pin=True)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.Stream(device=dev)
+    peak = eng.fp64_peak_tflops()
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    gathered = None
+
+    def step():
+        nonlocal gathered
+        with torch.cuda.stream(stream):
+            eng.frame_count_batch_device(d_in.data_ptr(), m, d_out.data_ptr(), stream.cuda_stream)
+            if world > 1:
+                gathered = sweep.gather_records(d_out, n_total, rank, world, rb)
+            else:
+                gathered = d_out
+
+    for _ in range(W):
+        step()
+    barrier()
+    launches0 = eng.kernel_launches()
+    ker_ms, step_ms = [], []
+    with ClockSampler(local_rank) as clocks:
+        for _ in range(K):
+            flush.fill_(1)                       # L2 flush, untimed
+            barrier()
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            with torch.cuda.stream(stream):
+                e0.record(stream)
+                eng.frame_count_batch_device(d_in.data_ptr(), m, d_out.data_ptr(), stream.cuda_stream)
+                e1.record(stream)
+                if world > 1:
+                    gathered = sweep.gather_records(d_out, n_total, rank, world, rb)
+                else:
+                    gathered = d_out
+                e2.record(stream)
+            stream.synchronize()
+            barrier()
+            ker_ms.append(e0.elapsed_time(e1))
+            step_ms.append(e0.elapsed_time(e2))
+    launches = eng.kernel_launches() - launches0
+    t = torch.tensor([sum(step_ms), sum(ker_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, kernel_total_ms = float(t[0]), float(t[1])
+
+    st, zc, fc = sweep.counts_from_records(gathered)
+    certified = int(((st == 0) & (fc == 0)).sum())
+    uncertified = int(n_total - certified)
+    steps_arr = np.frombuffer(gathered.cpu().numpy().tobytes(), dtype=np.int32).reshape(n_total, rb // 4)[:, 4]
+    value = certified * K / (total_ms * 1e-3)
+
+    # ---- end to end through the host-buffer C-ABI call (H2D + kernel + D2H inside), plus the gather when N > 1
+    res_host = (abi.FrontResult * m)()
+    h_ptr = C.cast(h_in.data_ptr(), C.POINTER(abi.FrontDesc))
+
+    def e2e_step():
+        rc = eng.L.ccp_frame_count_batch(h_ptr, m, res_host)
+        assert rc == 0, eng.L.ccp_last_error()
+        if world > 1:
+            loc = torch.frombuffer(res_host, dtype=torch.uint8).to(dev)
+            return sweep.gather_records(loc, n_total, rank, world, rb).cpu()
+        return None
+
+    for _ in range(min(W, 2)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        e2e_step()
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = certified * K / float(e2e_s[0])
+
+    # ---- roofline of the dominant kernel: counted FP64 flop of the implemented algorithm / CUDA-event time
+    flop_local = float(sum(pkg.front_flops(3, 20, 14, int(s)) for s in steps_arr[mine]))
+    achieved = flop_local / (sum(ker_ms) / K * 1e-3) / 1e12
+    roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": "measured live on this GPU: 8 independent DFMA.RM/RP chains per thread (ccp_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry (nominal 37 TF)",
+                "kernel": "ccp::front_kernel<3>", "kernel_ms": sum(ker_ms) / K, "flop_per_launch": flop_local,
+                "note": "FP64 vector-pipe bound: ~1.2 MB in / 1.7 MB out per launch vs ~2e11 flop; DFMA=2 flop, DADD/DMUL=1 (DESIGN.md 5)"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64 interval (directed rounding)", "data": "synthetic", "config": config,
+            "fronts_total": n_total, "certified": certified, "uncertified": uncertified,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": m * db * world, "d2h_bytes_per_step": m * rb * world},
+            "gpu_launches": int(launches), "clocks": clocks.summary(), "roofline": roofline}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        orc = ge.load_oracle()
+        s = cpu_reference_sample(pkg, orc, n_total, cores)
+        line["cpu_baseline"] = {"value": s["value"], "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": "%d fronts of the same sweep (evenly strided), one per host thread, %.1f s wall; oracle mode ref = reference-structured restatement (CAPD absent)" % (s["fronts"], s["seconds"])}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    eng.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

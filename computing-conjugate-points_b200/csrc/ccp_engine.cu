@@ -35,7 +35,7 @@ template <int N> int prepare_kernel() {
     const size_t smem = sizeof(ccp::FrontSmem<N>);
     CK(cudaFuncSetAttribute(ccp::front_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ccp::front_kernel<N>, 32, smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ccp::front_kernel<N>, ccp::NT, smem));
     if (per_sm < 1) { E.err = "kernel does not fit on an SM"; return CCP_E_CUDA; }
     E.grid_limit[N] = per_sm * E.sm_count;
     return 0;
@@ -44,10 +44,10 @@ template <int N> int prepare_kernel() {
 template <int N> int launch(const ccp_front_desc* d_desc, ccp_front_result* d_res, const int* d_index, int count,
                             ccp_series_rec* series, int series_cap, cudaStream_t st) {
     if (count <= 0) return 0;
-    // one warp (= one CTA) per front; the grid is sized to the number of CTAs that are resident at once
+    // one CTA of ccp::NT threads per front; the grid is sized to the number of CTAs that are resident at once
     // (multiple of the SM count) and strides over the batch.
     int grid = count < E.grid_limit[N] ? count : E.grid_limit[N];
-    ccp::front_kernel<N><<<grid, 32, sizeof(ccp::FrontSmem<N>), st>>>(d_desc, d_res, d_index, count, series, series_cap);
+    ccp::front_kernel<N><<<grid, ccp::NT, sizeof(ccp::FrontSmem<N>), st>>>(d_desc, d_res, d_index, count, series, series_cap);
     E.launches++;
     CK(cudaGetLastError());
     return 0;
@@ -127,7 +127,8 @@ __global__ void debug_prim_kernel(int op, const double* in, double* out, int n) 
         case 12: { mt a; a.m = x[0]; a.t = x[1]; ival r = mt2iv(a); o[0] = r.lo; o[1] = r.hi; break; }
         case 13: { acc4 a = acc_zero(); mt p, q; p.m = x[0]; p.t = x[1]; q.m = x[2]; q.t = x[3]; acc_term(a, p, q);
                    p.m = x[4]; p.t = x[5]; q.m = x[6]; q.t = x[7]; acc_term_neg(a, p, q); ival r = acc_finish(a); o[0] = r.lo; o[1] = r.hi; break; }
-        case 14: { ival r = idivk(mk(x[0], x[1]), (int)x[2]); o[0] = r.lo; o[1] = r.hi; break; }
+        case 14: { double il[32], ih[32]; const int k = (int)x[2]; il[k] = __ddiv_rd(1.0, (double)k); ih[k] = __ddiv_ru(1.0, (double)k);
+                   ival r = idivk_tab(mk(x[0], x[1]), il, ih, k); o[0] = r.lo; o[1] = r.hi; break; }
         case 15: { ival r = horner_rg(mk(x[0], x[1]), x[2], x[3], mk(x[4], x[5])); o[0] = r.lo; o[1] = r.hi; break; }
         case 16: { ival r = isub(mk(x[0], x[1]), mk(x[2], x[3])); o[0] = r.lo; o[1] = r.hi; break; }
         case 17: { ival r = iadd(mk(x[0], x[1]), mk(x[2], x[3])); o[0] = r.lo; o[1] = r.hi; break; }
@@ -157,6 +158,14 @@ int ccp_debug_primitives(int op, const double* in, double* out, size_t n) {
     cudaFree(d_in); cudaFree(d_out);
     return 0;
 }
+
+#ifdef CCP_PROFILE
+int ccp_debug_profile(unsigned long long* out, int reset) {
+    if (out) cudaMemcpyFromSymbol(out, ccp::g_prof, sizeof(unsigned long long) * 16);
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(ccp::g_prof, z, sizeof(z)); }
+    return 0;
+}
+#endif
 
 const char* ccp_version(void) { return "ccp_b200 0.1 (sm_100a, c1-structured interval Taylor kernel)"; }
 const char* ccp_last_error(void) { return E.err.c_str(); }

@@ -15,8 +15,8 @@
 
 namespace ccp {
 
-struct ival { double lo, hi; };
-struct mt   { double m, t; };
+struct __align__(16) ival { double lo, hi; };     // 16-byte aligned: one LDS.128 / STS.128 per interval
+struct __align__(16) mt   { double m, t; };
 
 __device__ __forceinline__ double dmin(double a, double b) { return (b < a) ? b : a; }   // same tie/zero behaviour as std::min
 __device__ __forceinline__ double dmax(double a, double b) { return (a < b) ? b : a; }   // same as std::max

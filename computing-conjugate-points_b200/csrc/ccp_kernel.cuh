@@ -14,27 +14,70 @@
 
 namespace ccp {
 
+// Optional per-phase cycle counters (make prof): block 0 adds clock64() deltas into g_prof[phase].
+#ifdef CCP_PROFILE
+__device__ unsigned long long g_prof[16];
+#define PROF_T0() long long prof_t = clock64()
+#define PROF(i) do { long long prof_n = clock64(); if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&g_prof[i], (unsigned long long)(prof_n - prof_t)); prof_t = prof_n; } while (0)
+#else
+#define PROF_T0() do {} while (0)
+#define PROF(i) do {} while (0)
+#endif
+
 constexpr int KMAX = CCP_MAX_ORDER + 1;
 constexpr int GMAX = CCP_MAX_GRID;
+
+// Series index map of the table array T (one row = one Taylor series, KMAX coefficients, 16 B each).
+// Row stride 21*16 B = 84 words => 8 consecutive rows hit 8 disjoint 4-bank groups: LDS.128 conflict-free.
+template <int N> struct Lay {
+    static constexpr int D = 2 * N, NE = N - 1;
+    __host__ __device__ static constexpr int U(int set, int i) { return set * N + i; }
+    __host__ __device__ static constexpr int V(int set, int i) { return 2 * N + set * N + i; }
+    __host__ __device__ static constexpr int G(int set, int i) { return 4 * N + set * N + i; }
+    __host__ __device__ static constexpr int Q(int set, int e) { return 6 * N + set * NE + e; }     // set 0 rows hold z0 (see below)
+    __host__ __device__ static constexpr int MD(int i) { return 6 * N + 2 * NE + i; }
+    __host__ __device__ static constexpr int MO(int e) { return 7 * N + 2 * NE + e; }
+    __host__ __device__ static constexpr int PU(int i, int c) { return 7 * N + 3 * NE + i * D + c; }
+    __host__ __device__ static constexpr int PV(int i, int c) { return 7 * N + 3 * NE + N * D + i * D + c; }
+    __host__ __device__ static constexpr int Z(int set, int i) { return 7 * N + 3 * NE + 2 * N * D + set * N + i; }   // z = 1 - u
+    static constexpr int NS = 9 * N + 3 * NE + 2 * N * D;
+    // w = u - 1/2 differs from u only at order 0: w0 lives in the unused slot G(set,i)[KMAX-1] (g is only needed
+    // to order p-1) and enters the products as a peeled end term.  z = 1 - u has its own rows (z_k = -u_k).
+    static constexpr int NA = 2 * N + NE;             // A tasks: g[set][i] = u*z, q[e] = w_e*w_{e+1} (hull)
+    static constexpr int NB = 2 * (3 * N - 2);        // B tasks: g_i*w_i, g_{i-1}*w_i, g_{i+1}*w_i per set
+    static constexpr int NC = D * (3 * N - 2);        // C tasks: Md_i*Pu_i^c, Mo*Pu_{i+-1}^c
+    static constexpr int NTASK = NA + NB + NC;
+    static constexpr int NPH = (NTASK + 31) / 32 + ((NA + NC) <= 32 && NB > 0 && NTASK <= 32 ? 1 : 0);   // >= 2 always (A before B)
+};
+
+struct Majorant { double rho_phi, rho_phi_d, rho_psi, rho_psi_d; ival Gs_u, Gs_v; bool ok; };
+// parameter interval as sign * [pl, ph] with 0 <= pl <= ph (see imul_par)
+struct SPar { double pl, ph; int neg, straddle; };
 
 template <int N>
 struct FrontSmem {
     static constexpr int D = 2 * N;
     static constexpr int NE = (N > 1) ? (N - 1) : 1;
-    // Taylor tables: [set 0 = centre, 1 = hull]
-    mt u[2][N][KMAX], v[2][N][KMAX], g[2][N][KMAX], q[2][NE][KMAX];
-    mt w0[2][N], z0[2][N];
-    mt Md[N][KMAX], Mo[NE][KMAX];
-    mt Pu[N][D][KMAX], Pv[N][D][KMAX];
+    mt T[Lay<N>::NS][KMAX];                  // Taylor tables; dead rows double as EV / DT buffers in the grid loop
     ival Fk[KMAX][N][N];
     // set state (double buffered)
     double x[2][D], C[2][D][D];
     ival r[2][D], P[2][D][D];
-    ival r0[D], Err[N][N], X[D], y[D], J[D][D], JC[D][D], Ws[D][N], bpar[N], cpar[NE];
+    ival r0[D], Err[N][N], X[D], y[D], J[D][D], Ws[D][N], bpar[N], cpar[NE];
     mt Wm[D][N];
     double rhoF[N], rhoFd[N];
-    ival FD[GMAX][N][N];
-    ccp_front_desc desc;
+    double invlo[KMAX + 2], invhi[KMAX + 2]; // [rd(1/k), ru(1/k)]
+    double gp[GMAX + 1];                     // grid points of the current step (utils.cpp:219-223)
+    ival dtime[GMAX];
+    SPar spb[N], spc[NE];
+    int dec[GMAX];
+    int flag;
+    Majorant mj;
+    union alignas(16) {
+        ival scratch[Lay<N>::NB + Lay<N>::NC + 1];   // table loop: per-task Cauchy sums awaiting combination; last slot = [0,0]
+        ival JC[2 * N][2 * N];               // set update: J*C before its midpoint is split off
+        ccp_front_desc desc;                 // start of the front only
+    } un;
 };
 
 static_assert(sizeof(ccp_front_desc) % 16 == 0, "descriptors are staged with 16-byte loads");
@@ -109,8 +152,6 @@ __device__ __forceinline__ int count_decide(const ival& time, const ival& L, con
     return 2;
 }
 
-struct Majorant { double rho_phi, rho_phi_d, rho_psi, rho_psi_d; ival Gs_u, Gs_v; bool ok; };
-
 // oracle/c1.hpp:c1_majorant -- a-priori box + scalar majorant series (round-up), once per front, all lanes redundantly
 template <int N>
 __device__ inline Majorant majorant(const ival* b, const ival* c, int p, double h) {
@@ -183,322 +224,492 @@ __host__ __device__ inline int step_count(double L_minus, double h) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// One warp = one front.  `series` (optional) receives steps*grid records.
+// Cauchy tasks.  Every Taylor-table product of one order is one "task" = sum_j a(j) b(kk-j) with
+//   a(0) = T[a0r][a0c], a(j) = T[iA][j];   b(0) = T[b0r][b0c], b(m) = +-T[iB][m]  (sign flip for z = 1-u).
+// A CTA of NT = 128 threads owns one front.  Each task is split over a lane pair (j < hsplit, j >= hsplit) and
+// the two accumulators are merged with one shuffle; 64 tasks run per phase:
+//   phase 0: A(k) = g, q of order k   + C(k-1) tasks (Psi products of the previous order)
+//   phase 1: B(k) = g*w products      + remaining C(k-1) tasks            (B needs g[k] from phase 0)
+// then one combine phase turns the sums into the order-(k+1) coefficients of u, v, the order-k coefficients
+// of M and the order-k coefficients of Psi.  Same values as oracle/c1.hpp, which computes them serially.
+// ------------------------------------------------------------------------------------------------
+constexpr int NT = 64;                  // threads per front (one CTA): warp 0 = front tables (phi), warp 1 = variational tables (Psi)
+constexpr int NWARP = NT / 32;
+
+struct Task { short iA, iB, a0r, a0c, b0r, b0c, out; signed char kind, flip; };   // kind: -1 none, 0 A, 1 B, 2 C
+
+// kind 0 (A): lane l < NA of the phi warp;  kind 1 (B): lane l < NB of the phi warp;
+// kind 2 (C): C task index cidx = round*32 + lane of the Psi warp.
+template <int N>
+__device__ inline Task decode_task(int kind, int idx) {
+    using L = Lay<N>;
+    Task t; t.kind = -1; t.iA = t.iB = t.a0r = t.a0c = t.b0r = t.b0c = t.out = 0; t.flip = 0;
+    if (kind == 0) {
+        if (idx >= L::NA) return t;
+        t.kind = 0;
+        if (idx < 2 * N) {                     // g[set][i] = u*z
+            const int set = idx / N, i = idx % N;
+            t.iA = L::U(set, i); t.iB = L::Z(set, i);
+            t.a0r = L::U(set, i); t.a0c = 0; t.b0r = L::Z(set, i); t.b0c = 0;
+            t.out = L::G(set, i);
+        } else {                                // q[e] = w_e*w_{e+1} over the hull
+            const int e = idx - 2 * N;
+            t.iA = L::U(1, e); t.iB = L::U(1, e + 1);
+            t.a0r = L::G(1, e); t.a0c = KMAX - 1; t.b0r = L::G(1, e + 1); t.b0c = KMAX - 1;
+            t.out = L::Q(1, e);
+        }
+        return t;
+    }
+    if (kind == 1) {
+        if (idx >= L::NB) return t;
+        int c = 0;
+        for (int set = 0; set < 2; set++) for (int i = 0; i < N; i++) for (int w = 0; w < 3; w++) {
+            if ((w == 1 && i == 0) || (w == 2 && i == N - 1)) continue;
+            if (c == idx) {
+                const int gi = (w == 0) ? i : (w == 1 ? i - 1 : i + 1);
+                t.kind = 1;
+                t.iA = L::G(set, gi); t.iB = L::U(set, i);
+                t.a0r = L::G(set, gi); t.a0c = 0; t.b0r = L::G(set, i); t.b0c = KMAX - 1;
+                t.out = idx;
+            }
+            c++;
+        }
+        return t;
+    }
+    if (idx < L::NC) {
+        int c = 0;
+        for (int i = 0; i < N; i++) for (int cc = 0; cc < 2 * N; cc++) for (int w = 0; w < 3; w++) {
+            if ((w == 1 && i == 0) || (w == 2 && i == N - 1)) continue;
+            if (c == idx) {
+                t.kind = 2;
+                t.iA = (w == 0) ? L::MD(i) : (w == 1 ? L::MO(i - 1) : L::MO(i));
+                t.iB = (w == 0) ? L::PU(i, cc) : (w == 1 ? L::PU(i - 1, cc) : L::PU(i + 1, cc));
+                t.a0r = t.iA; t.a0c = 0; t.b0r = t.iB; t.b0c = 0;
+                t.out = L::NB + idx;
+            }
+            c++;
+        }
+    }
+    return t;
+}
+template <int N> struct PhaseCheck {
+    using L = Lay<N>;
+    static_assert(L::NA <= 32 && L::NB <= 32, "the phi warp holds one A task and one B task per lane");
+    static constexpr int CROUNDS = (L::NC + 31) / 32;
+    static_assert(CROUNDS <= 3, "Psi warp: at most 3 rounds of C tasks");
+};
+
+__device__ __forceinline__ void bar_pair() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
+
+// Per-thread task registers.  The fields are laundered through an empty asm so that the compiler keeps them
+// in registers instead of re-deriving them from threadIdx with select chains inside the hot loop.
+struct TaskR { int offA, offB, offa0, offb0, out, kind; };
+__device__ __forceinline__ int opaque(int v) { asm volatile("" : "+r"(v)); return v; }
+__device__ __forceinline__ TaskR make_taskr(const Task& t) {
+    TaskR r;
+    r.offA = opaque((int)t.iA * KMAX); r.offB = opaque((int)t.iB * KMAX);
+    r.offa0 = opaque((int)t.a0r * KMAX + t.a0c); r.offb0 = opaque((int)t.b0r * KMAX + t.b0c);
+    r.out = opaque((int)t.out); r.kind = opaque((int)t.kind);
+    return r;
+}
+// One Cauchy sum  sum_{j=0..kk} a(j) b(kk-j),  accumulated in ascending j exactly as oracle/c1.hpp:cauchy.
+// The two end terms (j = 0 uses a(0), j = kk uses b(0)) are peeled so that the interior loop is
+// 2 LDS.128 + 4 DFMA per term with pointer walking.
+__device__ __forceinline__ ival run_task(const mt* __restrict__ Tf, const TaskR& t, int kk) {
+    acc4 a = acc_zero();
+    acc_term(a, Tf[t.offa0], Tf[kk == 0 ? t.offb0 : t.offB + kk]);
+    if (kk >= 1) {
+        const mt* pa = Tf + t.offA + 1;
+        const mt* pb = Tf + t.offB + (kk - 1);
+#pragma unroll 2
+        for (int j = 1; j < kk; j++) { acc_term(a, *pa, *pb); pa++; pb--; }
+        acc_term(a, Tf[t.offA + kk], Tf[t.offb0]);
+    }
+    return acc_finish(a);
+}
+// product with a parameter interval of known sign: c = sg * [pl, ph], 0 <= pl <= ph.  Same end points as imul(a, c).
+__device__ __forceinline__ SPar make_spar(const ival& c) {
+    SPar s; s.straddle = (c.lo < 0 && c.hi > 0) ? 1 : 0; s.neg = (c.hi <= 0 && c.lo < 0) ? 1 : 0;
+    s.pl = s.neg ? -c.hi : c.lo; s.ph = s.neg ? -c.lo : c.hi;
+    return s;
+}
+__device__ __forceinline__ ival imul_pos3(const ival& a, double pl, double ph, int neg) {   // a * (neg ? -[pl,ph] : [pl,ph]), 0 <= pl <= ph
+    const double lo = __dmul_rd(a.lo, a.lo >= 0 ? pl : ph), hi = __dmul_ru(a.hi, a.hi >= 0 ? ph : pl);
+    return neg ? mk(-hi, -lo) : mk(lo, hi);
+}
+__device__ __forceinline__ ival imul_par(const ival& a, const SPar& s, const ival& c) {
+    if (s.straddle) return imul(a, c);
+    const double lo = __dmul_rd(a.lo, a.lo >= 0 ? s.pl : s.ph), hi = __dmul_ru(a.hi, a.hi >= 0 ? s.ph : s.pl);
+    return s.neg ? mk(-hi, -lo) : mk(lo, hi);
+}
+// a / k as a product with [rd(1/k), ru(1/k)]  (oracle/c1.hpp:divk)
+__device__ __forceinline__ ival idivk_tab(const ival& a, const double* ilo, const double* ihi, int k) {
+    return mk(__dmul_rd(a.lo, a.lo >= 0 ? ilo[k] : ihi[k]), __dmul_ru(a.hi, a.hi >= 0 ? ihi[k] : ilo[k]));
+}
+
+// ------------------------------------------------------------------------------------------------
+// One CTA (NT threads) = one front.  `series` (optional) receives steps*grid records.
 // ------------------------------------------------------------------------------------------------
 template <int N>
 __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gdesc, ccp_front_result* __restrict__ gres,
                           ccp_series_rec* __restrict__ series, int series_cap) {
+    using L = Lay<N>;
     constexpr int D = 2 * N;
-    constexpr unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
+    const int tid = threadIdx.x;
+    mt (*T)[KMAX] = S.T;
+    (void)sizeof(PhaseCheck<N>);
 
     // ---- stage the descriptor: coalesced 16-byte loads HBM -> shared ----
     {
         const int4* src = reinterpret_cast<const int4*>(gdesc);
-        int4* dst = reinterpret_cast<int4*>(&S.desc);
-        for (int i = lane; i < (int)(sizeof(ccp_front_desc) / 16); i += 32) dst[i] = src[i];
+        int4* dst = reinterpret_cast<int4*>(&S.un.desc);
+        for (int i = tid; i < (int)(sizeof(ccp_front_desc) / 16); i += NT) dst[i] = src[i];
     }
-    __syncwarp();
-    const ccp_front_desc& d = S.desc;
-    const int p = d.order, g = d.grid;
-    // result header defaults (lane 0 writes at the end)
+    __syncthreads();
+    const int p = S.un.desc.order, g = S.un.desc.grid, step_log2 = S.un.desc.step_log2;
+    const double L_minus = S.un.desc.L_minus;
     int status = CCP_OK;
-    if (d.n != N || p < 2 || p > CCP_MAX_ORDER || g < 1 || g > GMAX || d.step_log2 < 1 || d.step_log2 > 20 || !(d.L_minus > 0) || !isfinite(d.L_minus))
+    if (S.un.desc.n != N || p < 2 || p > CCP_MAX_ORDER || g < 1 || g > GMAX || step_log2 < 1 || step_log2 > 20 || !(L_minus > 0) || !isfinite(L_minus))
         status = CCP_ST_BAD_DESC;
     if (status != CCP_OK) {
-        if (lane == 0) {
+        __syncthreads();
+        if (tid == 0) {
             ccp_front_result z; memset(&z, 0, sizeof(z)); z.status = status; z.first_failure = -1;
             *gres = z;
         }
         return;
     }
-    const double h = ldexp(1.0, -d.step_log2);
-    if (lane < N) S.bpar[lane] = fromc(d.b[lane]);
-    if (lane < N - 1) S.cpar[lane] = fromc(d.c[lane]);
-    if (lane < D) {
-        ival pi = fromc(d.p_i[lane]);
-        double xm = mid_ru(pi);
-        S.x[0][lane] = xm; S.r[0][lane] = isub(pi, pt(xm)); S.r0[lane] = fromc(d.Uxy[lane]);
+    const double h = ldexp(1.0, -step_log2);
+    {
+        const ccp_front_desc& d = S.un.desc;
+        if (tid < N) S.bpar[tid] = fromc(d.b[tid]);
+        if (tid < N - 1) S.cpar[tid] = fromc(d.c[tid]);
+        if (tid < D) {
+            ival pi = fromc(d.p_i[tid]);
+            double xm = mid_ru(pi);
+            S.x[0][tid] = xm; S.r[0][tid] = isub(pi, pt(xm)); S.r0[tid] = fromc(d.Uxy[tid]);
+        }
+        for (int t = tid; t < D * D; t += NT) { int i = t / D, j = t % D; double a = d.A_u[i * CCP_MAX_DIM + j]; S.C[0][i][j] = a; S.P[0][i][j] = pt(a); }
+        for (int t = tid; t < N * N; t += NT) { int j = t / N, k = t % N; S.Err[j][k] = fromc(d.Eu_err[j * CCP_MAX_N + k]); }
+        if (tid >= 32 && tid < 32 + KMAX + 2) { const int k = tid - 32; if (k >= 1) { S.invlo[k] = __ddiv_rd(1.0, (double)k); S.invhi[k] = __ddiv_ru(1.0, (double)k); } else { S.invlo[0] = S.invhi[0] = 0.0; } }
     }
-    for (int t = lane; t < D * D; t += 32) { int i = t / D, j = t % D; double a = d.A_u[i * CCP_MAX_DIM + j]; S.C[0][i][j] = a; S.P[0][i][j] = pt(a); }
-    for (int t = lane; t < N * N; t += 32) { int j = t / N, k = t % N; S.Err[j][k] = fromc(d.Eu_err[j * CCP_MAX_N + k]); }
-    // zero the parts of the result record that are filled piecemeal
-    for (int t = lane; t < (int)(sizeof(ccp_front_result) / 8); t += 32) reinterpret_cast<double*>(gres)[t] = 0.0;
-    __syncwarp();
-    const Majorant mj = majorant<N>(S.bpar, S.cpar, p, h);
+    for (int t = tid; t < (int)(sizeof(ccp_front_result) / 8); t += NT) reinterpret_cast<double*>(gres)[t] = 0.0;
+    __syncthreads();                                // the descriptor (un.desc) is dead from here on
+    if (tid == 0) { S.mj = majorant<N>(S.bpar, S.cpar, p, h); S.flag = 0; }
+    if (tid >= 32 && tid < 32 + N) S.spb[tid - 32] = make_spar(S.bpar[tid - 32]);
+    if (tid >= 48 && tid < 48 + N - 1) S.spc[tid - 48] = make_spar(S.cpar[tid - 48]);
+    __syncthreads();
+    const Majorant mj = S.mj;
     if (!mj.ok) status = CCP_ST_ENCLOSURE;
 
-    const int Stot = step_count(d.L_minus, h);
-    int zero_count = 0, failure_count = 0, first_failure = -1, n_conj = 0;
+    // slot = task handled by this lane pair; consecutive slots go to different warps so that every phase is spread
+    // evenly over the 4 warp schedulers
+    const int wq = tid >> 5, lane = tid & 31;
+    constexpr int CROUNDS = PhaseCheck<N>::CROUNDS;
+    // phi warp: tA, tB = this lane's A and B task;  Psi warp: tA, tB, tC = this lane's C tasks of rounds 0, 1, 2
+    const TaskR tA = make_taskr(decode_task<N>(wq == 0 ? 0 : 2, lane));
+    const TaskR tB = make_taskr(decode_task<N>(wq == 0 ? 1 : 2, wq == 0 ? lane : 32 + lane));
+    const TaskR tC = make_taskr(decode_task<N>(2, (wq == 0 || CROUNDS < 3) ? (1 << 20) : 64 + lane));
+    const mt* const Tf = &T[0][0];
+    const int Stot = step_count(L_minus, h);
+    int zero_count = 0, failure_count = 0, first_failure = -1, n_conj = 0;      // maintained by thread 0
     ival tprev = pt(0.0);
     int cur = 0;
-    ival det_first = pt(0.0), det_last = pt(0.0);
+    ival det_first = pt(0.0), det_last = pt(0.0);                                // thread 0
+    // views of dead table rows used by the grid loop: EV[arg][row][col] frame enclosures, DT[.] determinants
+    ival* const EV = reinterpret_cast<ival*>(&T[L::PU(0, 0)][0]);
+    ival* const DT = reinterpret_cast<ival*>(&T[L::MD(0)][0]);                  // 3*(GMAX+1) intervals << N rows of 21
 
     for (int s = 0; s < Stot && status == CCP_OK; s++) {
+        PROF_T0();
         const bool last = (s == Stot - 1);
-        const double hs = last ? __dadd_ru(d.L_minus, -tprev.hi) : h;
+        const double hs = last ? __dadd_ru(L_minus, -tprev.hi) : h;
         const int nxt = cur ^ 1;
+        // grid points of this step: gp[i] = inf(i*h/grid), gp[grid] = h  (same for every full step)
+        if ((s == 0 || last) && tid >= 32 && tid <= 32 + g) { const int i = tid - 32; S.gp[i] = (i < g) ? __ddiv_rd(__dmul_rd((double)i, hs), (double)g) : hs; }
         // ---- hull of the phi-set ----
-        if (lane < D) {
-            ival a = pt(S.x[cur][lane]);
-            for (int j = 0; j < D; j++) a = iadd(a, imul(pt(S.C[cur][lane][j]), S.r0[j]));
-            S.X[lane] = iadd(a, S.r[cur][lane]);
+        if (tid < D) {
+            ival a = pt(S.x[cur][tid]);
+            for (int j = 0; j < D; j++) a = iadd(a, imul(pt(S.C[cur][tid][j]), S.r0[j]));
+            a = iadd(a, S.r[cur][tid]);
+            S.X[tid] = a;
+            if (!ifinite(a)) atomicOr(&S.flag, 1);
+            else if (!isubset(a, tid < N ? mj.Gs_u : mj.Gs_v)) atomicOr(&S.flag, 2);
         }
-        __syncwarp();
+        __syncthreads();
         {
-            bool inside = true, fin = true;
-            if (lane < D) { inside = isubset(S.X[lane], lane < N ? mj.Gs_u : mj.Gs_v); fin = ifinite(S.X[lane]); }
-            if (!__all_sync(FULL, fin)) { status = CCP_ST_NONFINITE; break; }
-            if (!__all_sync(FULL, inside)) { status = CCP_ST_ENCLOSURE; break; }
+            const int fl = S.flag;
+            if (fl & 1) { status = CCP_ST_NONFINITE; break; }
+            if (fl & 2) { status = CCP_ST_ENCLOSURE; break; }
         }
-        // ---- Taylor tables of phi: set 0 = centre x, set 1 = hull X ----
-        if (lane < 2 * N) {
-            const int set = lane / N, i = lane % N;
+        // ---- order 0 of all tables: set 0 = centre x, set 1 = hull X; Psi = identity ----
+        if (tid < 2 * N) {
+            const int set = tid / N, i = tid % N;
             ival u0 = set ? S.X[i] : pt(S.x[cur][i]);
             ival v0 = set ? S.X[N + i] : pt(S.x[cur][N + i]);
-            S.u[set][i][0] = iv2mt(u0); S.v[set][i][0] = iv2mt(v0);
-            S.w0[set][i] = iv2mt(isub(u0, pt(0.5))); S.z0[set][i] = iv2mt(isub(pt(1.0), u0));
+            T[L::U(set, i)][0] = iv2mt(u0); T[L::V(set, i)][0] = iv2mt(v0);
+            T[L::G(set, i)][KMAX - 1] = iv2mt(isub(u0, pt(0.5)));          // w0
+            T[L::Z(set, i)][0] = iv2mt(isub(pt(1.0), u0));                 // z0
         }
-        // Psi order 0 = identity
-        for (int t = lane; t < N * D; t += 32) {
+        for (int t = tid; t < N * D; t += NT) {
             const int i = t / D, cc = t % D;
-            S.Pu[i][cc][0] = iv2mt(pt(cc == i ? 1.0 : 0.0));
-            S.Pv[i][cc][0] = iv2mt(pt(cc == N + i ? 1.0 : 0.0));
+            T[L::PU(i, cc)][0] = iv2mt(pt(cc == i ? 1.0 : 0.0));
+            T[L::PV(i, cc)][0] = iv2mt(pt(cc == N + i ? 1.0 : 0.0));
         }
-        __syncwarp();
-        for (int k = 0; k < p; k++) {
-            // stage A: g_i[k] = (u*z)[k], q_e[k] = (w_e*w_{e+1})[k]
-            if (lane < 2 * N) {
-                const int set = lane / N, i = lane % N;
-                const mt* uu = S.u[set][i];
-                acc4 a = acc_zero();
-                for (int j = 0; j < k; j++) acc_term_neg(a, uu[j], uu[k - j]);
-                acc_term(a, uu[k], S.z0[set][i]);
-                S.g[set][i][k] = iv2mt(acc_finish(a));
-            } else if (lane < 2 * N + 2 * (N - 1)) {
-                const int t = lane - 2 * N, set = t / (N - 1), e = t % (N - 1);
-                const mt* ua = S.u[set][e]; const mt* ub = S.u[set][e + 1];
-                acc4 a = acc_zero();
-                for (int j = 0; j <= k; j++) acc_term(a, j == 0 ? S.w0[set][e] : ua[j], k - j == 0 ? S.w0[set][e + 1] : ub[k - j]);
-                S.q[set][e][k] = iv2mt(acc_finish(a));
+        __syncthreads();
+        PROF(0);
+        // ---- Taylor tables, order by order.  Warp 0 builds the front tables (centre + hull) of order k while warp 1
+        //      builds the variational tables of order k-1 from the M-series warp 0 finished one iteration earlier;
+        //      the two warps meet once per order (bar.sync 1), everything else is __syncwarp. ----
+        for (int k = 0; k <= p; k++) {
+            if (wq == 0) {
+                if (k < p) {
+                    PROF(12);
+                    if (tA.kind == 0) T[0][tA.out * KMAX + k] = iv2mt(run_task(Tf, tA, k));          // g[k], q[k]
+                    __syncwarp();
+                    PROF(7);
+                    if (tB.kind == 1) S.un.scratch[tB.out] = run_task(Tf, tB, k);                     // g*w products
+                    __syncwarp();
+                    PROF(8);
+                    if (lane < 2 * N) {
+                        const int set = lane / N, i = lane % N;
+                        int b0 = set * (3 * N - 2) + (i == 0 ? 0 : 3 * i - 1);           // first B task of (set,i)
+                        ival f = ineg(imul_par(S.un.scratch[b0], S.spb[i], S.bpar[i])); b0++;
+                        if (i > 0)     { f = isub(f, imul_par(S.un.scratch[b0], S.spc[i - 1], S.cpar[i - 1])); b0++; }
+                        if (i < N - 1) { f = isub(f, imul_par(S.un.scratch[b0], S.spc[i], S.cpar[i])); }
+                        T[L::V(set, i)][k + 1] = iv2mt(idivk_tab(f, S.invlo, S.invhi, k + 1));
+                        const mt un = iv2mt(idivk_tab(mt2iv(T[L::V(set, i)][k]), S.invlo, S.invhi, k + 1));
+                        T[L::U(set, i)][k + 1] = un;
+                        mt zn; zn.m = -un.m; zn.t = un.t;
+                        T[L::Z(set, i)][k + 1] = zn;
+                    }
+                }
+            } else if (k >= 1) {
+                // M-series of order k-1 from the hull g, q the phi warp finished one iteration ago
+                if (lane < N) {
+                    const int i = lane, km = k - 1;
+                    ival t3 = imulk(mt2iv(T[L::G(1, i)][km]), 3);
+                    if (km == 0) t3 = isub(t3, pt(0.5));
+                    ival dd = ineg(imul_par(t3, S.spb[i], S.bpar[i]));
+                    if (i > 0)     dd = isub(dd, imul_par(mt2iv(T[L::G(1, i - 1)][km]), S.spc[i - 1], S.cpar[i - 1]));
+                    if (i < N - 1) dd = isub(dd, imul_par(mt2iv(T[L::G(1, i + 1)][km]), S.spc[i], S.cpar[i]));
+                    T[L::MD(i)][km] = iv2mt(dd);
+                } else if (lane >= 16 && lane < 16 + (N - 1)) {
+                    const int e = lane - 16, km = k - 1;
+                    const ival qe = mt2iv(T[L::Q(1, e)][km]);
+                    T[L::MO(e)][km] = iv2mt(imul_par(mk(2.0 * qe.lo, 2.0 * qe.hi), S.spc[e], S.cpar[e]));
+                }
+                __syncwarp();
+                if (tA.kind == 2) S.un.scratch[tA.out] = run_task(Tf, tA, k - 1);
+                if (tB.kind == 2) S.un.scratch[tB.out] = run_task(Tf, tB, k - 1);
+                if (CROUNDS >= 3 && tC.kind == 2) S.un.scratch[tC.out] = run_task(Tf, tC, k - 1);
+                __syncwarp();
+                for (int e = lane; e < N * D; e += 32) {
+                    const int i = e / D, cc = e % D;
+                    int c0 = L::NB + (i == 0 ? 0 : (3 * i - 1) * D) + cc * ((i == 0 || i == N - 1) ? 2 : 3);   // first C task of (i,cc)
+                    ival sm = S.un.scratch[c0]; c0++;
+                    if (i > 0)     { sm = iadd(sm, S.un.scratch[c0]); c0++; }
+                    if (i < N - 1) { sm = iadd(sm, S.un.scratch[c0]); }
+                    T[L::PV(i, cc)][k] = iv2mt(idivk_tab(sm, S.invlo, S.invhi, k));
+                    T[L::PU(i, cc)][k] = iv2mt(idivk_tab(mt2iv(T[L::PV(i, cc)][k - 1]), S.invlo, S.invhi, k));
+                }
             }
-            __syncwarp();
-            // stage B: v_i[k+1], u_i[k+1]  (lanes 0..2N-1)  and  Md_i[k], Mo_e[k] from the hull (lanes 2N..)
-            if (lane < 2 * N) {
-                const int set = lane / N, i = lane % N;
-                const mt* uu = S.u[set][i]; const mt w0 = S.w0[set][i];
-                acc4 a = acc_zero();
-                { const mt* gg = S.g[set][i]; for (int j = 0; j <= k; j++) acc_term(a, gg[j], k - j == 0 ? w0 : uu[k - j]); }
-                ival f = ineg(imul(S.bpar[i], acc_finish(a)));
-                if (i > 0)     { acc4 a2 = acc_zero(); const mt* gg = S.g[set][i - 1]; for (int j = 0; j <= k; j++) acc_term(a2, gg[j], k - j == 0 ? w0 : uu[k - j]); f = isub(f, imul(S.cpar[i - 1], acc_finish(a2))); }
-                if (i < N - 1) { acc4 a2 = acc_zero(); const mt* gg = S.g[set][i + 1]; for (int j = 0; j <= k; j++) acc_term(a2, gg[j], k - j == 0 ? w0 : uu[k - j]); f = isub(f, imul(S.cpar[i], acc_finish(a2))); }
-                S.v[set][i][k + 1] = iv2mt(idivk(f, k + 1));
-                S.u[set][i][k + 1] = iv2mt(idivk(mt2iv(S.v[set][i][k]), k + 1));
-            } else if (lane < 3 * N) {
-                const int i = lane - 2 * N;
-                ival t3 = imulk(mt2iv(S.g[1][i][k]), 3);
-                if (k == 0) t3 = isub(t3, pt(0.5));
-                ival dd = ineg(imul(S.bpar[i], t3));
-                if (i > 0)     dd = isub(dd, imul(S.cpar[i - 1], mt2iv(S.g[1][i - 1][k])));
-                if (i < N - 1) dd = isub(dd, imul(S.cpar[i], mt2iv(S.g[1][i + 1][k])));
-                S.Md[i][k] = iv2mt(dd);
-            } else if (lane < 3 * N + (N - 1)) {
-                const int e = lane - 3 * N;
-                ival c2 = mk(2.0 * S.cpar[e].lo, 2.0 * S.cpar[e].hi);
-                S.Mo[e][k] = iv2mt(imul(c2, mt2iv(S.q[1][e][k])));
+            PROF(9);
+            bar_pair();
+            PROF(10);
+        }
+        PROF(1);
+        // ---- step image: y = Phi(x) (centre tables), J = DPhi over the hull (Psi tables); frame at step start ----
+        for (int t = tid; t < D + D * D + D * N; t += NT) {
+            if (t < D) {
+                const int i = t % N;
+                S.y[t] = iadd(eval_pt(t < N ? T[L::U(0, i)] : T[L::V(0, i)], p, hs), sym(mj.rho_phi));
+            } else if (t < D + D * D) {
+                const int e = t - D, row = e / D, cc = e % D, i = row % N;
+                S.J[row][cc] = iadd(eval_pt(row < N ? T[L::PU(i, cc)] : T[L::PV(i, cc)], p, hs), sym(mj.rho_psi));
+            } else {
+                const int e = t - D - D * D, cc = e / N, bb = e % N;
+                ival a = S.P[cur][cc][bb];
+                for (int j = 0; j < N; j++) a = iadd(a, imul(S.P[cur][cc][N + j], S.Err[j][bb]));
+                S.Ws[cc][bb] = a; S.Wm[cc][bb] = iv2mt(a);
             }
-            __syncwarp();
-            // stage C: Psi order k+1
-            for (int t = lane; t < N * D; t += 32) {
-                const int i = t / D, cc = t % D;
-                acc4 a = acc_zero();
-                { const mt* mm = S.Md[i]; const mt* pp = S.Pu[i][cc]; for (int j = 0; j <= k; j++) acc_term(a, mm[j], pp[k - j]); }
-                if (i > 0)     { const mt* mm = S.Mo[i - 1]; const mt* pp = S.Pu[i - 1][cc]; for (int j = 0; j <= k; j++) acc_term(a, mm[j], pp[k - j]); }
-                if (i < N - 1) { const mt* mm = S.Mo[i]; const mt* pp = S.Pu[i + 1][cc]; for (int j = 0; j <= k; j++) acc_term(a, mm[j], pp[k - j]); }
-                S.Pv[i][cc][k + 1] = iv2mt(idivk(acc_finish(a), k + 1));
-                S.Pu[i][cc][k + 1] = iv2mt(idivk(mt2iv(S.Pv[i][cc][k]), k + 1));
-            }
-            __syncwarp();
         }
-        // ---- frame at step start, frame tables F_k = Psi^u_k * Ws ----
-        for (int t = lane; t < D * N; t += 32) {
-            const int cc = t / N, bb = t % N;
-            ival a = S.P[cur][cc][bb];
-            for (int j = 0; j < N; j++) a = iadd(a, imul(S.P[cur][cc][N + j], S.Err[j][bb]));
-            S.Ws[cc][bb] = a; S.Wm[cc][bb] = iv2mt(a);
+        __syncthreads();
+        PROF(2);
+        if (tid < N) {
+            double sm = 0; for (int cc = 0; cc < D; cc++) sm = __dadd_ru(sm, imag(S.Ws[cc][tid]));
+            S.rhoF[tid] = __dmul_ru(mj.rho_psi, sm); S.rhoFd[tid] = __dmul_ru(mj.rho_psi_d, sm);
         }
-        __syncwarp();
-        if (lane < N) {
-            double sm = 0; for (int cc = 0; cc < D; cc++) sm = __dadd_ru(sm, imag(S.Ws[cc][lane]));
-            S.rhoF[lane] = __dmul_ru(mj.rho_psi, sm); S.rhoFd[lane] = __dmul_ru(mj.rho_psi_d, sm);
-        }
-        __syncwarp();
-        for (int t = lane; t < (p + 1) * N * N; t += 32) {
+        __syncthreads();
+        // ---- frame tables F_k = Psi^u_k * Ws ----
+        for (int t = tid; t < (p + 1) * N * N; t += NT) {
             const int k = t / (N * N), a = (t / N) % N, bb = t % N;
             acc4 ac = acc_zero();
-            for (int cc = 0; cc < D; cc++) acc_term(ac, S.Pu[a][cc][k], S.Wm[cc][bb]);
+#pragma unroll
+            for (int cc = 0; cc < D; cc++) acc_term(ac, T[L::PU(a, cc)][k], S.Wm[cc][bb]);
             ival f = acc_finish(ac);
             if (k == 0) f = iadd(f, sym(S.rhoF[bb]));
             S.Fk[k][a][bb] = f;
         }
-        __syncwarp();
-        // ---- grid loop + topFrame: lanes 0..g evaluate the frame at the grid points (and its derivative range for
-        //      sub-interval `lane`), lanes 16..16+g-1 the range enclosure, dets and decisions ----
-        {
-            const int gi = lane & 15;                                  // grid index handled by this lane
-            const bool is_point = lane <= g && lane < 16;              // lanes 0..g
-            const bool is_range = lane >= 16 && (lane - 16) < g;       // lanes 16..16+g-1  -> sub-interval gi
-            double tau_lo = 0, tau_hi = 0;
-            if (is_point) { tau_lo = (gi < g) ? __ddiv_rd(__dmul_rd((double)gi, hs), (double)g) : hs; tau_hi = (gi + 1 < g) ? __ddiv_rd(__dmul_rd((double)(gi + 1), hs), (double)g) : hs; }
-            if (is_range) { tau_lo = __ddiv_rd(__dmul_rd((double)gi, hs), (double)g); tau_hi = (gi + 1 < g) ? __ddiv_rd(__dmul_rd((double)(gi + 1), hs), (double)g) : hs; }
-            ival Fm[N][N];
-            ival detP = pt(0.0);
-            if (is_point) {
-#pragma unroll
-                for (int a = 0; a < N; a++)
-#pragma unroll
-                    for (int bb = 0; bb < N; bb++) {
-                        ival acc = S.Fk[p][a][bb];
-                        for (int k = p - 1; k >= 0; k--) acc = horner_pt(acc, tau_lo, S.Fk[k][a][bb]);
-                        Fm[a][bb] = acc;
-                    }
-                detP = Det<N>::det(Fm);
-                if (gi < g) {          // derivative range on sub-interval gi, handed to the range lane through shared memory
-#pragma unroll
-                    for (int a = 0; a < N; a++)
-#pragma unroll
-                        for (int bb = 0; bb < N; bb++) {
-                            ival acc = imulk(S.Fk[p][a][bb], p);
-                            for (int k = p - 1; k >= 1; k--) acc = horner_rg(acc, tau_lo, tau_hi, imulk(S.Fk[k][a][bb], k));
-                            S.FD[gi][a][bb] = iadd(acc, sym(S.rhoFd[bb]));
-                        }
-                }
-            } else if (is_range) {
-#pragma unroll
-                for (int a = 0; a < N; a++)
-#pragma unroll
-                    for (int bb = 0; bb < N; bb++) {
-                        ival acc = S.Fk[p][a][bb];
-                        for (int k = p - 1; k >= 0; k--) acc = horner_rg(acc, tau_lo, tau_hi, S.Fk[k][a][bb]);
-                        Fm[a][bb] = acc;
-                    }
-            }
-            __syncwarp();
-            // det at left / right end of sub-interval gi comes from point lanes gi and gi+1
-            const double dLlo = __shfl_sync(FULL, detP.lo, gi), dLhi = __shfl_sync(FULL, detP.hi, gi);
-            const double dRlo = __shfl_sync(FULL, detP.lo, (gi + 1) & 15), dRhi = __shfl_sync(FULL, detP.hi, (gi + 1) & 15);
-            int decision = 0;
-            ival timeI = pt(0.0), dV = pt(0.0), dD = pt(0.0);
-            if (is_range) {
-                ival FDm[N][N];
-#pragma unroll
-                for (int a = 0; a < N; a++)
-#pragma unroll
-                    for (int bb = 0; bb < N; bb++) FDm[a][bb] = S.FD[gi][a][bb];
-                dV = Det<N>::det(Fm);
-                dD = jacobi_derivative<N>(Fm, FDm);
-                timeI = mk(__dadd_rd(tprev.lo, tau_lo), __dadd_ru(tprev.hi, tau_hi));
-                const ival dL = mk(dLlo, dLhi), dR = mk(dRlo, dRhi);
-                decision = count_decide(timeI, dL, dR, dV, dD);
-                if (!(ifinite(dL) && ifinite(dR) && ifinite(dV) && ifinite(dD))) decision |= 4;
-                const int idx = s * g + gi;
-                if (series != nullptr && idx < series_cap) {
-                    ccp_series_rec rec; rec.time = toc(timeI); rec.det_L = toc(dL); rec.det_R = toc(dR); rec.det_V = toc(dV); rec.det_D = toc(dD);
-                    series[idx] = rec;
-                }
-                if (idx == 0) det_first = dV;
-                if (idx == Stot * g - 1) det_last = dV;
-            }
-            const unsigned zmask = __ballot_sync(FULL, is_range && (decision & 3) == 1);
-            const unsigned fmask = __ballot_sync(FULL, is_range && (decision & 3) == 2);
-            const unsigned nmask = __ballot_sync(FULL, is_range && (decision & 4));
-            if (nmask) status = CCP_ST_NONFINITE;
-            if (fmask && failure_count == 0) first_failure = s * g + (__ffs(fmask) - 1 - 16);
-            failure_count += __popc(fmask);
-            if (zmask) {
-                if (is_range && (decision & 3) == 1) {
-                    const int slot = n_conj + __popc(zmask & ((1u << lane) - 1u));
-                    if (slot < CCP_MAX_CONJ) { gres->conj_time[slot] = toc(timeI); gres->conj_index[slot] = s * g + gi; }
-                }
-                n_conj += __popc(zmask); zero_count += __popc(zmask);
-            }
-            // first / last det range enclosure live on one lane: broadcast
-            det_first.lo = __shfl_sync(FULL, det_first.lo, 16); det_first.hi = __shfl_sync(FULL, det_first.hi, 16);
-            if (last) { det_last.lo = __shfl_sync(FULL, det_last.lo, 16 + g - 1); det_last.hi = __shfl_sync(FULL, det_last.hi, 16 + g - 1); }
-        }
-        // ---- first-frame data (topFrame::getFirstFrame) ----
+        // ---- first / last frame data (topFrame::getFirstFrame / getLastFrame): rare ----
         if (s == 0) {
             const double t0 = 0.0, t1 = (1 < g) ? __ddiv_rd(__dmul_rd(1.0, hs), (double)g) : hs;
-            for (int t = lane; t < D * N; t += 32) { const int rr = t / N, k = t % N; gres->first_frame[rr * (CCP_MAX_N + 1) + k] = toc(S.Ws[rr][k]); }
-            if (lane < N) {
-                ival du = iadd(eval_rg(S.v[1][lane], p, t0, t1), sym(mj.rho_phi));
-                ival dv = iadd(eval_rg_deriv(S.v[1][lane], p, t0, t1), sym(mj.rho_phi_d));
-                gres->first_frame[lane * (CCP_MAX_N + 1) + N] = toc(du);
-                gres->first_frame[(N + lane) * (CCP_MAX_N + 1) + N] = toc(dv);
+            for (int t = tid; t < D * N; t += NT) { const int rr = t / N, k = t % N; gres->first_frame[rr * (CCP_MAX_N + 1) + k] = toc(S.Ws[rr][k]); }
+            if (tid < N) {
+                ival du = iadd(eval_rg(T[L::V(1, tid)], p, t0, t1), sym(mj.rho_phi));
+                ival dv = iadd(eval_rg_deriv(T[L::V(1, tid)], p, t0, t1), sym(mj.rho_phi_d));
+                gres->first_frame[tid * (CCP_MAX_N + 1) + N] = toc(du);
+                gres->first_frame[(N + tid) * (CCP_MAX_N + 1) + N] = toc(dv);
             }
         }
-        // ---- step: y = Phi(x) (centre tables), J = DPhi over the hull (Psi tables) ----
-        for (int t = lane; t < D + D * D; t += 32) {
-            if (t < D) {
-                const int i = t % N;
-                S.y[t] = iadd(eval_pt(t < N ? S.u[0][i] : S.v[0][i], p, hs), sym(mj.rho_phi));
-            } else {
-                const int e = t - D, row = e / D, cc = e % D, i = row % N;
-                S.J[row][cc] = iadd(eval_pt(row < N ? S.Pu[i][cc] : S.Pv[i][cc], p, hs), sym(mj.rho_psi));
-            }
-        }
-        __syncwarp();
-        if (last) {   // topFrame::getLastFrame
+        if (last) {
             constexpr int ld = CCP_MAX_N + 2;
-            for (int t = lane; t < D * N; t += 32) {
+            for (int t = tid; t < D * N; t += NT) {
                 const int rr = t / N, k = t % N;
                 ival a = pt(0.0);
                 for (int cc = 0; cc < D; cc++) a = iadd(a, imul(S.J[rr][cc], S.Ws[cc][k]));
                 gres->last_frame[rr * ld + k] = toc(a);
             }
-            if (lane < N) {
+            if (tid < N) {
                 const double tl = __ddiv_rd(__dmul_rd((double)(g - 1), hs), (double)g);
-                ival du = iadd(eval_rg(S.v[1][lane], p, tl, hs), sym(mj.rho_phi));
-                ival dv = iadd(eval_rg_deriv(S.v[1][lane], p, tl, hs), sym(mj.rho_phi_d));
-                gres->last_frame[lane * ld + N] = toc(du);
-                gres->last_frame[(N + lane) * ld + N] = toc(dv);
+                ival du = iadd(eval_rg(T[L::V(1, tid)], p, tl, hs), sym(mj.rho_phi));
+                ival dv = iadd(eval_rg_deriv(T[L::V(1, tid)], p, tl, hs), sym(mj.rho_phi_d));
+                gres->last_frame[tid * ld + N] = toc(du);
+                gres->last_frame[(N + tid) * ld + N] = toc(dv);
             }
         }
+        __syncthreads();                            // Fk complete; Psi tables and un.scratch are dead from here
+        PROF(3);
+        // ---- grid loop (utils.cpp:219-252): evaluation task = (argument, frame row).  arguments:
+        //      [0, g]        point tau_i                  -> rows of F at the grid points
+        //      [g+1, 2g]     range [tau_i, tau_{i+1}]      -> rows of the range enclosure
+        //      [2g+1, 3g]    derivative over the same range
+        {
+            const int nargs = 3 * g + 1;
+            for (int t = tid; t < nargs * N; t += NT) {
+                const int arg = t / N, a = t % N;
+                const int kind = arg <= g ? 0 : (arg <= 2 * g ? 1 : 2);
+                const int gi = kind == 0 ? arg : (kind == 1 ? arg - (g + 1) : arg - (2 * g + 1));
+                const double tlo = S.gp[gi], thi = S.gp[gi < g ? gi + 1 : g];
+                ival acc[N];
+                if (kind == 0) {
+#pragma unroll
+                    for (int bb = 0; bb < N; bb++) acc[bb] = S.Fk[p][a][bb];
+                    for (int k = p - 1; k >= 0; k--) {
+#pragma unroll
+                        for (int bb = 0; bb < N; bb++) acc[bb] = horner_pt(acc[bb], tlo, S.Fk[k][a][bb]);
+                    }
+                } else if (kind == 1) {
+#pragma unroll
+                    for (int bb = 0; bb < N; bb++) acc[bb] = S.Fk[p][a][bb];
+                    for (int k = p - 1; k >= 0; k--) {
+#pragma unroll
+                        for (int bb = 0; bb < N; bb++) acc[bb] = horner_rg(acc[bb], tlo, thi, S.Fk[k][a][bb]);
+                    }
+                } else {
+#pragma unroll
+                    for (int bb = 0; bb < N; bb++) acc[bb] = imulk(S.Fk[p][a][bb], p);
+                    for (int k = p - 1; k >= 1; k--) {
+#pragma unroll
+                        for (int bb = 0; bb < N; bb++) acc[bb] = horner_rg(acc[bb], tlo, thi, imulk(S.Fk[k][a][bb], k));
+                    }
+#pragma unroll
+                    for (int bb = 0; bb < N; bb++) acc[bb] = iadd(acc[bb], sym(S.rhoFd[bb]));
+                }
+#pragma unroll
+                for (int bb = 0; bb < N; bb++) EV[(arg * N + a) * N + bb] = acc[bb];
+            }
+        }
+        __syncthreads();
+        PROF(4);
+        // ---- determinants (topFrame::constructDetSeries) and Jacobi derivative: one thread each ----
+        for (int t = tid; t < 3 * g + 1; t += NT) {
+            ival Fm[N][N];
+            const int src = (t <= 2 * g) ? t : t - g;            // Jacobi task t in [2g+1,3g] reads range frame (t-g) and derivative frame t
+#pragma unroll
+            for (int a = 0; a < N; a++)
+#pragma unroll
+                for (int bb = 0; bb < N; bb++) Fm[a][bb] = EV[(src * N + a) * N + bb];
+            if (t <= 2 * g) DT[t] = Det<N>::det(Fm);
+            else {
+                ival Dm[N][N];
+#pragma unroll
+                for (int a = 0; a < N; a++)
+#pragma unroll
+                    for (int bb = 0; bb < N; bb++) Dm[a][bb] = EV[(t * N + a) * N + bb];
+                DT[t] = jacobi_derivative<N>(Fm, Dm);
+            }
+        }
+        __syncthreads();
+        // ---- topFrame::countZeros decision per sub-interval (threads 0..g-1), tally by thread 0 ----
+        if (tid < g) {
+            const int gi = tid;
+            const double tl = S.gp[gi], th = S.gp[gi + 1];
+            const ival timeI = mk(__dadd_rd(tprev.lo, tl), __dadd_ru(tprev.hi, th));
+            const ival dL = DT[gi], dR = DT[gi + 1], dV = DT[g + 1 + gi], dD = DT[2 * g + 1 + gi];
+            int decision = count_decide(timeI, dL, dR, dV, dD);
+            if (!(ifinite(dL) && ifinite(dR) && ifinite(dV) && ifinite(dD))) decision |= 4;
+            S.dec[gi] = decision; S.dtime[gi] = timeI;
+            const int idx = s * g + gi;
+            if (series != nullptr && idx < series_cap) {
+                ccp_series_rec rec; rec.time = toc(timeI); rec.det_L = toc(dL); rec.det_R = toc(dR); rec.det_V = toc(dV); rec.det_D = toc(dD);
+                series[idx] = rec;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            for (int gi = 0; gi < g; gi++) {
+                const int dcs = S.dec[gi], idx = s * g + gi;
+                if (dcs & 4) S.flag |= 1;
+                if ((dcs & 3) == 2) { if (failure_count == 0) first_failure = idx; failure_count++; }
+                if ((dcs & 3) == 1) {
+                    if (n_conj < CCP_MAX_CONJ) { gres->conj_time[n_conj] = toc(S.dtime[gi]); gres->conj_index[n_conj] = idx; }
+                    n_conj++; zero_count++;
+                }
+            }
+            if (s == 0) det_first = DT[g + 1];
+            if (last) det_last = DT[2 * g];
+        }
+        PROF(5);
         // ---- set update ----
-        if (lane < D) S.x[nxt][lane] = mid_ru(S.y[lane]);
-        for (int t = lane; t < D * D; t += 32) {
-            const int i = t / D, j = t % D;
-            ival a = pt(0.0);
-            for (int k = 0; k < D; k++) a = iadd(a, imul(S.J[i][k], pt(S.C[cur][k][j])));
-            S.JC[i][j] = a; S.C[nxt][i][j] = mid_ru(a);
+        if (tid < D) S.x[nxt][tid] = mid_ru(S.y[tid]);
+        for (int t = tid; t < 2 * D * D; t += NT) {
+            const int e = t % (D * D), i = e / D, j = e % D;
+            if (t < D * D) {
+                ival a = pt(0.0);
+#pragma unroll
+                for (int k = 0; k < D; k++) a = iadd(a, imul(S.J[i][k], pt(S.C[cur][k][j])));
+                S.un.JC[i][j] = a; S.C[nxt][i][j] = mid_ru(a);
+            } else {
+                ival b = pt(0.0);
+#pragma unroll
+                for (int k = 0; k < D; k++) b = iadd(b, imul(S.J[i][k], S.P[cur][k][j]));
+                S.P[nxt][i][j] = b;
+            }
         }
-        for (int t = lane; t < D * D; t += 32) {
-            const int i = t / D, j = t % D;
-            ival a = pt(0.0);
-            for (int k = 0; k < D; k++) a = iadd(a, imul(S.J[i][k], S.P[cur][k][j]));
-            S.P[nxt][i][j] = a;
-        }
-        __syncwarp();
-        if (lane < D) {
-            const int i = lane;
+        __syncthreads();
+        if (S.flag & 1) status = CCP_ST_NONFINITE;
+        if (tid < D) {
+            const int i = tid;
             ival z = isub(S.y[i], pt(S.x[nxt][i]));
-            for (int j = 0; j < D; j++) z = iadd(z, imul(isub(S.JC[i][j], pt(S.C[nxt][i][j])), S.r0[j]));
+            for (int j = 0; j < D; j++) z = iadd(z, imul(isub(S.un.JC[i][j], pt(S.C[nxt][i][j])), S.r0[j]));
             ival a = pt(0.0);
             for (int j = 0; j < D; j++) a = iadd(a, imul(S.J[i][j], S.r[cur][j]));
             S.r[nxt][i] = iadd(a, z);
         }
-        __syncwarp();
+        __syncthreads();
+        PROF(6);
         tprev = mk(__dadd_rd(tprev.lo, hs), __dadd_ru(tprev.hi, hs));
         cur = nxt;
-        if (last && lane < D) {
+        if (last && status == CCP_OK && tid < D) {
             constexpr int ld = CCP_MAX_N + 2;
-            ival a = pt(S.x[cur][lane]);
-            for (int j = 0; j < D; j++) a = iadd(a, imul(pt(S.C[cur][lane][j]), S.r0[j]));
-            gres->last_frame[lane * ld + N + 1] = toc(iadd(a, S.r[cur][lane]));
+            ival a = pt(S.x[cur][tid]);
+            for (int j = 0; j < D; j++) a = iadd(a, imul(pt(S.C[cur][tid][j]), S.r0[j]));
+            gres->last_frame[tid * ld + N + 1] = toc(iadd(a, S.r[cur][tid]));
         }
     }
-    __syncwarp();
-    if (lane == 0) {
+    __syncthreads();
+    if (tid == 0) {
         gres->status = status; gres->zero_count = zero_count; gres->failure_count = failure_count;
         gres->series_length = Stot * g; gres->steps = Stot; gres->n_conj = n_conj < CCP_MAX_CONJ ? n_conj : CCP_MAX_CONJ;
         gres->first_failure = first_failure; gres->reserved = 0;
@@ -507,14 +718,14 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
 }
 
 template <int N>
-__global__ void __launch_bounds__(32) front_kernel(const ccp_front_desc* __restrict__ descs, ccp_front_result* __restrict__ results,
-                                                   const int* __restrict__ index, int count, ccp_series_rec* series, int series_cap) {
+__global__ void __launch_bounds__(NT, 7) front_kernel(const ccp_front_desc* __restrict__ descs, ccp_front_result* __restrict__ results,
+                                                      const int* __restrict__ index, int count, ccp_series_rec* series, int series_cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FrontSmem<N>& S = *reinterpret_cast<FrontSmem<N>*>(smem_raw);
     for (int w = blockIdx.x; w < count; w += gridDim.x) {
         const int f = index ? index[w] : w;
         run_front<N>(S, descs + f, results + f, series, series_cap);
-        __syncwarp();
+        __syncthreads();
     }
 }
 

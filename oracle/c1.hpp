@@ -51,7 +51,14 @@ static inline ival acc_finish(const acc4& a) {
     return ival(sub_rd(a.slo, R), add_ru(a.shi, R));
 }
 static inline void cauchy(acc4& a, const mt* x, const mt* y, int k) { for (int j = 0; j <= k; j++) acc_term(a, x[j], y[k - j]); }
-static inline ival divk(const ival& a, int k) { return ival(div_rd(a.lo, (double)k), div_ru(a.hi, (double)k)); }
+// a / k for an integer k >= 1, as a product with the enclosure [rd(1/k), ru(1/k)] (no division in the hot loop:
+// a directed FP64 division is a ~100-instruction dependent chain on the GPU).  One ulp wider than a true division.
+struct InvK { double lo[MAXP + 3], hi[MAXP + 3]; InvK() { for (int k = 1; k < MAXP + 3; k++) { lo[k] = div_rd(1.0, (double)k); hi[k] = div_ru(1.0, (double)k); } } };
+static inline ival divk(const ival& a, int k) {
+    static thread_local InvK* inv = nullptr;
+    if (!inv) inv = new InvK();       // built under FE_UPWARD by the calling oracle thread
+    return ival(mul_rd(a.lo, a.lo >= 0 ? inv->lo[k] : inv->hi[k]), mul_ru(a.hi, a.hi >= 0 ? inv->hi[k] : inv->lo[k]));
+}
 static inline ival mulk(const ival& a, int k) { return ival(mul_rd((double)k, a.lo), mul_ru((double)k, a.hi)); }
 
 // Horner steps for tau >= 0
@@ -123,7 +130,7 @@ static inline void phi_tables(PhiTables& t, int n, int p, const ival* b, const i
         t.w0[i] = iv2mt(u0[i] - ival(0.5)); t.z0[i] = iv2mt(ival(1.0) - u0[i]);
     }
     for (int k = 0; k < p; k++) {
-        for (int i = 0; i < n; i++) {                 // g_i[k] = (u*z)[k]
+        for (int i = 0; i < n; i++) {                 // g_i[k] = (u*z)[k], ascending j
             acc4 a;
             for (int j = 0; j < k; j++) acc_term_neg(a, t.u[i][j], t.u[i][k - j]);
             acc_term(a, t.u[i][k], t.z0[i]);
@@ -135,11 +142,14 @@ static inline void phi_tables(PhiTables& t, int n, int p, const ival* b, const i
             t.q[e][k] = iv2mt(acc_finish(a));
         }
         for (int i = 0; i < n; i++) {
-            acc4 a;
-            for (int j = 0; j <= k; j++) acc_term(a, t.g[i][j], k - j == 0 ? t.w0[i] : t.u[i][k - j]);
-            ival f = -(b[i] * acc_finish(a));
-            if (i > 0)     { acc4 a2; for (int j = 0; j <= k; j++) acc_term(a2, t.g[i - 1][j], k - j == 0 ? t.w0[i] : t.u[i][k - j]); f = f - c[i - 1] * acc_finish(a2); }
-            if (i < n - 1) { acc4 a2; for (int j = 0; j <= k; j++) acc_term(a2, t.g[i + 1][j], k - j == 0 ? t.w0[i] : t.u[i][k - j]); f = f - c[i] * acc_finish(a2); }
+            auto gw = [&](int gi) {
+                acc4 a;
+                for (int j = 0; j <= k; j++) acc_term(a, t.g[gi][j], k - j == 0 ? t.w0[i] : t.u[i][k - j]);
+                return acc_finish(a);
+            };
+            ival f = -(gw(i) * b[i]);
+            if (i > 0)     f = f - gw(i - 1) * c[i - 1];
+            if (i < n - 1) f = f - gw(i + 1) * c[i];
             t.v[i][k + 1] = iv2mt(divk(f, k + 1));
             t.u[i][k + 1] = iv2mt(divk(mt2iv(t.v[i][k]), k + 1));
         }
@@ -165,14 +175,14 @@ static inline void psi_tables(PsiTables& s, const PhiTables& hu, int n, int p, c
             if (i > 0)     d = d - c[i - 1] * mt2iv(hu.g[i - 1][k]);
             if (i < n - 1) d = d - c[i] * mt2iv(hu.g[i + 1][k]);
             s.Md[i][k] = iv2mt(d);
-            if (i < n - 1) { ival c2(2.0 * c[i].lo, 2.0 * c[i].hi); s.Mo[i][k] = iv2mt(c2 * mt2iv(hu.q[i][k])); }
+            if (i < n - 1) { ival qe = mt2iv(hu.q[i][k]); s.Mo[i][k] = iv2mt(ival(2.0 * qe.lo, 2.0 * qe.hi) * c[i]); }
         }
         for (int i = 0; i < n; i++) for (int cc = 0; cc < D; cc++) {
-            acc4 a;
-            cauchy(a, s.Md[i], s.Pu[i][cc], k);
-            if (i > 0)     cauchy(a, s.Mo[i - 1], s.Pu[i - 1][cc], k);
-            if (i < n - 1) cauchy(a, s.Mo[i], s.Pu[i + 1][cc], k);
-            s.Pv[i][cc][k + 1] = iv2mt(divk(acc_finish(a), k + 1));
+            acc4 a0; cauchy(a0, s.Md[i], s.Pu[i][cc], k);
+            ival sm = acc_finish(a0);                     // each product is enclosed on its own (one GPU lane each), then summed
+            if (i > 0)     { acc4 a1; cauchy(a1, s.Mo[i - 1], s.Pu[i - 1][cc], k); sm = sm + acc_finish(a1); }
+            if (i < n - 1) { acc4 a2; cauchy(a2, s.Mo[i], s.Pu[i + 1][cc], k); sm = sm + acc_finish(a2); }
+            s.Pv[i][cc][k + 1] = iv2mt(divk(sm, k + 1));
             s.Pu[i][cc][k + 1] = iv2mt(divk(mt2iv(s.Pv[i][cc][k]), k + 1));
         }
     }
@@ -305,7 +315,6 @@ static inline void run_front(const ccp_front_desc& d, ccp_front_result& res, std
             if (idx == S * g - 1) res.det_last = toc(dV);
             if (!(finite(dL) && finite(dR) && finite(dV) && finite(dD))) res.status = CCP_ST_NONFINITE;
         }
-        if (res.status != CCP_OK) break;
         // first-frame data (topFrame::getFirstFrame, topFrame.cpp:301-331)
         if (s == 0) {
             for (int rr = 0; rr < D; rr++) for (int k = 0; k < n; k++) res.first_frame[rr * (CCP_MAX_N + 1) + k] = toc(Ws[rr][k]);
@@ -339,6 +348,7 @@ static inline void run_front(const ccp_front_desc& d, ccp_front_result& res, std
                 res.last_frame[(n + i) * ld + n] = toc(dv);
             }
         }
+        if (res.status != CCP_OK) break;          // non-finite determinant: stop before the set update
         // set update
         double xn[MAXD], Cn[MAXD][MAXD]; ival rn[MAXD], JC[MAXD][MAXD], Pn[MAXD][MAXD];
         for (int i = 0; i < D; i++) xn[i] = mid_ru(y[i]);
