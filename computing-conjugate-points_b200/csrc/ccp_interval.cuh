@@ -33,6 +33,9 @@ __device__ __forceinline__ ival imul(const ival& a, const ival& b) {
     double h = dmax(dmax(__dmul_ru(a.lo, b.lo), __dmul_ru(a.lo, b.hi)), dmax(__dmul_ru(a.hi, b.lo), __dmul_ru(a.hi, b.hi)));
     return mk(l, h);
 }
+// out-of-line copy for the many cold call sites (determinants, set update): keeps the step loop's code small enough
+// for the instruction cache; the arithmetic is identical
+__device__ __noinline__ ival imul_nl(const ival& a, const ival& b) { return imul(a, b); }
 __device__ __forceinline__ ival ihull(const ival& a, const ival& b) { return mk(dmin(a.lo, b.lo), dmax(a.hi, b.hi)); }
 __device__ __forceinline__ double imag(const ival& a) { return dmax(fabs(a.lo), fabs(a.hi)); }
 __device__ __forceinline__ bool idefinite(const ival& a) { return a.lo > 0 || a.hi < 0; }

@@ -87,14 +87,14 @@ static_assert(sizeof(ccp_front_result) % 16 == 0, "result records are 16-byte al
 template <int N> struct Det;
 template <> struct Det<1> { __device__ static __forceinline__ ival det(const ival (&F)[1][1]) { return F[0][0]; } };
 template <> struct Det<2> {
-    __device__ static __forceinline__ ival det(const ival (&F)[2][2]) { return isub(imul(F[0][0], F[1][1]), imul(F[0][1], F[1][0])); }
+    __device__ static __forceinline__ ival det(const ival (&F)[2][2]) { return isub(imul_nl(F[0][0], F[1][1]), imul_nl(F[0][1], F[1][0])); }
 };
-__device__ __forceinline__ ival det2(const ival& a, const ival& b, const ival& c, const ival& d) { return isub(imul(a, d), imul(b, c)); }
+__device__ __forceinline__ ival det2(const ival& a, const ival& b, const ival& c, const ival& d) { return isub(imul_nl(a, d), imul_nl(b, c)); }
 template <> struct Det<3> {
     __device__ static __forceinline__ ival det(const ival (&m)[3][3]) {
-        ival t0 = imul(m[0][0], det2(m[1][1], m[1][2], m[2][1], m[2][2]));
-        ival t1 = imul(m[0][1], det2(m[1][0], m[1][2], m[2][0], m[2][2]));
-        ival t2 = imul(m[0][2], det2(m[1][0], m[1][1], m[2][0], m[2][1]));
+        ival t0 = imul_nl(m[0][0], det2(m[1][1], m[1][2], m[2][1], m[2][2]));
+        ival t1 = imul_nl(m[0][1], det2(m[1][0], m[1][2], m[2][0], m[2][2]));
+        ival t2 = imul_nl(m[0][2], det2(m[1][0], m[1][1], m[2][0], m[2][1]));
         return iadd(isub(t0, t1), t2);
     }
 };
@@ -109,10 +109,10 @@ __device__ __forceinline__ ival minor_det(const ival (&F)[N][N], int ih, int jh)
 }
 template <> struct Det<4> {
     __device__ static __forceinline__ ival det(const ival (&F)[4][4]) {
-        ival acc = imul(F[0][0], minor_det<4>(F, 0, 0));
+        ival acc = imul_nl(F[0][0], minor_det<4>(F, 0, 0));
 #pragma unroll
         for (int j = 1; j < 4; j++) {
-            ival term = imul(F[0][j], minor_det<4>(F, 0, j));
+            ival term = imul_nl(F[0][j], minor_det<4>(F, 0, j));
             acc = (j & 1) ? isub(acc, term) : iadd(acc, term);
         }
         return acc;
@@ -128,7 +128,7 @@ __device__ __forceinline__ ival jacobi_derivative(const ival (&A)[N][N], const i
         for (int j = 0; j < N; j++) {
             ival cof = minor_det<N>(A, j, i);
             if ((i + j) & 1) cof = ineg(cof);
-            diag = iadd(diag, imul(cof, Ad[j][i]));
+            diag = iadd(diag, imul_nl(cof, Ad[j][i]));
         }
         tr = iadd(tr, diag);
     }
@@ -137,12 +137,12 @@ __device__ __forceinline__ ival jacobi_derivative(const ival (&A)[N][N], const i
 
 // decision of topFrame::countZeros for one sub-interval: 0 = certified no zero, 1 = certified zero, 2 = failure
 __device__ __forceinline__ int count_decide(const ival& time, const ival& L, const ival& R, const ival& V, const ival& Dv) {
-    ival LR = imul(L, R);
+    ival LR = imul_nl(L, R);
     if (LR.lo > 0) {
         if (idefinite(V)) return 0;
         if (idefinite(Dv)) return 0;
         ival w = isub(time, pt(time.lo));
-        ival mvt = imul(w, Dv);
+        ival mvt = imul_nl(w, Dv);
         ival half = mk(mvt.lo * 0.5, mvt.hi * 0.5);
         ival bound = ihull(iadd(L, half), isub(R, half));
         return idefinite(bound) ? 0 : 2;
@@ -294,7 +294,7 @@ __device__ inline Task decode_task(int kind, int idx) {
 }
 template <int N> struct PhaseCheck {
     using L = Lay<N>;
-    static_assert(L::NA <= 32 && L::NB <= 32, "the phi warp holds one A task and one B task per lane");
+    static_assert(L::NA + L::NB <= 32, "the phi warp holds the A tasks and the B tasks side by side");
     static constexpr int CROUNDS = (L::NC + 31) / 32;
     static_assert(CROUNDS <= 3, "Psi warp: at most 3 rounds of C tasks");
 };
@@ -327,7 +327,20 @@ __device__ __forceinline__ ival run_task(const mt* __restrict__ Tf, const TaskR&
     }
     return acc_finish(a);
 }
-// product with a parameter interval of known sign: c = sg * [pl, ph], 0 <= pl <= ph.  Same end points as imul(a, c).
+// terms j = 0 .. upto-1 of the same sum (upto <= kk: the last term, which needs the newest a(kk), is added later)
+__device__ __forceinline__ acc4 run_partial(const mt* __restrict__ Tf, const TaskR& t, int kk, int upto) {
+    acc4 a = acc_zero();
+    if (upto <= 0) return a;
+    acc_term(a, Tf[t.offa0], Tf[kk == 0 ? t.offb0 : t.offB + kk]);
+    const mt* pa = Tf + t.offA + 1;
+    const mt* pb = Tf + t.offB + (kk - 1);
+    const int jend = upto < kk ? upto : kk;
+#pragma unroll 2
+    for (int j = 1; j < jend; j++) { acc_term(a, *pa, *pb); pa++; pb--; }
+    if (upto == kk + 1 && kk >= 1) acc_term(a, Tf[t.offA + kk], Tf[t.offb0]);
+    return a;
+}
+// product with a parameter interval of known sign: c = sg * [pl, ph], 0 <= pl <= ph.  Same end points as imul_nl(a, c).
 __device__ __forceinline__ SPar make_spar(const ival& c) {
     SPar s; s.straddle = (c.lo < 0 && c.hi > 0) ? 1 : 0; s.neg = (c.hi <= 0 && c.lo < 0) ? 1 : 0;
     s.pl = s.neg ? -c.hi : c.lo; s.ph = s.neg ? -c.lo : c.hi;
@@ -338,7 +351,7 @@ __device__ __forceinline__ ival imul_pos3(const ival& a, double pl, double ph, i
     return neg ? mk(-hi, -lo) : mk(lo, hi);
 }
 __device__ __forceinline__ ival imul_par(const ival& a, const SPar& s, const ival& c) {
-    if (s.straddle) return imul(a, c);
+    if (s.straddle) return imul_nl(a, c);
     const double lo = __dmul_rd(a.lo, a.lo >= 0 ? s.pl : s.ph), hi = __dmul_ru(a.hi, a.hi >= 0 ? s.ph : s.pl);
     return s.neg ? mk(-hi, -lo) : mk(lo, hi);
 }
@@ -407,8 +420,8 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
     const int wq = tid >> 5, lane = tid & 31;
     constexpr int CROUNDS = PhaseCheck<N>::CROUNDS;
     // phi warp: tA, tB = this lane's A and B task;  Psi warp: tA, tB, tC = this lane's C tasks of rounds 0, 1, 2
-    const TaskR tA = make_taskr(decode_task<N>(wq == 0 ? 0 : 2, lane));
-    const TaskR tB = make_taskr(decode_task<N>(wq == 0 ? 1 : 2, wq == 0 ? lane : 32 + lane));
+    const TaskR tA = make_taskr(wq == 0 ? (lane < L::NA ? decode_task<N>(0, lane) : decode_task<N>(1, lane - L::NA)) : decode_task<N>(2, lane));
+    const TaskR tB = make_taskr(decode_task<N>(2, wq == 0 ? (1 << 20) : 32 + lane));
     const TaskR tC = make_taskr(decode_task<N>(2, (wq == 0 || CROUNDS < 3) ? (1 << 20) : 64 + lane));
     const mt* const Tf = &T[0][0];
     const int Stot = step_count(L_minus, h);
@@ -430,7 +443,7 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
         // ---- hull of the phi-set ----
         if (tid < D) {
             ival a = pt(S.x[cur][tid]);
-            for (int j = 0; j < D; j++) a = iadd(a, imul(pt(S.C[cur][tid][j]), S.r0[j]));
+            for (int j = 0; j < D; j++) a = iadd(a, imul_nl(pt(S.C[cur][tid][j]), S.r0[j]));
             a = iadd(a, S.r[cur][tid]);
             S.X[tid] = a;
             if (!ifinite(a)) atomicOr(&S.flag, 1);
@@ -465,10 +478,16 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
             if (wq == 0) {
                 if (k < p) {
                     PROF(12);
-                    if (tA.kind == 0) T[0][tA.out * KMAX + k] = iv2mt(run_task(Tf, tA, k));          // g[k], q[k]
+                    // one pass for both task kinds: A lanes sum all k+1 terms, B lanes the first k terms (their last
+                    // term g[k]*w0 needs the g[k] the A lanes are producing right now)
+                    acc4 acc = run_partial(Tf, tA, k, tA.kind == 0 ? k + 1 : (tA.kind == 1 ? k : 0));
+                    if (tA.kind == 0) T[0][tA.out * KMAX + k] = iv2mt(acc_finish(acc));               // g[k], q[k]
                     __syncwarp();
                     PROF(7);
-                    if (tB.kind == 1) S.un.scratch[tB.out] = run_task(Tf, tB, k);                     // g*w products
+                    if (tA.kind == 1) {
+                        if (k == 0) acc_term(acc, Tf[tA.offa0], Tf[tA.offb0]); else acc_term(acc, Tf[tA.offA + k], Tf[tA.offb0]);
+                        S.un.scratch[tA.out] = acc_finish(acc);                                        // g*w products
+                    }
                     __syncwarp();
                     PROF(8);
                     if (lane < 2 * N) {
@@ -530,7 +549,7 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
             } else {
                 const int e = t - D - D * D, cc = e / N, bb = e % N;
                 ival a = S.P[cur][cc][bb];
-                for (int j = 0; j < N; j++) a = iadd(a, imul(S.P[cur][cc][N + j], S.Err[j][bb]));
+                for (int j = 0; j < N; j++) a = iadd(a, imul_nl(S.P[cur][cc][N + j], S.Err[j][bb]));
                 S.Ws[cc][bb] = a; S.Wm[cc][bb] = iv2mt(a);
             }
         }
@@ -567,7 +586,7 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
             for (int t = tid; t < D * N; t += NT) {
                 const int rr = t / N, k = t % N;
                 ival a = pt(0.0);
-                for (int cc = 0; cc < D; cc++) a = iadd(a, imul(S.J[rr][cc], S.Ws[cc][k]));
+                for (int cc = 0; cc < D; cc++) a = iadd(a, imul_nl(S.J[rr][cc], S.Ws[cc][k]));
                 gres->last_frame[rr * ld + k] = toc(a);
             }
             if (tid < N) {
@@ -678,12 +697,12 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
             if (t < D * D) {
                 ival a = pt(0.0);
 #pragma unroll
-                for (int k = 0; k < D; k++) a = iadd(a, imul(S.J[i][k], pt(S.C[cur][k][j])));
+                for (int k = 0; k < D; k++) a = iadd(a, imul_nl(S.J[i][k], pt(S.C[cur][k][j])));
                 S.un.JC[i][j] = a; S.C[nxt][i][j] = mid_ru(a);
             } else {
                 ival b = pt(0.0);
 #pragma unroll
-                for (int k = 0; k < D; k++) b = iadd(b, imul(S.J[i][k], S.P[cur][k][j]));
+                for (int k = 0; k < D; k++) b = iadd(b, imul_nl(S.J[i][k], S.P[cur][k][j]));
                 S.P[nxt][i][j] = b;
             }
         }
@@ -692,9 +711,9 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
         if (tid < D) {
             const int i = tid;
             ival z = isub(S.y[i], pt(S.x[nxt][i]));
-            for (int j = 0; j < D; j++) z = iadd(z, imul(isub(S.un.JC[i][j], pt(S.C[nxt][i][j])), S.r0[j]));
+            for (int j = 0; j < D; j++) z = iadd(z, imul_nl(isub(S.un.JC[i][j], pt(S.C[nxt][i][j])), S.r0[j]));
             ival a = pt(0.0);
-            for (int j = 0; j < D; j++) a = iadd(a, imul(S.J[i][j], S.r[cur][j]));
+            for (int j = 0; j < D; j++) a = iadd(a, imul_nl(S.J[i][j], S.r[cur][j]));
             S.r[nxt][i] = iadd(a, z);
         }
         __syncthreads();
@@ -704,7 +723,7 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
         if (last && status == CCP_OK && tid < D) {
             constexpr int ld = CCP_MAX_N + 2;
             ival a = pt(S.x[cur][tid]);
-            for (int j = 0; j < D; j++) a = iadd(a, imul(pt(S.C[cur][tid][j]), S.r0[j]));
+            for (int j = 0; j < D; j++) a = iadd(a, imul_nl(pt(S.C[cur][tid][j]), S.r0[j]));
             gres->last_frame[tid * ld + N + 1] = toc(iadd(a, S.r[cur][tid]));
         }
     }

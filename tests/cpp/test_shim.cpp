@@ -1,0 +1,31 @@
+// Exercises the C++ host shim the way the reference's driver would (heteroclinic.cpp:299-334):
+// build propagateManifold, call frameDet, read countZeros / getLastFrame.  Exit code 0 = ok, 77 = no GPU.
+#include "../../computing-conjugate-points_b200/host/ccp_frame_det.hpp"
+#include <cmath>
+#include <cstdio>
+using namespace ccp_host;
+int main() {
+    if (ccp_device_count() <= 0) { std::printf("no GPU: shim compiled and linked only\n"); return 77; }
+    if (ccp_init(0) != 0) { std::printf("init failed: %s\n", ccp_last_error()); return 1; }
+    double params[5] = {1.0, 0.98, 0.96, 0.04, 0.02};
+    ccp_front_desc d; ccp_setup_info info;
+    ccp_setup_opts o{}; o.xy_nbd = -1; o.cone_L = -1; o.eig_err = -1; o.scale = -1; o.L_minus_percent = -1; o.L_minus_override = -1;
+    if (ccp_setup_front(3, params, &o, &d, &info) != 0) return 2;
+    const int n = 3;
+    IVector par(5), p_i(6), Uxy(6); DMatrix A(6, std::vector<double>(6)); IMatrix E(3, IVector(3));
+    for (int i = 0; i < 3; i++) par[i] = from_c(d.b[i]);
+    for (int i = 0; i < 2; i++) par[3 + i] = from_c(d.c[i]);
+    for (int i = 0; i < 6; i++) { p_i[i] = from_c(d.p_i[i]); Uxy[i] = from_c(d.Uxy[i]); for (int j = 0; j < 6; j++) A[i][j] = d.A_u[i * CCP_MAX_DIM + j]; }
+    for (int j = 0; j < 3; j++) for (int k = 0; k < 3; k++) E[j][k] = from_c(d.Eu_err[j * CCP_MAX_N + k]);
+    propagateManifold E_u(n, par, A, p_i, Uxy, E, /*order*/ 20, /*stepsize*/ 5);
+    E_u.plotting(false);
+    int unstable_e_values = E_u.frameDet(interval(info.L_minus), /*grid*/ 14, IVector(6));
+    std::printf("frameDet = %d, last frame U(0,0) in [%.6e, %.6e]\n", unstable_e_values, E_u.frame().getLastFrame()[0][0].lo, E_u.frame().getLastFrame()[0][0].hi);
+    if (unstable_e_values != 2) return 3;
+    E_u.L_plus = [](const topFrame&, const IVector&) { return false; };
+    if (E_u.frameDet(interval(info.L_minus), 14, IVector(6)) != -4) return 4;
+    E_u.below_Lminus = [] { return false; };
+    if (E_u.frameDet(interval(info.L_minus), 14, IVector(6)) != -5) return 5;
+    ccp_shutdown();
+    return 0;
+}

@@ -1,0 +1,30 @@
+"""The C++ host shim (reference entry-point names above the C ABI) builds and links; on a GPU it runs the
+reference's single-front flow (heteroclinic.cpp:299-334) and returns the reference's codes."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "tests", "cpp", "test_shim")
+
+
+def _build(pkg):
+    cmd = ["g++", "-std=c++17", "-O1", "-o", EXE, os.path.join(ROOT, "tests", "cpp", "test_shim.cpp"),
+           "-L", pkg.PKG_DIR, "-lccp_b200", "-Wl,-rpath," + pkg.PKG_DIR]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_shim_compiles_and_links(pkg):
+    _build(pkg)
+    r = subprocess.run([EXE], capture_output=True, text=True)
+    assert r.returncode in (0, 77), r.stdout + r.stderr       # 77 = no GPU: there is no CPU fallback to run
+
+
+@pytest.mark.gpu
+def test_shim_runs_frameDet_on_gpu(pkg):
+    _build(pkg)
+    r = subprocess.run([EXE], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "frameDet = 2" in r.stdout
