@@ -327,6 +327,23 @@ __device__ __forceinline__ ival run_task(const mt* __restrict__ Tf, const TaskR&
     }
     return acc_finish(a);
 }
+// Two sums of the same order in one loop (Psi warp, rounds 0 and 1): 8 independent FMA chains per lane hide the
+// LDS / DFMA latency that a single 4-chain sum exposes.  Each sum is accumulated exactly as in run_task.
+__device__ __forceinline__ void run_task2(const mt* __restrict__ Tf, const TaskR& t0, const TaskR& t1, bool on1, int kk, ival& r0, ival& r1) {
+    acc4 a = acc_zero(), b = acc_zero();
+    acc_term(a, Tf[t0.offa0], Tf[kk == 0 ? t0.offb0 : t0.offB + kk]);
+    acc_term(b, Tf[t1.offa0], Tf[kk == 0 ? t1.offb0 : t1.offB + kk]);
+    if (kk >= 1) {
+        const mt* pa = Tf + t0.offA + 1; const mt* pb = Tf + t0.offB + (kk - 1);
+        const mt* qa = Tf + t1.offA + 1; const mt* qb = Tf + t1.offB + (kk - 1);
+#pragma unroll 2
+        for (int j = 1; j < kk; j++) { acc_term(a, *pa, *pb); acc_term(b, *qa, *qb); pa++; pb--; qa++; qb--; }
+        acc_term(a, Tf[t0.offA + kk], Tf[t0.offb0]);
+        acc_term(b, Tf[t1.offA + kk], Tf[t1.offb0]);
+    }
+    r0 = acc_finish(a); r1 = acc_finish(b);
+    (void)on1;
+}
 // terms j = 0 .. upto-1 of the same sum (upto <= kk: the last term, which needs the newest a(kk), is added later)
 __device__ __forceinline__ acc4 run_partial(const mt* __restrict__ Tf, const TaskR& t, int kk, int upto) {
     acc4 a = acc_zero();
@@ -519,8 +536,14 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
                     T[L::MO(e)][km] = iv2mt(imul_par(mk(2.0 * qe.lo, 2.0 * qe.hi), S.spc[e], S.cpar[e]));
                 }
                 __syncwarp();
-                if (tA.kind == 2) S.un.scratch[tA.out] = run_task(Tf, tA, k - 1);
-                if (tB.kind == 2) S.un.scratch[tB.out] = run_task(Tf, tB, k - 1);
+                {   // rounds 0 and 1 of the C tasks, fused; lanes without a round-1 task redo their round-0 task (discarded)
+                    ival r0, r1;
+                    if (tA.kind == 2) {
+                        run_task2(Tf, tA, tB.kind == 2 ? tB : tA, tB.kind == 2, k - 1, r0, r1);
+                        S.un.scratch[tA.out] = r0;
+                        if (tB.kind == 2) S.un.scratch[tB.out] = r1;
+                    }
+                }
                 if (CROUNDS >= 3 && tC.kind == 2) S.un.scratch[tC.out] = run_task(Tf, tC, k - 1);
                 __syncwarp();
                 for (int e = lane; e < N * D; e += 32) {

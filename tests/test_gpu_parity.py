@@ -207,3 +207,37 @@ def test_full_size_sweep_properties(engine, pkg):
     assert ok.mean() > 0.9
     assert np.array_equal(codes[ok], exp[ok])
     assert all(r.status == 0 for r in full)
+
+
+def test_config4_subboxes(engine, pkg, orc):
+    """BASELINE config 4 (reduced: 4^3 = 64 sub-boxes of the eigenfunction-error box of one front, part() rule of
+    utils.cpp:3-10): every sub-box is propagated and counted independently; all tallies agree, every sub-box result is
+    bit-identical to the oracle, and the hull of the sub-box enclosures lies inside the undivided enclosure."""
+    desc, _ = pkg.setup_front(3, [1.0, .98, .96, .04, .02], pkg.abi.SetupOpts.default(L_minus_override=26.0))
+    subs = pkg.subdivide_front(desc, 4)
+    gpu = engine.frame_count_batch(subs)
+    cpu, _ = orc.run_batch(pkg.abi, subs, orc.MODE_C1)
+    a = np.frombuffer(gpu, dtype=np.float64).reshape(len(subs), -1)
+    b = np.frombuffer(cpu, dtype=np.float64).reshape(len(subs), -1)
+    assert _same_bits(a, b)
+    whole = engine.frame_count_batch((pkg.abi.FrontDesc * 1)(desc))[0]
+    assert {(r.status, r.zero_count, r.failure_count) for r in gpu} == {(0, whole.zero_count, 0)} == {(0, 2, 0)}
+    for row in range(6):
+        for col in range(3):
+            lo = min(r.last_frame[row * 6 + col].lo for r in gpu)
+            hi = max(r.last_frame[row * 6 + col].hi for r in gpu)
+            w = whole.last_frame[row * 6 + col]
+            tol = 1e-9 * max(abs(w.lo), abs(w.hi))
+            assert w.lo - tol <= lo and hi <= w.hi + tol
+
+
+def test_config5_n4_throughput_path(engine, pkg, orc):
+    """BASELINE config 5: the n=4 chain (8x4 frames, d=16) through the batched entry point, against the oracle."""
+    params = [[1.0, .98, .96, .94, .04, .02, .03], [1.0, .98, .96, .94, .04, -.02, .03], [1.0, .97, .95, .93, -.03, .02, .04]]
+    descs, infos = pkg.setup_sweep(4, np.array(params))
+    assert all(i.converged == 1 for i in infos)
+    gpu = engine.frame_count_batch(descs)
+    cpu, _ = orc.run_batch(pkg.abi, descs, orc.MODE_C1)
+    assert _same_bits(np.frombuffer(gpu, dtype=np.float64), np.frombuffer(cpu, dtype=np.float64))
+    assert [r.status for r in gpu] == [0, 0, 0]
+    assert gpu[0].zero_count == 3 and gpu[0].failure_count == 0
