@@ -627,9 +627,10 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
         //      [g+1, 2g]     range [tau_i, tau_{i+1}]      -> rows of the range enclosure
         //      [2g+1, 3g]    derivative over the same range
         {
-            const int nargs = 3 * g + 1;
+            // argument 0 (tau = 0) needs no Horner pass: F(0) = F_0 exactly, read straight from Fk[0] below
+            const int nargs = 3 * g;
             for (int t = tid; t < nargs * N; t += NT) {
-                const int arg = t / N, a = t % N;
+                const int arg = 1 + t / N, a = t % N;
                 const int kind = arg <= g ? 0 : (arg <= 2 * g ? 1 : 2);
                 const int gi = kind == 0 ? arg : (kind == 1 ? arg - (g + 1) : arg - (2 * g + 1));
                 const double tlo = S.gp[gi], thi = S.gp[gi < g ? gi + 1 : g];
@@ -664,31 +665,34 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
         }
         __syncthreads();
         PROF(4);
-        // ---- determinants (topFrame::constructDetSeries) and Jacobi derivative: one thread each ----
-        for (int t = tid; t < 3 * g + 1; t += NT) {
+        // ---- determinants (topFrame::constructDetSeries): one thread per point / range frame ----
+        for (int t = tid; t < 2 * g + 1; t += NT) {
             ival Fm[N][N];
-            const int src = (t <= 2 * g) ? t : t - g;            // Jacobi task t in [2g+1,3g] reads range frame (t-g) and derivative frame t
 #pragma unroll
             for (int a = 0; a < N; a++)
 #pragma unroll
-                for (int bb = 0; bb < N; bb++) Fm[a][bb] = EV[(src * N + a) * N + bb];
-            if (t <= 2 * g) DT[t] = Det<N>::det(Fm);
-            else {
-                ival Dm[N][N];
-#pragma unroll
-                for (int a = 0; a < N; a++)
-#pragma unroll
-                    for (int bb = 0; bb < N; bb++) Dm[a][bb] = EV[(t * N + a) * N + bb];
-                DT[t] = jacobi_derivative<N>(Fm, Dm);
-            }
+                for (int bb = 0; bb < N; bb++) Fm[a][bb] = (t == 0) ? S.Fk[0][a][bb] : EV[(t * N + a) * N + bb];
+            DT[t] = Det<N>::det(Fm);
         }
         __syncthreads();
-        // ---- topFrame::countZeros decision per sub-interval (threads 0..g-1), tally by thread 0 ----
+        // ---- topFrame::countZeros decision per sub-interval (threads 0..g-1), tally by thread 0.  As in the reference the
+        //      Jacobi derivative (calculateDerivative) is only formed when the rough enclosures do not settle the sub-interval ----
         if (tid < g) {
             const int gi = tid;
             const double tl = S.gp[gi], th = S.gp[gi + 1];
             const ival timeI = mk(__dadd_rd(tprev.lo, tl), __dadd_ru(tprev.hi, th));
-            const ival dL = DT[gi], dR = DT[gi + 1], dV = DT[g + 1 + gi], dD = DT[2 * g + 1 + gi];
+            const ival dL = DT[gi], dR = DT[gi + 1], dV = DT[g + 1 + gi];
+            const ival LR = imul_nl(dL, dR);
+            const bool need_D = (series != nullptr) || !(LR.lo > 0 && idefinite(dV));
+            ival dD = pt(0.0);
+            if (need_D) {
+                ival Fm[N][N], Dm[N][N];
+#pragma unroll
+                for (int a = 0; a < N; a++)
+#pragma unroll
+                    for (int bb = 0; bb < N; bb++) { Fm[a][bb] = EV[((g + 1 + gi) * N + a) * N + bb]; Dm[a][bb] = EV[((2 * g + 1 + gi) * N + a) * N + bb]; }
+                dD = jacobi_derivative<N>(Fm, Dm);
+            }
             int decision = count_decide(timeI, dL, dR, dV, dD);
             if (!(ifinite(dL) && ifinite(dR) && ifinite(dV) && ifinite(dD))) decision |= 4;
             S.dec[gi] = decision; S.dtime[gi] = timeI;

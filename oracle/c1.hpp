@@ -307,7 +307,11 @@ static inline void run_front(const ccp_front_desc& d, ccp_front_result& res, std
             }
             ival time(add_rd(tprev.lo, tl), add_ru(tprev.hi, th));
             ival dL = detN(FL, n), dR = detN(FR, n), dV = detN(FV, n);
-            ival dD = jacobi_derivative(FV, FD, n);
+            // the Jacobi derivative is formed lazily (as topFrame::countZeros does): only when the rough enclosures do not
+            // settle the sub-interval, or when the series is requested
+            const ival LR = dL * dR;
+            const bool need_D = (series != nullptr) || !(LR.lo > 0 && definite(dV));
+            ival dD = need_D ? jacobi_derivative(FV, FD, n) : ival(0.0);
             int idx = s * g + i;
             count_step(cnt, idx, time, dL, dR, dV, dD);
             if (series) { ccp_series_rec rec; rec.time = toc(time); rec.det_L = toc(dL); rec.det_R = toc(dR); rec.det_V = toc(dV); rec.det_D = toc(dD); series->push_back(rec); }
