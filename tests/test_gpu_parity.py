@@ -241,3 +241,16 @@ def test_config5_n4_throughput_path(engine, pkg, orc):
     assert _same_bits(np.frombuffer(gpu, dtype=np.float64), np.frombuffer(cpu, dtype=np.float64))
     assert [r.status for r in gpu] == [0, 0, 0]
     assert gpu[0].zero_count == 3 and gpu[0].failure_count == 0
+
+
+@pytest.mark.parametrize("order,step_log2,grid", [(12, 4, 7), (20, 6, 15), (8, 5, 1), (2, 7, 3)])
+def test_non_default_order_step_grid(engine, pkg, orc, order, step_log2, grid):
+    """Ragged configurations: every supported (order, step, grid) -- including the maxima order 20 / grid 15 and the
+    minima order 2 / grid 1 -- stays bit-identical to the oracle."""
+    opts = pkg.abi.SetupOpts.default(L_minus_override=3.3, order=order, step_log2=step_log2, grid=grid)
+    desc, _ = pkg.setup_front(3, [1.0, .98, .96, .04, .02], opts)
+    g, gs = engine.frame_count_series(desc)
+    c, cs = orc.run_front(pkg.abi, desc, orc.MODE_C1, series=True)
+    assert gs.shape == cs.shape and gs.shape[0] == g.steps * grid
+    assert _same_bits(gs, cs) and _same_bits(_raw(g), _raw(c))
+    assert g.status == c.status
