@@ -159,6 +159,13 @@ int ccp_debug_primitives(int op, const double* in, double* out, size_t n) {
     return 0;
 }
 
+#ifdef CCP_TRACE
+int ccp_debug_trace(long long* out, int* n) {
+    cudaMemcpyFromSymbol(out, ccp::g_trace, sizeof(long long) * 1024);
+    cudaMemcpyFromSymbol(n, ccp::g_trace_n, sizeof(int) * 2);
+    return 0;
+}
+#endif
 #ifdef CCP_PROFILE
 int ccp_debug_profile(unsigned long long* out, int reset) {
     if (out) cudaMemcpyFromSymbol(out, ccp::g_prof, sizeof(unsigned long long) * 16);

@@ -15,6 +15,16 @@
 namespace ccp {
 
 // Optional per-phase cycle counters (make prof): block 0 adds clock64() deltas into g_prof[phase].
+#ifdef CCP_TRACE
+// timeline trace of ONE step of block 0: (clock, marker) pairs written by lane 0 of each warp (scripts/gpu_trace.py)
+__device__ long long g_trace[2][512];
+__device__ int g_trace_n[2];
+#define TRC_DECL() int trc_n = 0
+#define TRC(id) do { if (blockIdx.x == 0 && s == 500 && (threadIdx.x & 31) == 0 && trc_n < 255) { g_trace[threadIdx.x >> 5][2 * trc_n] = clock64(); g_trace[threadIdx.x >> 5][2 * trc_n + 1] = (id); trc_n++; g_trace_n[threadIdx.x >> 5] = trc_n; } } while (0)
+#else
+#define TRC_DECL() do {} while (0)
+#define TRC(id) do {} while (0)
+#endif
 #ifdef CCP_PROFILE
 __device__ unsigned long long g_prof[16];
 #define PROF_T0() long long prof_t = clock64()
@@ -69,7 +79,7 @@ struct FrontSmem {
     double invlo[KMAX + 2], invhi[KMAX + 2]; // [rd(1/k), ru(1/k)]
     double gp[GMAX + 1];                     // grid points of the current step (utils.cpp:219-223)
     ival dtime[GMAX];
-    SPar spb[N], spc[NE];
+    SPar par[3 * N];                         // unified: b_i | c_e | zero | -c_e   (indices N+e, 2N-1, 2N+e) for the branch-free combines
     int dec[GMAX];
     int flag;
     Majorant mj;
@@ -297,6 +307,7 @@ template <int N> struct PhaseCheck {
     static_assert(L::NA + L::NB <= 32, "the phi warp holds the A tasks and the B tasks side by side");
     static constexpr int CROUNDS = (L::NC + 31) / 32;
     static_assert(CROUNDS <= 3, "Psi warp: at most 3 rounds of C tasks");
+    static_assert(N * 2 * N <= 32, "Psi warp: one combine task per lane");
 };
 
 __device__ __forceinline__ void bar_pair() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
@@ -426,8 +437,13 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
     for (int t = tid; t < (int)(sizeof(ccp_front_result) / 8); t += NT) reinterpret_cast<double*>(gres)[t] = 0.0;
     __syncthreads();                                // the descriptor (un.desc) is dead from here on
     if (tid == 0) { S.mj = majorant<N>(S.bpar, S.cpar, p, h); S.flag = 0; }
-    if (tid >= 32 && tid < 32 + N) S.spb[tid - 32] = make_spar(S.bpar[tid - 32]);
-    if (tid >= 48 && tid < 48 + N - 1) S.spc[tid - 48] = make_spar(S.cpar[tid - 48]);
+    if (tid < 3 * N - 1) {
+        SPar q; q.pl = 0; q.ph = 0; q.neg = 0; q.straddle = 0;                       // index 2N-1: zero parameter
+        if (tid < N) q = make_spar(S.bpar[tid]);
+        else if (tid < 2 * N - 1) q = make_spar(S.cpar[tid - N]);
+        else if (tid >= 2 * N) { q = make_spar(S.cpar[tid - 2 * N]); q.neg = q.neg ? 0 : 1; }   // -c_e
+        S.par[tid] = q;
+    }
     __syncthreads();
     const Majorant mj = S.mj;
     if (!mj.ok) status = CCP_ST_ENCLOSURE;
@@ -441,6 +457,53 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
     const TaskR tB = make_taskr(decode_task<N>(2, wq == 0 ? (1 << 20) : 32 + lane));
     const TaskR tC = make_taskr(decode_task<N>(2, (wq == 0 || CROUNDS < 3) ? (1 << 20) : 64 + lane));
     const mt* const Tf = &T[0][0];
+    // ---- per-lane operands of the three "combine" stages, fixed for the whole front.  Every stage is ONE branch-free
+    //      instruction stream: out = -(P0*X0) - P1*X1 - P2*X2 (missing neighbours: zero parameter / zero slot).
+    //        phi warp, lanes < 2N      : X = Cauchy sums g*w (scratch), out/(k+1) -> v[k+1]; v[k]/(k+1) -> u[k+1], z[k+1]
+    //        Psi warp, lanes < N       : Md_i[k-1]:  X0 = 3 g_i - [k==1]/2, X1 = g_{i-1}, X2 = g_{i+1}  (hull g rows)
+    //        Psi warp, lanes N..2N-2   : Mo_e[k-1]:  X0 = 2 q_e, P0 = -c_e
+    //        Psi warp, lanes < N*D     : Pv[k] = (X0 + X1 + X2)/k from the C sums (scratch); Pu[k] = Pv[k-1]/k
+    constexpr int ZSLOT = L::NB + L::NC;
+    if (tid == 0) S.un.scratch[ZSLOT] = pt(0.0);
+    bool anystr = false;
+    for (int i = 0; i < 2 * N - 1; i++) anystr = anystr || S.par[i].straddle;
+    // combine 1 (phi: B sums -> v,u,z;  Psi: C sums -> Pv,Pu); parameters by index into S.par (2N-1 = zero)
+    constexpr int PZ = 2 * N - 1;
+    int cs0 = ZSLOT, cs1 = ZSLOT, cs2 = ZSLOT, rowV = 0, rowU = 0, rowZ = 0;
+    int ap0 = PZ, ap1 = PZ, ap2 = PZ;
+    // combine 2 (Psi: M series)
+    int mr0 = 0, mr1 = 0, mr2 = 0, mout = 0, mscale = 0, mp0 = PZ, mp1 = PZ, mp2 = PZ; double mcst = 0;
+    if (wq == 0 && lane < 2 * N) {
+        const int set = lane / N, i = lane % N;
+        int b0 = set * (3 * N - 2) + (i == 0 ? 0 : 3 * i - 1);
+        cs0 = b0++; ap0 = i;
+        if (i > 0)     { cs1 = b0++; ap1 = N + i - 1; }
+        if (i < N - 1) { cs2 = b0;   ap2 = N + i; }
+        rowV = L::V(set, i) * KMAX; rowU = L::U(set, i) * KMAX; rowZ = L::Z(set, i) * KMAX;
+    } else if (wq == 1) {
+        if (lane < N * D) {
+            const int i = lane / D, cc = lane % D;
+            int c0 = L::NB + (i == 0 ? 0 : (3 * i - 1) * D) + cc * ((i == 0 || i == N - 1) ? 2 : 3);
+            cs0 = c0++;
+            if (i > 0)     cs1 = c0++;
+            if (i < N - 1) cs2 = c0;
+            rowV = L::PV(i, cc) * KMAX; rowU = L::PU(i, cc) * KMAX;
+        }
+        if (lane < N) {
+            const int i = lane;
+            mr0 = L::G(1, i) * KMAX; mscale = 3; mcst = 0.5; mout = L::MD(i) * KMAX; mp0 = i;
+            mr1 = mr2 = mr0;
+            if (i > 0)     { mr1 = L::G(1, i - 1) * KMAX; mp1 = N + i - 1; }
+            if (i < N - 1) { mr2 = L::G(1, i + 1) * KMAX; mp2 = N + i; }
+        } else if (lane < 2 * N - 1) {
+            const int e = lane - N;
+            mr0 = mr1 = mr2 = L::Q(1, e) * KMAX; mscale = 2; mcst = 0.0; mout = L::MO(e) * KMAX; mp0 = 2 * N + e;   // P0 = -c_e
+        }
+    }
+    ap0 = opaque(ap0); ap1 = opaque(ap1); ap2 = opaque(ap2); mp0 = opaque(mp0); mp1 = opaque(mp1); mp2 = opaque(mp2);
+    cs0 = opaque(cs0); cs1 = opaque(cs1); cs2 = opaque(cs2); rowV = opaque(rowV); rowU = opaque(rowU); rowZ = opaque(rowZ);
+    mr0 = opaque(mr0); mr1 = opaque(mr1); mr2 = opaque(mr2); mout = opaque(mout);
+
     const int Stot = step_count(L_minus, h);
     int zero_count = 0, failure_count = 0, first_failure = -1, n_conj = 0;      // maintained by thread 0
     ival tprev = pt(0.0);
@@ -452,6 +515,8 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
 
     for (int s = 0; s < Stot && status == CCP_OK; s++) {
         PROF_T0();
+        TRC_DECL();
+        TRC(1);
         const bool last = (s == Stot - 1);
         const double hs = last ? __dadd_ru(L_minus, -tprev.hi) : h;
         const int nxt = cur ^ 1;
@@ -488,6 +553,7 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
         }
         __syncthreads();
         PROF(0);
+        TRC(2);
         // ---- Taylor tables, order by order.  Warp 0 builds the front tables (centre + hull) of order k while warp 1
         //      builds the variational tables of order k-1 from the M-series warp 0 finished one iteration earlier;
         //      the two warps meet once per order (bar.sync 1), everything else is __syncwarp. ----
@@ -495,47 +561,73 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
             if (wq == 0) {
                 if (k < p) {
                     PROF(12);
+                    TRC(100 + k);
                     // one pass for both task kinds: A lanes sum all k+1 terms, B lanes the first k terms (their last
                     // term g[k]*w0 needs the g[k] the A lanes are producing right now)
                     acc4 acc = run_partial(Tf, tA, k, tA.kind == 0 ? k + 1 : (tA.kind == 1 ? k : 0));
                     if (tA.kind == 0) T[0][tA.out * KMAX + k] = iv2mt(acc_finish(acc));               // g[k], q[k]
                     __syncwarp();
                     PROF(7);
+                    TRC(200 + k);
                     if (tA.kind == 1) {
                         if (k == 0) acc_term(acc, Tf[tA.offa0], Tf[tA.offb0]); else acc_term(acc, Tf[tA.offA + k], Tf[tA.offb0]);
                         S.un.scratch[tA.out] = acc_finish(acc);                                        // g*w products
                     }
                     __syncwarp();
                     PROF(8);
+                    TRC(300 + k);
                     if (lane < 2 * N) {
-                        const int set = lane / N, i = lane % N;
-                        int b0 = set * (3 * N - 2) + (i == 0 ? 0 : 3 * i - 1);           // first B task of (set,i)
-                        ival f = ineg(imul_par(S.un.scratch[b0], S.spb[i], S.bpar[i])); b0++;
-                        if (i > 0)     { f = isub(f, imul_par(S.un.scratch[b0], S.spc[i - 1], S.cpar[i - 1])); b0++; }
-                        if (i < N - 1) { f = isub(f, imul_par(S.un.scratch[b0], S.spc[i], S.cpar[i])); }
-                        T[L::V(set, i)][k + 1] = iv2mt(idivk_tab(f, S.invlo, S.invhi, k + 1));
-                        const mt un = iv2mt(idivk_tab(mt2iv(T[L::V(set, i)][k]), S.invlo, S.invhi, k + 1));
-                        T[L::U(set, i)][k + 1] = un;
+                        const ival s0 = S.un.scratch[cs0], s1 = S.un.scratch[cs1], s2 = S.un.scratch[cs2];
+                        const mt vk = Tf[rowV + k];
+                        const double il = S.invlo[k + 1], ih = S.invhi[k + 1];
+                        ival f;
+                        if (!anystr) {
+                            const SPar q0 = S.par[ap0], q1 = S.par[ap1], q2 = S.par[ap2];
+                            f = ineg(imul_pos3(s0, q0.pl, q0.ph, q0.neg));
+                            f = isub(f, imul_pos3(s1, q1.pl, q1.ph, q1.neg));
+                            f = isub(f, imul_pos3(s2, q2.pl, q2.ph, q2.neg));
+                        } else {                                  // a parameter interval straddles zero: general products
+                            const int i = lane % N;
+                            f = ineg(imul_nl(s0, S.bpar[i]));
+                            if (i > 0)     f = isub(f, imul_nl(s1, S.cpar[i - 1]));
+                            if (i < N - 1) f = isub(f, imul_nl(s2, S.cpar[i]));
+                        }
+                        const ival fv = mk(__dmul_rd(f.lo, f.lo >= 0 ? il : ih), __dmul_ru(f.hi, f.hi >= 0 ? ih : il));
+                        const ival vi = mt2iv(vk);
+                        const ival fu = mk(__dmul_rd(vi.lo, vi.lo >= 0 ? il : ih), __dmul_ru(vi.hi, vi.hi >= 0 ? ih : il));
+                        T[0][rowV + k + 1] = iv2mt(fv);
+                        const mt un = iv2mt(fu);
+                        T[0][rowU + k + 1] = un;
                         mt zn; zn.m = -un.m; zn.t = un.t;
-                        T[L::Z(set, i)][k + 1] = zn;
+                        T[0][rowZ + k + 1] = zn;
                     }
                 }
             } else if (k >= 1) {
-                // M-series of order k-1 from the hull g, q the phi warp finished one iteration ago
-                if (lane < N) {
-                    const int i = lane, km = k - 1;
-                    ival t3 = imulk(mt2iv(T[L::G(1, i)][km]), 3);
-                    if (km == 0) t3 = isub(t3, pt(0.5));
-                    ival dd = ineg(imul_par(t3, S.spb[i], S.bpar[i]));
-                    if (i > 0)     dd = isub(dd, imul_par(mt2iv(T[L::G(1, i - 1)][km]), S.spc[i - 1], S.cpar[i - 1]));
-                    if (i < N - 1) dd = isub(dd, imul_par(mt2iv(T[L::G(1, i + 1)][km]), S.spc[i], S.cpar[i]));
-                    T[L::MD(i)][km] = iv2mt(dd);
-                } else if (lane >= 16 && lane < 16 + (N - 1)) {
-                    const int e = lane - 16, km = k - 1;
-                    const ival qe = mt2iv(T[L::Q(1, e)][km]);
-                    T[L::MO(e)][km] = iv2mt(imul_par(mk(2.0 * qe.lo, 2.0 * qe.hi), S.spc[e], S.cpar[e]));
+                TRC(600 + k);
+                // M-series of order k-1 from the hull g, q the phi warp finished one iteration ago (lanes < 2N-1, uniform)
+                if (lane < 2 * N - 1) {
+                    const int km = k - 1;
+                    const ival x0r = mt2iv(Tf[mr0 + km]), x1 = mt2iv(Tf[mr1 + km]), x2 = mt2iv(Tf[mr2 + km]);
+                    ival x0 = imulk(x0r, mscale);
+                    if (km == 0) x0 = isub(x0, pt(mcst));
+                    ival dd;
+                    if (!anystr) {
+                        const SPar q0 = S.par[mp0], q1 = S.par[mp1], q2 = S.par[mp2];
+                        dd = ineg(imul_pos3(x0, q0.pl, q0.ph, q0.neg));
+                        dd = isub(dd, imul_pos3(x1, q1.pl, q1.ph, q1.neg));
+                        dd = isub(dd, imul_pos3(x2, q2.pl, q2.ph, q2.neg));
+                    } else if (lane < N) {
+                        const int i = lane;
+                        dd = ineg(imul_nl(x0, S.bpar[i]));
+                        if (i > 0)     dd = isub(dd, imul_nl(x1, S.cpar[i - 1]));
+                        if (i < N - 1) dd = isub(dd, imul_nl(x2, S.cpar[i]));
+                    } else {
+                        dd = imul_nl(x0, S.cpar[lane - N]);
+                    }
+                    T[0][mout + km] = iv2mt(dd);
                 }
                 __syncwarp();
+                TRC(700 + k);
                 {   // rounds 0 and 1 of the C tasks, fused; lanes without a round-1 task redo their round-0 task (discarded)
                     ival r0, r1;
                     if (tA.kind == 2) {
@@ -546,21 +638,27 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
                 }
                 if (CROUNDS >= 3 && tC.kind == 2) S.un.scratch[tC.out] = run_task(Tf, tC, k - 1);
                 __syncwarp();
-                for (int e = lane; e < N * D; e += 32) {
-                    const int i = e / D, cc = e % D;
-                    int c0 = L::NB + (i == 0 ? 0 : (3 * i - 1) * D) + cc * ((i == 0 || i == N - 1) ? 2 : 3);   // first C task of (i,cc)
-                    ival sm = S.un.scratch[c0]; c0++;
-                    if (i > 0)     { sm = iadd(sm, S.un.scratch[c0]); c0++; }
-                    if (i < N - 1) { sm = iadd(sm, S.un.scratch[c0]); }
-                    T[L::PV(i, cc)][k] = iv2mt(idivk_tab(sm, S.invlo, S.invhi, k));
-                    T[L::PU(i, cc)][k] = iv2mt(idivk_tab(mt2iv(T[L::PV(i, cc)][k - 1]), S.invlo, S.invhi, k));
+                TRC(800 + k);
+                if (lane < N * D) {
+                    const ival s0 = S.un.scratch[cs0], s1 = S.un.scratch[cs1], s2 = S.un.scratch[cs2];
+                    const mt pvk = Tf[rowV + k - 1];
+                    const double il = S.invlo[k], ih = S.invhi[k];
+                    const ival sm = iadd(iadd(s0, s1), s2);
+                    const ival fv = mk(__dmul_rd(sm.lo, sm.lo >= 0 ? il : ih), __dmul_ru(sm.hi, sm.hi >= 0 ? ih : il));
+                    const ival vi = mt2iv(pvk);
+                    const ival fu = mk(__dmul_rd(vi.lo, vi.lo >= 0 ? il : ih), __dmul_ru(vi.hi, vi.hi >= 0 ? ih : il));
+                    T[0][rowV + k] = iv2mt(fv);
+                    T[0][rowU + k] = iv2mt(fu);
                 }
             }
             PROF(9);
+            TRC(400 + k);
             bar_pair();
             PROF(10);
+            TRC(500 + k);
         }
         PROF(1);
+        TRC(3);
         // ---- step image: y = Phi(x) (centre tables), J = DPhi over the hull (Psi tables); frame at step start ----
         for (int t = tid; t < D + D * D + D * N; t += NT) {
             if (t < D) {
@@ -578,6 +676,7 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
         }
         __syncthreads();
         PROF(2);
+        TRC(4);
         if (tid < N) {
             double sm = 0; for (int cc = 0; cc < D; cc++) sm = __dadd_ru(sm, imag(S.Ws[cc][tid]));
             S.rhoF[tid] = __dmul_ru(mj.rho_psi, sm); S.rhoFd[tid] = __dmul_ru(mj.rho_psi_d, sm);
@@ -622,6 +721,7 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
         }
         __syncthreads();                            // Fk complete; Psi tables and un.scratch are dead from here
         PROF(3);
+        TRC(5);
         // ---- grid loop (utils.cpp:219-252): evaluation task = (argument, frame row).  arguments:
         //      [0, g]        point tau_i                  -> rows of F at the grid points
         //      [g+1, 2g]     range [tau_i, tau_{i+1}]      -> rows of the range enclosure
@@ -665,6 +765,7 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
         }
         __syncthreads();
         PROF(4);
+        TRC(6);
         // ---- determinants (topFrame::constructDetSeries): one thread per point / range frame ----
         for (int t = tid; t < 2 * g + 1; t += NT) {
             ival Fm[N][N];
@@ -717,6 +818,7 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
             if (last) det_last = DT[2 * g];
         }
         PROF(5);
+        TRC(7);
         // ---- set update ----
         if (tid < D) S.x[nxt][tid] = mid_ru(S.y[tid]);
         for (int t = tid; t < 2 * D * D; t += NT) {
@@ -745,6 +847,7 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
         }
         __syncthreads();
         PROF(6);
+        TRC(8);
         tprev = mk(__dadd_rd(tprev.lo, hs), __dadd_ru(tprev.hi, hs));
         cur = nxt;
         if (last && status == CCP_OK && tid < D) {
