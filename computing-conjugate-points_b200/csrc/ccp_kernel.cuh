@@ -302,11 +302,34 @@ __device__ inline Task decode_task(int kind, int idx) {
     }
     return t;
 }
+// C tasks are processed in PAIRS that share their first operand (the same M-series times two columns of Psi):
+// pair P -> group (i,w) = P / (D/2) in the enumeration order of decode_task, columns 2*(P % (D/2)) and +1.
+template <int N>
+__device__ inline void pair_tasks(int P, int& idx0, int& idx1) {
+    constexpr int D = 2 * N, H = D / 2;
+    idx0 = idx1 = 1 << 20;
+    if (P < 0 || P >= Lay<N>::NC / 2) return;
+    const int grp = P / H, pr = P % H;
+    int gcount = 0;
+    for (int i = 0; i < N; i++) {
+        const int nw = 1 + (i > 0 ? 1 : 0) + (i < N - 1 ? 1 : 0);
+        int widx = 0;
+        for (int w = 0; w < 3; w++) {
+            if ((w == 1 && i == 0) || (w == 2 && i == N - 1)) continue;
+            if (gcount == grp) {
+                const int base = (i == 0 ? 0 : (3 * i - 1) * D);
+                idx0 = base + (2 * pr) * nw + widx;
+                idx1 = base + (2 * pr + 1) * nw + widx;
+            }
+            gcount++; widx++;
+        }
+    }
+}
 template <int N> struct PhaseCheck {
     using L = Lay<N>;
     static_assert(L::NA + L::NB <= 32, "the phi warp holds the A tasks and the B tasks side by side");
-    static constexpr int CROUNDS = (L::NC + 31) / 32;
-    static_assert(CROUNDS <= 3, "Psi warp: at most 3 rounds of C tasks");
+    static constexpr int CROUNDS = (L::NC / 2 + 31) / 32;      // rounds of C-task PAIRS in the Psi warp
+    static_assert(CROUNDS <= 2 && L::NC % 2 == 0, "Psi warp: at most 2 rounds of C-task pairs");
     static_assert(N * 2 * N <= 32, "Psi warp: one combine task per lane");
 };
 
@@ -338,22 +361,22 @@ __device__ __forceinline__ ival run_task(const mt* __restrict__ Tf, const TaskR&
     }
     return acc_finish(a);
 }
-// Two sums of the same order in one loop (Psi warp, rounds 0 and 1): 8 independent FMA chains per lane hide the
-// LDS / DFMA latency that a single 4-chain sum exposes.  Each sum is accumulated exactly as in run_task.
-__device__ __forceinline__ void run_task2(const mt* __restrict__ Tf, const TaskR& t0, const TaskR& t1, bool on1, int kk, ival& r0, ival& r1) {
+// Two sums of the same order that SHARE their first operand series (Psi warp: M-series times two columns of Psi):
+// 3 LDS.128 + 8 DFMA per term; 8 independent FMA chains per lane.  Each sum is accumulated exactly as in run_task.
+__device__ __forceinline__ void run_pair(const mt* __restrict__ Tf, const TaskR& t0, const TaskR& t1, int kk, ival& r0, ival& r1) {
     acc4 a = acc_zero(), b = acc_zero();
-    acc_term(a, Tf[t0.offa0], Tf[kk == 0 ? t0.offb0 : t0.offB + kk]);
-    acc_term(b, Tf[t1.offa0], Tf[kk == 0 ? t1.offb0 : t1.offB + kk]);
+    const mt a0 = Tf[t0.offa0];
+    acc_term(a, a0, Tf[kk == 0 ? t0.offb0 : t0.offB + kk]);
+    acc_term(b, a0, Tf[kk == 0 ? t1.offb0 : t1.offB + kk]);
     if (kk >= 1) {
-        const mt* pa = Tf + t0.offA + 1; const mt* pb = Tf + t0.offB + (kk - 1);
-        const mt* qa = Tf + t1.offA + 1; const mt* qb = Tf + t1.offB + (kk - 1);
+        const mt* pa = Tf + t0.offA + 1; const mt* pb = Tf + t0.offB + (kk - 1); const mt* qb = Tf + t1.offB + (kk - 1);
 #pragma unroll 2
-        for (int j = 1; j < kk; j++) { acc_term(a, *pa, *pb); acc_term(b, *qa, *qb); pa++; pb--; qa++; qb--; }
-        acc_term(a, Tf[t0.offA + kk], Tf[t0.offb0]);
-        acc_term(b, Tf[t1.offA + kk], Tf[t1.offb0]);
+        for (int j = 1; j < kk; j++) { const mt x = *pa; acc_term(a, x, *pb); acc_term(b, x, *qb); pa++; pb--; qb--; }
+        const mt xk = Tf[t0.offA + kk];
+        acc_term(a, xk, Tf[t0.offb0]);
+        acc_term(b, xk, Tf[t1.offb0]);
     }
     r0 = acc_finish(a); r1 = acc_finish(b);
-    (void)on1;
 }
 // terms j = 0 .. upto-1 of the same sum (upto <= kk: the last term, which needs the newest a(kk), is added later)
 __device__ __forceinline__ acc4 run_partial(const mt* __restrict__ Tf, const TaskR& t, int kk, int upto) {
@@ -453,9 +476,12 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
     const int wq = tid >> 5, lane = tid & 31;
     constexpr int CROUNDS = PhaseCheck<N>::CROUNDS;
     // phi warp: tA, tB = this lane's A and B task;  Psi warp: tA, tB, tC = this lane's C tasks of rounds 0, 1, 2
-    const TaskR tA = make_taskr(wq == 0 ? (lane < L::NA ? decode_task<N>(0, lane) : decode_task<N>(1, lane - L::NA)) : decode_task<N>(2, lane));
-    const TaskR tB = make_taskr(decode_task<N>(2, wq == 0 ? (1 << 20) : 32 + lane));
-    const TaskR tC = make_taskr(decode_task<N>(2, (wq == 0 || CROUNDS < 3) ? (1 << 20) : 64 + lane));
+    int pi0, pi1, pi2, pi3;
+    pair_tasks<N>(wq == 1 ? lane : -1, pi0, pi1);
+    pair_tasks<N>((wq == 1 && CROUNDS > 1) ? 32 + lane : -1, pi2, pi3);
+    const TaskR tA = make_taskr(wq == 0 ? (lane < L::NA ? decode_task<N>(0, lane) : decode_task<N>(1, lane - L::NA)) : decode_task<N>(2, pi0));
+    const TaskR tB = make_taskr(decode_task<N>(2, wq == 0 ? (1 << 20) : pi1));
+    const TaskR tC = make_taskr(decode_task<N>(2, pi2)), tD = make_taskr(decode_task<N>(2, pi3));
     const mt* const Tf = &T[0][0];
     // ---- per-lane operands of the three "combine" stages, fixed for the whole front.  Every stage is ONE branch-free
     //      instruction stream: out = -(P0*X0) - P1*X1 - P2*X2 (missing neighbours: zero parameter / zero slot).
@@ -628,15 +654,16 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
                 }
                 __syncwarp();
                 TRC(700 + k);
-                {   // rounds 0 and 1 of the C tasks, fused; lanes without a round-1 task redo their round-0 task (discarded)
+                if (tA.kind == 2) {          // this lane's pair of C tasks (same M-series, two columns of Psi)
                     ival r0, r1;
-                    if (tA.kind == 2) {
-                        run_task2(Tf, tA, tB.kind == 2 ? tB : tA, tB.kind == 2, k - 1, r0, r1);
-                        S.un.scratch[tA.out] = r0;
-                        if (tB.kind == 2) S.un.scratch[tB.out] = r1;
-                    }
+                    run_pair(Tf, tA, tB, k - 1, r0, r1);
+                    S.un.scratch[tA.out] = r0; S.un.scratch[tB.out] = r1;
                 }
-                if (CROUNDS >= 3 && tC.kind == 2) S.un.scratch[tC.out] = run_task(Tf, tC, k - 1);
+                if (CROUNDS > 1 && tC.kind == 2) {
+                    ival r0, r1;
+                    run_pair(Tf, tC, tD, k - 1, r0, r1);
+                    S.un.scratch[tC.out] = r0; S.un.scratch[tD.out] = r1;
+                }
                 __syncwarp();
                 TRC(800 + k);
                 if (lane < N * D) {
