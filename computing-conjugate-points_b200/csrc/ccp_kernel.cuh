@@ -337,13 +337,24 @@ __device__ __forceinline__ void bar_pair() { asm volatile("bar.sync 1, 64;" ::: 
 
 // Per-thread task registers.  The fields are laundered through an empty asm so that the compiler keeps them
 // in registers instead of re-deriving them from threadIdx with select chains inside the hot loop.
-struct TaskR { int offA, offB, offa0, offb0, out, kind; };
+// Table offsets are < 2^11 (rows*21), scratch slots < 2^8: three words per task keep the loop-invariant state of four tasks
+// plus the combine operands in registers (unpacked with one shift/mask per use; a spilled word costs an LDL round trip).
+struct TaskR {
+    unsigned ab, zz, ok;     // ab = offA | offB<<16 ; zz = offa0 | offb0<<16 ; ok = out | (kind+1)<<16
+    __device__ __forceinline__ int offA() const { return (int)(ab & 0xffffu); }
+    __device__ __forceinline__ int offB() const { return (int)(ab >> 16); }
+    __device__ __forceinline__ int offa0() const { return (int)(zz & 0xffffu); }
+    __device__ __forceinline__ int offb0() const { return (int)(zz >> 16); }
+    __device__ __forceinline__ int out() const { return (int)(ok & 0xffffu); }
+    __device__ __forceinline__ int kind() const { return (int)(ok >> 16) - 1; }
+};
 __device__ __forceinline__ int opaque(int v) { asm volatile("" : "+r"(v)); return v; }
+__device__ __forceinline__ unsigned opaqueu(unsigned v) { asm volatile("" : "+r"(v)); return v; }
 __device__ __forceinline__ TaskR make_taskr(const Task& t) {
     TaskR r;
-    r.offA = opaque((int)t.iA * KMAX); r.offB = opaque((int)t.iB * KMAX);
-    r.offa0 = opaque((int)t.a0r * KMAX + t.a0c); r.offb0 = opaque((int)t.b0r * KMAX + t.b0c);
-    r.out = opaque((int)t.out); r.kind = opaque((int)t.kind);
+    r.ab = opaqueu((unsigned)((int)t.iA * KMAX) | ((unsigned)((int)t.iB * KMAX) << 16));
+    r.zz = opaqueu((unsigned)((int)t.a0r * KMAX + t.a0c) | ((unsigned)((int)t.b0r * KMAX + t.b0c) << 16));
+    r.ok = opaqueu((unsigned)t.out | ((unsigned)(t.kind + 1) << 16));
     return r;
 }
 // One Cauchy sum  sum_{j=0..kk} a(j) b(kk-j),  accumulated in ascending j exactly as oracle/c1.hpp:cauchy.
@@ -351,13 +362,13 @@ __device__ __forceinline__ TaskR make_taskr(const Task& t) {
 // 2 LDS.128 + 4 DFMA per term with pointer walking.
 __device__ __forceinline__ ival run_task(const mt* __restrict__ Tf, const TaskR& t, int kk) {
     acc4 a = acc_zero();
-    acc_term(a, Tf[t.offa0], Tf[kk == 0 ? t.offb0 : t.offB + kk]);
+    acc_term(a, Tf[t.offa0()], Tf[kk == 0 ? t.offb0() : t.offB() + kk]);
     if (kk >= 1) {
-        const mt* pa = Tf + t.offA + 1;
-        const mt* pb = Tf + t.offB + (kk - 1);
+        const mt* pa = Tf + t.offA() + 1;
+        const mt* pb = Tf + t.offB() + (kk - 1);
 #pragma unroll 2
         for (int j = 1; j < kk; j++) { acc_term(a, *pa, *pb); pa++; pb--; }
-        acc_term(a, Tf[t.offA + kk], Tf[t.offb0]);
+        acc_term(a, Tf[t.offA() + kk], Tf[t.offb0()]);
     }
     return acc_finish(a);
 }
@@ -365,16 +376,16 @@ __device__ __forceinline__ ival run_task(const mt* __restrict__ Tf, const TaskR&
 // 3 LDS.128 + 8 DFMA per term; 8 independent FMA chains per lane.  Each sum is accumulated exactly as in run_task.
 __device__ __forceinline__ void run_pair(const mt* __restrict__ Tf, const TaskR& t0, const TaskR& t1, int kk, ival& r0, ival& r1) {
     acc4 a = acc_zero(), b = acc_zero();
-    const mt a0 = Tf[t0.offa0];
-    acc_term(a, a0, Tf[kk == 0 ? t0.offb0 : t0.offB + kk]);
-    acc_term(b, a0, Tf[kk == 0 ? t1.offb0 : t1.offB + kk]);
+    const mt a0 = Tf[t0.offa0()];
+    acc_term(a, a0, Tf[kk == 0 ? t0.offb0() : t0.offB() + kk]);
+    acc_term(b, a0, Tf[kk == 0 ? t1.offb0() : t1.offB() + kk]);
     if (kk >= 1) {
-        const mt* pa = Tf + t0.offA + 1; const mt* pb = Tf + t0.offB + (kk - 1); const mt* qb = Tf + t1.offB + (kk - 1);
+        const mt* pa = Tf + t0.offA() + 1; const mt* pb = Tf + t0.offB() + (kk - 1); const mt* qb = Tf + t1.offB() + (kk - 1);
 #pragma unroll 2
         for (int j = 1; j < kk; j++) { const mt x = *pa; acc_term(a, x, *pb); acc_term(b, x, *qb); pa++; pb--; qb--; }
-        const mt xk = Tf[t0.offA + kk];
-        acc_term(a, xk, Tf[t0.offb0]);
-        acc_term(b, xk, Tf[t1.offb0]);
+        const mt xk = Tf[t0.offA() + kk];
+        acc_term(a, xk, Tf[t0.offb0()]);
+        acc_term(b, xk, Tf[t1.offb0()]);
     }
     r0 = acc_finish(a); r1 = acc_finish(b);
 }
@@ -382,13 +393,13 @@ __device__ __forceinline__ void run_pair(const mt* __restrict__ Tf, const TaskR&
 __device__ __forceinline__ acc4 run_partial(const mt* __restrict__ Tf, const TaskR& t, int kk, int upto) {
     acc4 a = acc_zero();
     if (upto <= 0) return a;
-    acc_term(a, Tf[t.offa0], Tf[kk == 0 ? t.offb0 : t.offB + kk]);
-    const mt* pa = Tf + t.offA + 1;
-    const mt* pb = Tf + t.offB + (kk - 1);
+    acc_term(a, Tf[t.offa0()], Tf[kk == 0 ? t.offb0() : t.offB() + kk]);
+    const mt* pa = Tf + t.offA() + 1;
+    const mt* pb = Tf + t.offB() + (kk - 1);
     const int jend = upto < kk ? upto : kk;
 #pragma unroll 2
     for (int j = 1; j < jend; j++) { acc_term(a, *pa, *pb); pa++; pb--; }
-    if (upto == kk + 1 && kk >= 1) acc_term(a, Tf[t.offA + kk], Tf[t.offb0]);
+    if (upto == kk + 1 && kk >= 1) acc_term(a, Tf[t.offA() + kk], Tf[t.offb0()]);
     return a;
 }
 // product with a parameter interval of known sign: c = sg * [pl, ph], 0 <= pl <= ph.  Same end points as imul_nl(a, c).
@@ -590,14 +601,14 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
                     TRC(100 + k);
                     // one pass for both task kinds: A lanes sum all k+1 terms, B lanes the first k terms (their last
                     // term g[k]*w0 needs the g[k] the A lanes are producing right now)
-                    acc4 acc = run_partial(Tf, tA, k, tA.kind == 0 ? k + 1 : (tA.kind == 1 ? k : 0));
-                    if (tA.kind == 0) T[0][tA.out * KMAX + k] = iv2mt(acc_finish(acc));               // g[k], q[k]
+                    acc4 acc = run_partial(Tf, tA, k, tA.kind() == 0 ? k + 1 : (tA.kind() == 1 ? k : 0));
+                    if (tA.kind() == 0) T[0][tA.out() * KMAX + k] = iv2mt(acc_finish(acc));               // g[k], q[k]
                     __syncwarp();
                     PROF(7);
                     TRC(200 + k);
-                    if (tA.kind == 1) {
-                        if (k == 0) acc_term(acc, Tf[tA.offa0], Tf[tA.offb0]); else acc_term(acc, Tf[tA.offA + k], Tf[tA.offb0]);
-                        S.un.scratch[tA.out] = acc_finish(acc);                                        // g*w products
+                    if (tA.kind() == 1) {
+                        if (k == 0) acc_term(acc, Tf[tA.offa0()], Tf[tA.offb0()]); else acc_term(acc, Tf[tA.offA() + k], Tf[tA.offb0()]);
+                        S.un.scratch[tA.out()] = acc_finish(acc);                                        // g*w products
                     }
                     __syncwarp();
                     PROF(8);
@@ -654,15 +665,15 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
                 }
                 __syncwarp();
                 TRC(700 + k);
-                if (tA.kind == 2) {          // this lane's pair of C tasks (same M-series, two columns of Psi)
+                if (tA.kind() == 2) {          // this lane's pair of C tasks (same M-series, two columns of Psi)
                     ival r0, r1;
                     run_pair(Tf, tA, tB, k - 1, r0, r1);
-                    S.un.scratch[tA.out] = r0; S.un.scratch[tB.out] = r1;
+                    S.un.scratch[tA.out()] = r0; S.un.scratch[tB.out()] = r1;
                 }
-                if (CROUNDS > 1 && tC.kind == 2) {
+                if (CROUNDS > 1 && tC.kind() == 2) {
                     ival r0, r1;
                     run_pair(Tf, tC, tD, k - 1, r0, r1);
-                    S.un.scratch[tC.out] = r0; S.un.scratch[tD.out] = r1;
+                    S.un.scratch[tC.out()] = r0; S.un.scratch[tD.out()] = r1;
                 }
                 __syncwarp();
                 TRC(800 + k);
