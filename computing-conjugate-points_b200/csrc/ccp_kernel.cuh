@@ -85,7 +85,7 @@ struct FrontSmem {
     Majorant mj;
     union alignas(16) {
         ival scratch[Lay<N>::NB + Lay<N>::NC + 1];   // table loop: per-task Cauchy sums awaiting combination; last slot = [0,0]
-        ival JC[2 * N][2 * N];               // set update: J*C before its midpoint is split off
+        ival JC[4 * N][2 * N];               // set update: rows 0..2n-1 = (J*C - C+)_ij r0_j, rows 2n..4n-1 = J_ij r_j
         ccp_front_desc desc;                 // start of the front only
     } un;
 };
@@ -501,7 +501,6 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
     //        Psi warp, lanes N..2N-2   : Mo_e[k-1]:  X0 = 2 q_e, P0 = -c_e
     //        Psi warp, lanes < N*D     : Pv[k] = (X0 + X1 + X2)/k from the C sums (scratch); Pu[k] = Pv[k-1]/k
     constexpr int ZSLOT = L::NB + L::NC;
-    if (tid == 0) S.un.scratch[ZSLOT] = pt(0.0);
     bool anystr = false;
     for (int i = 0; i < 2 * N - 1; i++) anystr = anystr || S.par[i].straddle;
     // combine 1 (phi: B sums -> v,u,z;  Psi: C sums -> Pv,Pu); parameters by index into S.par (2N-1 = zero)
@@ -559,6 +558,7 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
         const int nxt = cur ^ 1;
         // grid points of this step: gp[i] = inf(i*h/grid), gp[grid] = h  (same for every full step)
         if ((s == 0 || last) && tid >= 32 && tid <= 32 + g) { const int i = tid - 32; S.gp[i] = (i < g) ? __ddiv_rd(__dmul_rd((double)i, hs), (double)g) : hs; }
+        if (tid == NT - 1) S.un.scratch[ZSLOT] = pt(0.0);     // the union was reused by the set update of the previous step
         // ---- hull of the phi-set ----
         if (tid < D) {
             ival a = pt(S.x[cur][tid]);
@@ -816,74 +816,88 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
         __syncthreads();
         // ---- topFrame::countZeros decision per sub-interval (threads 0..g-1), tally by thread 0.  As in the reference the
         //      Jacobi derivative (calculateDerivative) is only formed when the rough enclosures do not settle the sub-interval ----
-        if (tid < g) {
-            const int gi = tid;
-            const double tl = S.gp[gi], th = S.gp[gi + 1];
-            const ival timeI = mk(__dadd_rd(tprev.lo, tl), __dadd_ru(tprev.hi, th));
-            const ival dL = DT[gi], dR = DT[gi + 1], dV = DT[g + 1 + gi];
-            const ival LR = imul_nl(dL, dR);
-            const bool need_D = (series != nullptr) || !(LR.lo > 0 && idefinite(dV));
-            ival dD = pt(0.0);
-            if (need_D) {
-                ival Fm[N][N], Dm[N][N];
+        if (wq == 0) {                              // warp 0: lane gi < g decides sub-interval gi; ballots replace a serial tally
+            const int gi = lane;
+            int decision = 0;
+            ival timeI = pt(0.0);
+            if (gi < g) {
+                const double tl = S.gp[gi], th = S.gp[gi + 1];
+                timeI = mk(__dadd_rd(tprev.lo, tl), __dadd_ru(tprev.hi, th));
+                const ival dL = DT[gi], dR = DT[gi + 1], dV = DT[g + 1 + gi];
+                const ival LR = imul_nl(dL, dR);
+                const bool need_D = (series != nullptr) || !(LR.lo > 0 && idefinite(dV));
+                ival dD = pt(0.0);
+                if (need_D) {
+                    ival Fm[N][N], Dm[N][N];
 #pragma unroll
-                for (int a = 0; a < N; a++)
+                    for (int a = 0; a < N; a++)
 #pragma unroll
-                    for (int bb = 0; bb < N; bb++) { Fm[a][bb] = EV[((g + 1 + gi) * N + a) * N + bb]; Dm[a][bb] = EV[((2 * g + 1 + gi) * N + a) * N + bb]; }
-                dD = jacobi_derivative<N>(Fm, Dm);
-            }
-            int decision = count_decide(timeI, dL, dR, dV, dD);
-            if (!(ifinite(dL) && ifinite(dR) && ifinite(dV) && ifinite(dD))) decision |= 4;
-            S.dec[gi] = decision; S.dtime[gi] = timeI;
-            const int idx = s * g + gi;
-            if (series != nullptr && idx < series_cap) {
-                ccp_series_rec rec; rec.time = toc(timeI); rec.det_L = toc(dL); rec.det_R = toc(dR); rec.det_V = toc(dV); rec.det_D = toc(dD);
-                series[idx] = rec;
-            }
-        }
-        __syncthreads();
-        if (tid == 0) {
-            for (int gi = 0; gi < g; gi++) {
-                const int dcs = S.dec[gi], idx = s * g + gi;
-                if (dcs & 4) S.flag |= 1;
-                if ((dcs & 3) == 2) { if (failure_count == 0) first_failure = idx; failure_count++; }
-                if ((dcs & 3) == 1) {
-                    if (n_conj < CCP_MAX_CONJ) { gres->conj_time[n_conj] = toc(S.dtime[gi]); gres->conj_index[n_conj] = idx; }
-                    n_conj++; zero_count++;
+                        for (int bb = 0; bb < N; bb++) { Fm[a][bb] = EV[((g + 1 + gi) * N + a) * N + bb]; Dm[a][bb] = EV[((2 * g + 1 + gi) * N + a) * N + bb]; }
+                    dD = jacobi_derivative<N>(Fm, Dm);
+                }
+                decision = count_decide(timeI, dL, dR, dV, dD);
+                if (!(ifinite(dL) && ifinite(dR) && ifinite(dV) && ifinite(dD))) decision |= 4;
+                const int idx = s * g + gi;
+                if (series != nullptr && idx < series_cap) {
+                    ccp_series_rec rec; rec.time = toc(timeI); rec.det_L = toc(dL); rec.det_R = toc(dR); rec.det_V = toc(dV); rec.det_D = toc(dD);
+                    series[idx] = rec;
                 }
             }
-            if (s == 0) det_first = DT[g + 1];
-            if (last) det_last = DT[2 * g];
+            const unsigned FULLM = 0xffffffffu;
+            const unsigned zmask = __ballot_sync(FULLM, (decision & 3) == 1);
+            const unsigned fmask = __ballot_sync(FULLM, (decision & 3) == 2);
+            const unsigned nmask = __ballot_sync(FULLM, (decision & 4) != 0);
+            if (nmask && lane == 0) S.flag |= 1;
+            if (fmask && failure_count == 0) first_failure = s * g + (__ffs(fmask) - 1);
+            failure_count += __popc(fmask);
+            if (zmask) {
+                if ((decision & 3) == 1) {
+                    const int slot = n_conj + __popc(zmask & ((1u << lane) - 1u));
+                    if (slot < CCP_MAX_CONJ) { gres->conj_time[slot] = toc(timeI); gres->conj_index[slot] = s * g + gi; }
+                }
+                n_conj += __popc(zmask); zero_count += __popc(zmask);
+            }
+            if (lane == 0) {
+                if (s == 0) det_first = DT[g + 1];
+                if (last) det_last = DT[2 * g];
+            }
         }
         PROF(5);
         TRC(7);
-        // ---- set update ----
+        // ---- set update (oracle/c1.hpp, same products and the same order of additions; the products of the r-update are
+        //      formed in the wide first phase so that the second phase is additions only) ----
         if (tid < D) S.x[nxt][tid] = mid_ru(S.y[tid]);
-        for (int t = tid; t < 2 * D * D; t += NT) {
-            const int e = t % (D * D), i = e / D, j = e % D;
-            if (t < D * D) {
-                ival a = pt(0.0);
+        {
+            for (int t = tid; t < 3 * D * D; t += NT) {
+                const int e = t % (D * D), i = e / D, j = e % D;
+                if (t < D * D) {
+                    ival a = pt(0.0);
 #pragma unroll
-                for (int k = 0; k < D; k++) a = iadd(a, imul_nl(S.J[i][k], pt(S.C[cur][k][j])));
-                S.un.JC[i][j] = a; S.C[nxt][i][j] = mid_ru(a);
-            } else {
-                ival b = pt(0.0);
+                    for (int k = 0; k < D; k++) a = iadd(a, imul_nl(S.J[i][k], pt(S.C[cur][k][j])));
+                    const double cm = mid_ru(a);
+                    S.C[nxt][i][j] = cm;
+                    S.un.JC[i][j] = imul_nl(isub(a, pt(cm)), S.r0[j]);                 // (JC - C+)_ij * r0_j
+                } else if (t < 2 * D * D) {
+                    ival b = pt(0.0);
 #pragma unroll
-                for (int k = 0; k < D; k++) b = iadd(b, imul_nl(S.J[i][k], S.P[cur][k][j]));
-                S.P[nxt][i][j] = b;
+                    for (int k = 0; k < D; k++) b = iadd(b, imul_nl(S.J[i][k], S.P[cur][k][j]));
+                    S.P[nxt][i][j] = b;
+                } else {
+                    S.un.JC[D + i][j] = imul_nl(S.J[i][j], S.r[cur][j]);
+                }
             }
+            __syncthreads();
+            if (S.flag & 1) status = CCP_ST_NONFINITE;
+            if (tid < D) {
+                const int i = tid;
+                ival z = isub(S.y[i], pt(S.x[nxt][i]));
+                for (int j = 0; j < D; j++) z = iadd(z, S.un.JC[i][j]);
+                ival a = pt(0.0);
+                for (int j = 0; j < D; j++) a = iadd(a, S.un.JC[D + i][j]);
+                S.r[nxt][i] = iadd(a, z);
+            }
+            __syncthreads();
         }
-        __syncthreads();
-        if (S.flag & 1) status = CCP_ST_NONFINITE;
-        if (tid < D) {
-            const int i = tid;
-            ival z = isub(S.y[i], pt(S.x[nxt][i]));
-            for (int j = 0; j < D; j++) z = iadd(z, imul_nl(isub(S.un.JC[i][j], pt(S.C[nxt][i][j])), S.r0[j]));
-            ival a = pt(0.0);
-            for (int j = 0; j < D; j++) a = iadd(a, imul_nl(S.J[i][j], S.r[cur][j]));
-            S.r[nxt][i] = iadd(a, z);
-        }
-        __syncthreads();
         PROF(6);
         TRC(8);
         tprev = mk(__dadd_rd(tprev.lo, hs), __dadd_ru(tprev.hi, hs));
