@@ -7,7 +7,9 @@ eng = pkg.Engine(0)
 nf = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 L = float(sys.argv[2]) if len(sys.argv) > 2 else 0.0
 opts = abi.SetupOpts.default(L_minus_override=L) if L > 0 else None
-desc, _ = pkg.setup_front(3, [1, .98, .96, .04, .02], opts)
+n = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+par = {2: [1, .97, .05], 3: [1, .98, .96, .04, .02], 4: [1, .98, .96, .94, .04, .02, .03]}[n]
+desc, _ = pkg.setup_front(n, par, opts)
 descs = (abi.FrontDesc * nf)(*[desc] * nf)
 out = eng.frame_count_batch(descs)
-print("kernel ms", eng.last_kernel_ms(), "steps", out[0].steps, "zeros", out[0].zero_count)
+print("n", n, "fronts", nf, "kernel ms", eng.last_kernel_ms(), "steps", out[0].steps, "zeros", out[0].zero_count, "fronts/s %.0f" % (nf / eng.last_kernel_ms() * 1e3), "model TFLOP/s %.2f" % (nf * pkg.front_flops(n, 20, 14, out[0].steps) / eng.last_kernel_ms() / 1e9))
