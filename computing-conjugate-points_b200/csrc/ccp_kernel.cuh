@@ -84,7 +84,7 @@ struct FrontSmem {
     int flag;
     Majorant mj;
     union alignas(16) {
-        ival scratch[Lay<N>::NB + Lay<N>::NC + 1];   // table loop: per-task Cauchy sums awaiting combination; last slot = [0,0]
+        ival scratch[Lay<N>::NB + Lay<N>::NC + 2 * N];   // table loop: Cauchy sums awaiting combination; then [0,0]; then the newest hull g, q
         ival JC[4 * N][2 * N];               // set update: rows 0..2n-1 = (J*C - C+)_ij r0_j, rows 2n..4n-1 = J_ij r_j
         ccp_front_desc desc;                 // start of the front only
     } un;
@@ -501,44 +501,43 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
     //        Psi warp, lanes N..2N-2   : Mo_e[k-1]:  X0 = 2 q_e, P0 = -c_e
     //        Psi warp, lanes < N*D     : Pv[k] = (X0 + X1 + X2)/k from the C sums (scratch); Pu[k] = Pv[k-1]/k
     constexpr int ZSLOT = L::NB + L::NC;
+    constexpr int GS = ZSLOT + 1;                    // scratch slots of the hull g_i (N) and q_e (N-1) of the newest order
+    static_assert(sizeof(S.un) >= (GS + 2 * N - 1) * sizeof(ival), "scratch slots");
     bool anystr = false;
     for (int i = 0; i < 2 * N - 1; i++) anystr = anystr || S.par[i].straddle;
-    // combine 1 (phi: B sums -> v,u,z;  Psi: C sums -> Pv,Pu); parameters by index into S.par (2N-1 = zero)
+    // parameters by index into S.par (2N-1 = zero)
     constexpr int PZ = 2 * N - 1;
     int cs0 = ZSLOT, cs1 = ZSLOT, cs2 = ZSLOT, rowV = 0, rowU = 0, rowZ = 0;
-    int ap0 = PZ, ap1 = PZ, ap2 = PZ;
-    // combine 2 (Psi: M series)
-    int mr0 = 0, mr1 = 0, mr2 = 0, mout = 0, mscale = 0, mp0 = PZ, mp1 = PZ, mp2 = PZ; double mcst = 0;
-    if (wq == 0 && lane < 2 * N) {
-        const int set = lane / N, i = lane % N;
-        int b0 = set * (3 * N - 2) + (i == 0 ? 0 : 3 * i - 1);
-        cs0 = b0++; ap0 = i;
-        if (i > 0)     { cs1 = b0++; ap1 = N + i - 1; }
-        if (i < N - 1) { cs2 = b0;   ap2 = N + i; }
-        rowV = L::V(set, i) * KMAX; rowU = L::U(set, i) * KMAX; rowZ = L::Z(set, i) * KMAX;
-    } else if (wq == 1) {
-        if (lane < N * D) {
-            const int i = lane / D, cc = lane % D;
-            int c0 = L::NB + (i == 0 ? 0 : (3 * i - 1) * D) + cc * ((i == 0 || i == N - 1) ? 2 : 3);
-            cs0 = c0++;
-            if (i > 0)     cs1 = c0++;
-            if (i < N - 1) cs2 = c0;
-            rowV = L::PV(i, cc) * KMAX; rowU = L::PU(i, cc) * KMAX;
+    int ap0 = PZ, ap1 = PZ, ap2 = PZ, mscale = 1, gslot = -1;
+    double mcst = 0;
+    if (wq == 0) {
+        if (lane < 2 * N) {                                  // v, u, z of the centre (set 0) and the hull (set 1)
+            const int set = lane / N, i = lane % N;
+            int b0 = set * (3 * N - 2) + (i == 0 ? 0 : 3 * i - 1);
+            cs0 = b0++; ap0 = i;
+            if (i > 0)     { cs1 = b0++; ap1 = N + i - 1; }
+            if (i < N - 1) { cs2 = b0;   ap2 = N + i; }
+            rowV = L::V(set, i) * KMAX; rowU = L::U(set, i) * KMAX; rowZ = L::Z(set, i) * KMAX;
+        } else if (lane < 3 * N) {                           // Md_i
+            const int i = lane - 2 * N;
+            cs0 = GS + i; ap0 = i; mscale = 3; mcst = 0.5; rowV = L::MD(i) * KMAX;
+            if (i > 0)     { cs1 = GS + i - 1; ap1 = N + i - 1; }
+            if (i < N - 1) { cs2 = GS + i + 1; ap2 = N + i; }
+        } else if (lane < 4 * N - 1) {                       // Mo_e = c_e * 2 q_e  (P0 = -c_e)
+            const int e = lane - 3 * N;
+            cs0 = GS + N + e; ap0 = 2 * N + e; mscale = 2; rowV = L::MO(e) * KMAX;
         }
-        if (lane < N) {
-            const int i = lane;
-            mr0 = L::G(1, i) * KMAX; mscale = 3; mcst = 0.5; mout = L::MD(i) * KMAX; mp0 = i;
-            mr1 = mr2 = mr0;
-            if (i > 0)     { mr1 = L::G(1, i - 1) * KMAX; mp1 = N + i - 1; }
-            if (i < N - 1) { mr2 = L::G(1, i + 1) * KMAX; mp2 = N + i; }
-        } else if (lane < 2 * N - 1) {
-            const int e = lane - N;
-            mr0 = mr1 = mr2 = L::Q(1, e) * KMAX; mscale = 2; mcst = 0.0; mout = L::MO(e) * KMAX; mp0 = 2 * N + e;   // P0 = -c_e
-        }
+        if (lane >= N && lane < L::NA) gslot = GS + (lane - N);    // A lanes of the hull g (task N+i) and q (task 2N+e)
+    } else if (lane < N * D) {
+        const int i = lane / D, cc = lane % D;
+        int c0 = L::NB + (i == 0 ? 0 : (3 * i - 1) * D) + cc * ((i == 0 || i == N - 1) ? 2 : 3);
+        cs0 = c0++;
+        if (i > 0)     cs1 = c0++;
+        if (i < N - 1) cs2 = c0;
+        rowV = L::PV(i, cc) * KMAX; rowU = L::PU(i, cc) * KMAX;
     }
-    ap0 = opaque(ap0); ap1 = opaque(ap1); ap2 = opaque(ap2); mp0 = opaque(mp0); mp1 = opaque(mp1); mp2 = opaque(mp2);
+    ap0 = opaque(ap0); ap1 = opaque(ap1); ap2 = opaque(ap2); mscale = opaque(mscale); gslot = opaque(gslot);
     cs0 = opaque(cs0); cs1 = opaque(cs1); cs2 = opaque(cs2); rowV = opaque(rowV); rowU = opaque(rowU); rowZ = opaque(rowZ);
-    mr0 = opaque(mr0); mr1 = opaque(mr1); mr2 = opaque(mr2); mout = opaque(mout);
 
     const int Stot = step_count(L_minus, h);
     int zero_count = 0, failure_count = 0, first_failure = -1, n_conj = 0;      // maintained by thread 0
@@ -582,6 +581,10 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
             T[L::U(set, i)][0] = iv2mt(u0); T[L::V(set, i)][0] = iv2mt(v0);
             T[L::G(set, i)][KMAX - 1] = iv2mt(isub(u0, pt(0.5)));          // w0
             T[L::Z(set, i)][0] = iv2mt(isub(pt(1.0), u0));                 // z0
+            const mt u1 = iv2mt(idivk_tab(mt2iv(iv2mt(v0)), S.invlo, S.invhi, 1));   // u[1] = v[0]/1
+            T[L::U(set, i)][1] = u1;
+            mt z1; z1.m = -u1.m; z1.t = u1.t;
+            T[L::Z(set, i)][1] = z1;
         }
         for (int t = tid; t < N * D; t += NT) {
             const int i = t / D, cc = t % D;
@@ -594,99 +597,111 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
         // ---- Taylor tables, order by order.  Warp 0 builds the front tables (centre + hull) of order k while warp 1
         //      builds the variational tables of order k-1 from the M-series warp 0 finished one iteration earlier;
         //      the two warps meet once per order (bar.sync 1), everything else is __syncwarp. ----
-        for (int k = 0; k <= p; k++) {
-            if (wq == 0) {
-                if (k < p) {
-                    PROF(12);
-                    TRC(100 + k);
-                    // one pass for both task kinds: A lanes sum all k+1 terms, B lanes the first k terms (their last
-                    // term g[k]*w0 needs the g[k] the A lanes are producing right now)
-                    acc4 acc = run_partial(Tf, tA, k, tA.kind() == 0 ? k + 1 : (tA.kind() == 1 ? k : 0));
-                    if (tA.kind() == 0) T[0][tA.out() * KMAX + k] = iv2mt(acc_finish(acc));               // g[k], q[k]
-                    __syncwarp();
-                    PROF(7);
-                    TRC(200 + k);
-                    if (tA.kind() == 1) {
-                        if (k == 0) acc_term(acc, Tf[tA.offa0()], Tf[tA.offb0()]); else acc_term(acc, Tf[tA.offA() + k], Tf[tA.offb0()]);
-                        S.un.scratch[tA.out()] = acc_finish(acc);                                        // g*w products
-                    }
-                    __syncwarp();
-                    PROF(8);
-                    TRC(300 + k);
-                    if (lane < 2 * N) {
-                        const ival s0 = S.un.scratch[cs0], s1 = S.un.scratch[cs1], s2 = S.un.scratch[cs2];
-                        const mt vk = Tf[rowV + k];
-                        const double il = S.invlo[k + 1], ih = S.invhi[k + 1];
-                        ival f;
-                        if (!anystr) {
-                            const SPar q0 = S.par[ap0], q1 = S.par[ap1], q2 = S.par[ap2];
-                            f = ineg(imul_pos3(s0, q0.pl, q0.ph, q0.neg));
-                            f = isub(f, imul_pos3(s1, q1.pl, q1.ph, q1.neg));
-                            f = isub(f, imul_pos3(s2, q2.pl, q2.ph, q2.neg));
-                        } else {                                  // a parameter interval straddles zero: general products
-                            const int i = lane % N;
-                            f = ineg(imul_nl(s0, S.bpar[i]));
-                            if (i > 0)     f = isub(f, imul_nl(s1, S.cpar[i - 1]));
-                            if (i < N - 1) f = isub(f, imul_nl(s2, S.cpar[i]));
-                        }
-                        const ival fv = mk(__dmul_rd(f.lo, f.lo >= 0 ? il : ih), __dmul_ru(f.hi, f.hi >= 0 ? ih : il));
-                        const ival vi = mt2iv(vk);
-                        const ival fu = mk(__dmul_rd(vi.lo, vi.lo >= 0 ? il : ih), __dmul_ru(vi.hi, vi.hi >= 0 ? ih : il));
-                        T[0][rowV + k + 1] = iv2mt(fv);
-                        const mt un = iv2mt(fu);
-                        T[0][rowU + k + 1] = un;
-                        mt zn; zn.m = -un.m; zn.t = un.t;
-                        T[0][rowZ + k + 1] = zn;
-                    }
+        // The A tasks run one order AHEAD of the B tasks: g[k+1] only needs u[<= k+1] = v[<= k]/(k+1), which is known before
+        // the products g*w of order k are -- so no lane ever waits for another lane's sum.  Lanes 2N..4N-2 of the phi warp turn
+        // the hull g, q of the newest order into the M-series with the same instruction stream that turns the g*w sums into v.
+        // Prologue: g, q, M of order 0.
+        if (wq == 0) {
+            if (tA.kind() == 0) {
+                const mt g0 = iv2mt(acc_finish(run_partial(Tf, tA, 0, 1)));
+                T[0][tA.out() * KMAX] = g0;
+                if (gslot >= 0) S.un.scratch[gslot] = mt2iv(g0);
+            }
+            __syncwarp();
+            if (lane >= 2 * N && lane < 4 * N - 1) {
+                ival x0 = imulk(S.un.scratch[cs0], mscale);
+                x0 = isub(x0, pt(mcst));
+                const ival x1 = S.un.scratch[cs1], x2 = S.un.scratch[cs2];
+                ival dd;
+                if (!anystr) {
+                    const SPar q0 = S.par[ap0], q1 = S.par[ap1], q2 = S.par[ap2];
+                    dd = ineg(imul_pos3(x0, q0.pl, q0.ph, q0.neg));
+                    dd = isub(dd, imul_pos3(x1, q1.pl, q1.ph, q1.neg));
+                    dd = isub(dd, imul_pos3(x2, q2.pl, q2.ph, q2.neg));
+                } else if (lane < 3 * N) {
+                    const int i = lane - 2 * N;
+                    dd = ineg(imul_nl(x0, S.bpar[i]));
+                    if (i > 0)     dd = isub(dd, imul_nl(x1, S.cpar[i - 1]));
+                    if (i < N - 1) dd = isub(dd, imul_nl(x2, S.cpar[i]));
+                } else {
+                    dd = imul_nl(x0, S.cpar[lane - 3 * N]);
                 }
-            } else if (k >= 1) {
-                TRC(600 + k);
-                // M-series of order k-1 from the hull g, q the phi warp finished one iteration ago (lanes < 2N-1, uniform)
-                if (lane < 2 * N - 1) {
-                    const int km = k - 1;
-                    const ival x0r = mt2iv(Tf[mr0 + km]), x1 = mt2iv(Tf[mr1 + km]), x2 = mt2iv(Tf[mr2 + km]);
-                    ival x0 = imulk(x0r, mscale);
-                    if (km == 0) x0 = isub(x0, pt(mcst));
-                    ival dd;
-                    if (!anystr) {
-                        const SPar q0 = S.par[mp0], q1 = S.par[mp1], q2 = S.par[mp2];
-                        dd = ineg(imul_pos3(x0, q0.pl, q0.ph, q0.neg));
-                        dd = isub(dd, imul_pos3(x1, q1.pl, q1.ph, q1.neg));
-                        dd = isub(dd, imul_pos3(x2, q2.pl, q2.ph, q2.neg));
-                    } else if (lane < N) {
-                        const int i = lane;
-                        dd = ineg(imul_nl(x0, S.bpar[i]));
-                        if (i > 0)     dd = isub(dd, imul_nl(x1, S.cpar[i - 1]));
-                        if (i < N - 1) dd = isub(dd, imul_nl(x2, S.cpar[i]));
-                    } else {
-                        dd = imul_nl(x0, S.cpar[lane - N]);
-                    }
-                    T[0][mout + km] = iv2mt(dd);
+                T[0][rowV] = iv2mt(dd);
+            }
+        }
+        bar_pair();
+        for (int k = 0; k < p; k++) {
+            if (wq == 0) {
+                PROF(12);
+                TRC(100 + k);
+                // one pass for both task kinds: A lanes g, q of order k+1, B lanes the products g*w of order k
+                const int isA = tA.kind() == 0;
+                const int kk = k + isA;
+                const int upto = (tA.kind() < 0 || (isA && kk > p - 1)) ? 0 : kk + 1;
+                const ival sum = acc_finish(run_partial(Tf, tA, kk, upto));
+                if (upto) {
+                    if (isA) { const mt gm = iv2mt(sum); T[0][tA.out() * KMAX + kk] = gm; if (gslot >= 0) S.un.scratch[gslot] = mt2iv(gm); }
+                    else S.un.scratch[tA.out()] = sum;
                 }
                 __syncwarp();
+                PROF(8);
+                TRC(300 + k);
+                const bool isV = lane < 2 * N;
+                if (isV || (lane < 4 * N - 1 && k + 1 <= p - 1)) {      // v[k+1] (lanes < 2N) and M[k+1] (lanes 2N..4N-2)
+                    const ival s0 = imulk(S.un.scratch[cs0], mscale), s1 = S.un.scratch[cs1], s2 = S.un.scratch[cs2];
+                    const double il = isV ? S.invlo[k + 1] : 1.0, ih = isV ? S.invhi[k + 1] : 1.0;
+                    ival f;
+                    if (!anystr) {
+                        const SPar q0 = S.par[ap0], q1 = S.par[ap1], q2 = S.par[ap2];
+                        f = ineg(imul_pos3(s0, q0.pl, q0.ph, q0.neg));
+                        f = isub(f, imul_pos3(s1, q1.pl, q1.ph, q1.neg));
+                        f = isub(f, imul_pos3(s2, q2.pl, q2.ph, q2.neg));
+                    } else if (lane < 3 * N) {                // a parameter interval straddles zero: general products
+                        const int i = lane % N;
+                        f = ineg(imul_nl(s0, S.bpar[i]));
+                        if (i > 0)     f = isub(f, imul_nl(s1, S.cpar[i - 1]));
+                        if (i < N - 1) f = isub(f, imul_nl(s2, S.cpar[i]));
+                    } else {
+                        f = imul_nl(s0, S.cpar[lane - 3 * N]);
+                    }
+                    const ival fv = mk(__dmul_rd(f.lo, f.lo >= 0 ? il : ih), __dmul_ru(f.hi, f.hi >= 0 ? ih : il));
+                    const mt vn = iv2mt(fv);
+                    T[0][rowV + k + 1] = vn;                                                     // v[k+1] = f[k]/(k+1);  M[k+1]
+                    if (isV && k + 2 <= p) {                                                     // u[k+2] = v[k+1]/(k+2)
+                        const double jl = S.invlo[k + 2], jh = S.invhi[k + 2];
+                        const ival vi = mt2iv(vn);
+                        const ival fu = mk(__dmul_rd(vi.lo, vi.lo >= 0 ? jl : jh), __dmul_ru(vi.hi, vi.hi >= 0 ? jh : jl));
+                        const mt un = iv2mt(fu);
+                        T[0][rowU + k + 2] = un;
+                        mt zn; zn.m = -un.m; zn.t = un.t;
+                        T[0][rowZ + k + 2] = zn;
+                    }
+                }
+            } else {
                 TRC(700 + k);
+                // variational tables: products M * Psi^u of order k -> Pv[k+1];  Pu[k+1] = Pv[k]/(k+1)
                 if (tA.kind() == 2) {          // this lane's pair of C tasks (same M-series, two columns of Psi)
                     ival r0, r1;
-                    run_pair(Tf, tA, tB, k - 1, r0, r1);
+                    run_pair(Tf, tA, tB, k, r0, r1);
                     S.un.scratch[tA.out()] = r0; S.un.scratch[tB.out()] = r1;
                 }
                 if (CROUNDS > 1 && tC.kind() == 2) {
                     ival r0, r1;
-                    run_pair(Tf, tC, tD, k - 1, r0, r1);
+                    run_pair(Tf, tC, tD, k, r0, r1);
                     S.un.scratch[tC.out()] = r0; S.un.scratch[tD.out()] = r1;
                 }
                 __syncwarp();
                 TRC(800 + k);
                 if (lane < N * D) {
                     const ival s0 = S.un.scratch[cs0], s1 = S.un.scratch[cs1], s2 = S.un.scratch[cs2];
-                    const mt pvk = Tf[rowV + k - 1];
-                    const double il = S.invlo[k], ih = S.invhi[k];
+                    const mt pvk = Tf[rowV + k];
+                    const double il = S.invlo[k + 1], ih = S.invhi[k + 1];
                     const ival sm = iadd(iadd(s0, s1), s2);
                     const ival fv = mk(__dmul_rd(sm.lo, sm.lo >= 0 ? il : ih), __dmul_ru(sm.hi, sm.hi >= 0 ? ih : il));
                     const ival vi = mt2iv(pvk);
                     const ival fu = mk(__dmul_rd(vi.lo, vi.lo >= 0 ? il : ih), __dmul_ru(vi.hi, vi.hi >= 0 ? ih : il));
-                    T[0][rowV + k] = iv2mt(fv);
-                    T[0][rowU + k] = iv2mt(fu);
+                    T[0][rowV + k + 1] = iv2mt(fv);
+                    T[0][rowU + k + 1] = iv2mt(fu);
                 }
             }
             PROF(9);
