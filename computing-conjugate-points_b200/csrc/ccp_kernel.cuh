@@ -357,50 +357,60 @@ __device__ __forceinline__ TaskR make_taskr(const Task& t) {
     r.ok = opaqueu((unsigned)t.out | ((unsigned)(t.kind + 1) << 16));
     return r;
 }
-// One Cauchy sum  sum_{j=0..kk} a(j) b(kk-j),  accumulated in ascending j exactly as oracle/c1.hpp:cauchy.
-// The two end terms (j = 0 uses a(0), j = kk uses b(0)) are peeled so that the interior loop is
-// 2 LDS.128 + 4 DFMA per term with pointer walking.
-__device__ __forceinline__ ival run_task(const mt* __restrict__ Tf, const TaskR& t, int kk) {
-    acc4 a = acc_zero();
-    acc_term(a, Tf[t.offa0()], Tf[kk == 0 ? t.offb0() : t.offB() + kk]);
+// Cauchy sums of TWO consecutive orders (kk, kk+1) of one task in one pass over the operands.  Summation order of every sum
+// (oracle/c1.hpp:cauchy_order): interior terms j = 1..order-1 ascending, then the end terms j = 0 and j = order.  The end terms
+// are the only ones that involve coefficients of that order, so while the sum of order kk is completed (s0), the interior of
+// order kk+1 (s1) is accumulated from the same two loads: 2 LDS.128 + 8 DFMA per term, 8 independent FMA chains.
+//   s0 += a[j-1] * b[kk+1-j]   (term j-1 of order kk)        s1 += a[j] * b[kk+1-j]   (term j of order kk+1)
+// a(0), b(0) live at their own offsets (w0 = u0 - 1/2 and z0 = 1 - u0 differ from u only in order 0).
+__device__ __forceinline__ void run_block(const mt* __restrict__ Tf, const TaskR& t, int kk, acc4& s0, acc4& s1) {
+    s0 = acc_zero(); s1 = acc_zero();
     if (kk >= 1) {
         const mt* pa = Tf + t.offA() + 1;
-        const mt* pb = Tf + t.offB() + (kk - 1);
+        const mt* pb = Tf + t.offB() + kk;
+        mt xp = *pa;
+        acc_term(s1, xp, *pb);                                   // j = 1
+        pa++; pb--;
 #pragma unroll 2
-        for (int j = 1; j < kk; j++) { acc_term(a, *pa, *pb); pa++; pb--; }
-        acc_term(a, Tf[t.offA() + kk], Tf[t.offb0()]);
+        for (int j = 2; j <= kk; j++) { const mt x = *pa, y = *pb; acc_term(s0, xp, y); acc_term(s1, x, y); xp = x; pa++; pb--; }
+        acc_term(s0, Tf[t.offa0()], Tf[t.offB() + kk]);
+        acc_term(s0, xp, Tf[t.offb0()]);                         // xp = a[kk]
+    } else {
+        acc_term(s0, Tf[t.offa0()], Tf[t.offb0()]);
     }
-    return acc_finish(a);
 }
-// Two sums of the same order that SHARE their first operand series (Psi warp: M-series times two columns of Psi):
-// 3 LDS.128 + 8 DFMA per term; 8 independent FMA chains per lane.  Each sum is accumulated exactly as in run_task.
-__device__ __forceinline__ void run_pair(const mt* __restrict__ Tf, const TaskR& t0, const TaskR& t1, int kk, ival& r0, ival& r1) {
-    acc4 a = acc_zero(), b = acc_zero();
-    const mt a0 = Tf[t0.offa0()];
-    acc_term(a, a0, Tf[kk == 0 ? t0.offb0() : t0.offB() + kk]);
-    acc_term(b, a0, Tf[kk == 0 ? t1.offb0() : t1.offB() + kk]);
+// end terms of order ord >= 1:  s += a0 * b[ord];  s += a[ord] * b0
+__device__ __forceinline__ void run_ends(const mt* __restrict__ Tf, const TaskR& t, int ord, acc4& s) {
+    acc_term(s, Tf[t.offa0()], Tf[t.offB() + ord]);
+    acc_term(s, Tf[t.offA() + ord], Tf[t.offb0()]);
+}
+// Two tasks that SHARE their first operand series (Psi warp: one M-series times two columns of Psi): 3 LDS.128 + 16 DFMA per term.
+__device__ __forceinline__ void run_block_pair(const mt* __restrict__ Tf, const TaskR& t0, const TaskR& t1, int kk,
+                                               acc4& a0, acc4& a1, acc4& b0, acc4& b1) {
+    a0 = acc_zero(); a1 = acc_zero(); b0 = acc_zero(); b1 = acc_zero();
+    const mt x0 = Tf[t0.offa0()];
     if (kk >= 1) {
-        const mt* pa = Tf + t0.offA() + 1; const mt* pb = Tf + t0.offB() + (kk - 1); const mt* qb = Tf + t1.offB() + (kk - 1);
+        const mt* pa = Tf + t0.offA() + 1; const mt* pb = Tf + t0.offB() + kk; const mt* qb = Tf + t1.offB() + kk;
+        mt xp = *pa;
+        const mt yk = *pb, zk = *qb;
+        acc_term(a1, xp, yk); acc_term(b1, xp, zk);              // j = 1
+        pa++; pb--; qb--;
 #pragma unroll 2
-        for (int j = 1; j < kk; j++) { const mt x = *pa; acc_term(a, x, *pb); acc_term(b, x, *qb); pa++; pb--; qb--; }
-        const mt xk = Tf[t0.offA() + kk];
-        acc_term(a, xk, Tf[t0.offb0()]);
-        acc_term(b, xk, Tf[t1.offb0()]);
+        for (int j = 2; j <= kk; j++) {
+            const mt x = *pa, y = *pb, z = *qb;
+            acc_term(a0, xp, y); acc_term(b0, xp, z); acc_term(a1, x, y); acc_term(b1, x, z);
+            xp = x; pa++; pb--; qb--;
+        }
+        acc_term(a0, x0, yk); acc_term(b0, x0, zk);
+        acc_term(a0, xp, Tf[t0.offb0()]); acc_term(b0, xp, Tf[t1.offb0()]);
+    } else {
+        acc_term(a0, x0, Tf[t0.offb0()]); acc_term(b0, x0, Tf[t1.offb0()]);
     }
-    r0 = acc_finish(a); r1 = acc_finish(b);
 }
-// terms j = 0 .. upto-1 of the same sum (upto <= kk: the last term, which needs the newest a(kk), is added later)
-__device__ __forceinline__ acc4 run_partial(const mt* __restrict__ Tf, const TaskR& t, int kk, int upto) {
-    acc4 a = acc_zero();
-    if (upto <= 0) return a;
-    acc_term(a, Tf[t.offa0()], Tf[kk == 0 ? t.offb0() : t.offB() + kk]);
-    const mt* pa = Tf + t.offA() + 1;
-    const mt* pb = Tf + t.offB() + (kk - 1);
-    const int jend = upto < kk ? upto : kk;
-#pragma unroll 2
-    for (int j = 1; j < jend; j++) { acc_term(a, *pa, *pb); pa++; pb--; }
-    if (upto == kk + 1 && kk >= 1) acc_term(a, Tf[t.offA() + kk], Tf[t.offb0()]);
-    return a;
+__device__ __forceinline__ void run_ends_pair(const mt* __restrict__ Tf, const TaskR& t0, const TaskR& t1, int ord, acc4& a, acc4& b) {
+    const mt x0 = Tf[t0.offa0()], xk = Tf[t0.offA() + ord];
+    acc_term(a, x0, Tf[t0.offB() + ord]); acc_term(b, x0, Tf[t1.offB() + ord]);
+    acc_term(a, xk, Tf[t0.offb0()]);      acc_term(b, xk, Tf[t1.offb0()]);
 }
 // product with a parameter interval of known sign: c = sg * [pl, ph], 0 <= pl <= ph.  Same end points as imul_nl(a, c).
 __device__ __forceinline__ SPar make_spar(const ival& c) {
@@ -420,6 +430,21 @@ __device__ __forceinline__ ival imul_par(const ival& a, const SPar& s, const iva
 // a / k as a product with [rd(1/k), ru(1/k)]  (oracle/c1.hpp:divk)
 __device__ __forceinline__ ival idivk_tab(const ival& a, const double* ilo, const double* ihi, int k) {
     return mk(__dmul_rd(a.lo, a.lo >= 0 ? ilo[k] : ihi[k]), __dmul_ru(a.hi, a.hi >= 0 ? ihi[k] : ilo[k]));
+}
+
+// Enclosure of F'(tau) over [tl, th] for every frame entry: Horner on the derivative series k*F_k, plus the tail bound
+// (the reference's rangeEnclosure of the vector field along the frame, utils.cpp:243-251).  Cold: only sub-intervals whose
+// rough test fails reach it.
+template <int N>
+__device__ __noinline__ void deriv_entries(const ival* __restrict__ Fk0, const double* __restrict__ rhoFd, int p, double tl, double th, ival (&Dm)[N][N]) {
+    constexpr int NN = N * N;
+    for (int a = 0; a < N; a++)
+        for (int bb = 0; bb < N; bb++) {
+            const int c = a * N + bb;
+            ival acc = imulk(Fk0[p * NN + c], p);
+            for (int k = p - 1; k >= 1; k--) acc = horner_rg(acc, tl, th, imulk(Fk0[k * NN + c], k));
+            Dm[a][bb] = iadd(acc, sym(rhoFd[bb]));
+        }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -600,10 +625,13 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
         // The A tasks run one order AHEAD of the B tasks: g[k+1] only needs u[<= k+1] = v[<= k]/(k+1), which is known before
         // the products g*w of order k are -- so no lane ever waits for another lane's sum.  Lanes 2N..4N-2 of the phi warp turn
         // the hull g, q of the newest order into the M-series with the same instruction stream that turns the g*w sums into v.
+        // Orders are processed in blocks of two (run_block): long pass = sums of order k complete + interior of order k+1,
+        // combine(k), then the two end terms of order k+1 (they need the coefficients combine(k) just produced), combine(k+1).
         // Prologue: g, q, M of order 0.
         if (wq == 0) {
             if (tA.kind() == 0) {
-                const mt g0 = iv2mt(acc_finish(run_partial(Tf, tA, 0, 1)));
+                acc4 s0, s1; run_block(Tf, tA, 0, s0, s1);
+                const mt g0 = iv2mt(acc_finish(s0));
                 T[0][tA.out() * KMAX] = g0;
                 if (gslot >= 0) S.un.scratch[gslot] = mt2iv(g0);
             }
@@ -630,78 +658,117 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
             }
         }
         bar_pair();
-        for (int k = 0; k < p; k++) {
+        // phi warp: scratch sums of order kc -> v[kc+1], u[kc+2], z[kc+2] (lanes < 2N);  hull g, q of order kc+1 -> M[kc+1]
+        auto combine_phi = [&](int kc) {
+            const bool isV = lane < 2 * N;
+            if (isV || (lane < 4 * N - 1 && kc + 1 <= p - 1)) {
+                const ival s0 = imulk(S.un.scratch[cs0], mscale), s1 = S.un.scratch[cs1], s2 = S.un.scratch[cs2];
+                const double il = isV ? S.invlo[kc + 1] : 1.0, ih = isV ? S.invhi[kc + 1] : 1.0;
+                ival f;
+                if (!anystr) {
+                    const SPar q0 = S.par[ap0], q1 = S.par[ap1], q2 = S.par[ap2];
+                    f = ineg(imul_pos3(s0, q0.pl, q0.ph, q0.neg));
+                    f = isub(f, imul_pos3(s1, q1.pl, q1.ph, q1.neg));
+                    f = isub(f, imul_pos3(s2, q2.pl, q2.ph, q2.neg));
+                } else if (lane < 3 * N) {                // a parameter interval straddles zero: general products
+                    const int i = lane % N;
+                    f = ineg(imul_nl(s0, S.bpar[i]));
+                    if (i > 0)     f = isub(f, imul_nl(s1, S.cpar[i - 1]));
+                    if (i < N - 1) f = isub(f, imul_nl(s2, S.cpar[i]));
+                } else {
+                    f = imul_nl(s0, S.cpar[lane - 3 * N]);
+                }
+                const ival fv = mk(__dmul_rd(f.lo, f.lo >= 0 ? il : ih), __dmul_ru(f.hi, f.hi >= 0 ? ih : il));
+                const mt vn = iv2mt(fv);
+                T[0][rowV + kc + 1] = vn;                                                    // v[kc+1] = f[kc]/(kc+1);  M[kc+1]
+                if (isV && kc + 2 <= p) {                                                    // u[kc+2] = v[kc+1]/(kc+2)
+                    const double jl = S.invlo[kc + 2], jh = S.invhi[kc + 2];
+                    const ival vi = mt2iv(vn);
+                    const ival fu = mk(__dmul_rd(vi.lo, vi.lo >= 0 ? jl : jh), __dmul_ru(vi.hi, vi.hi >= 0 ? jh : jl));
+                    const mt un = iv2mt(fu);
+                    T[0][rowU + kc + 2] = un;
+                    mt zn; zn.m = -un.m; zn.t = un.t;
+                    T[0][rowZ + kc + 2] = zn;
+                }
+            }
+        };
+        // Psi warp: scratch sums of order kc -> Pv[kc+1];  Pu[kc+1] = Pv[kc]/(kc+1)
+        auto combine_psi = [&](int kc) {
+            if (lane < N * D) {
+                const ival s0 = S.un.scratch[cs0], s1 = S.un.scratch[cs1], s2 = S.un.scratch[cs2];
+                const mt pvk = Tf[rowV + kc];
+                const double il = S.invlo[kc + 1], ih = S.invhi[kc + 1];
+                const ival sm = iadd(iadd(s0, s1), s2);
+                const ival fv = mk(__dmul_rd(sm.lo, sm.lo >= 0 ? il : ih), __dmul_ru(sm.hi, sm.hi >= 0 ? ih : il));
+                const ival vi = mt2iv(pvk);
+                const ival fu = mk(__dmul_rd(vi.lo, vi.lo >= 0 ? il : ih), __dmul_ru(vi.hi, vi.hi >= 0 ? ih : il));
+                T[0][rowV + kc + 1] = iv2mt(fv);
+                T[0][rowU + kc + 1] = iv2mt(fu);
+            }
+        };
+        for (int k = 0; k < p; k += 2) {
+            const bool two = k + 1 < p;                           // uniform: the block has a second order
             if (wq == 0) {
                 PROF(12);
                 TRC(100 + k);
-                // one pass for both task kinds: A lanes g, q of order k+1, B lanes the products g*w of order k
+                // A lanes: g, q of orders k+1, k+2;  B lanes: products g*w of orders k, k+1
                 const int isA = tA.kind() == 0;
                 const int kk = k + isA;
-                const int upto = (tA.kind() < 0 || (isA && kk > p - 1)) ? 0 : kk + 1;
-                const ival sum = acc_finish(run_partial(Tf, tA, kk, upto));
-                if (upto) {
+                const bool act0 = tA.kind() >= 0 && kk <= (isA ? p - 1 : p);
+                const bool act1 = tA.kind() >= 0 && kk + 1 <= p - 1;
+                acc4 s0, s1;
+                if (act0) {
+                    run_block(Tf, tA, kk, s0, s1);
+                    const ival sum = acc_finish(s0);
                     if (isA) { const mt gm = iv2mt(sum); T[0][tA.out() * KMAX + kk] = gm; if (gslot >= 0) S.un.scratch[gslot] = mt2iv(gm); }
                     else S.un.scratch[tA.out()] = sum;
                 }
                 __syncwarp();
                 PROF(8);
                 TRC(300 + k);
-                const bool isV = lane < 2 * N;
-                if (isV || (lane < 4 * N - 1 && k + 1 <= p - 1)) {      // v[k+1] (lanes < 2N) and M[k+1] (lanes 2N..4N-2)
-                    const ival s0 = imulk(S.un.scratch[cs0], mscale), s1 = S.un.scratch[cs1], s2 = S.un.scratch[cs2];
-                    const double il = isV ? S.invlo[k + 1] : 1.0, ih = isV ? S.invhi[k + 1] : 1.0;
-                    ival f;
-                    if (!anystr) {
-                        const SPar q0 = S.par[ap0], q1 = S.par[ap1], q2 = S.par[ap2];
-                        f = ineg(imul_pos3(s0, q0.pl, q0.ph, q0.neg));
-                        f = isub(f, imul_pos3(s1, q1.pl, q1.ph, q1.neg));
-                        f = isub(f, imul_pos3(s2, q2.pl, q2.ph, q2.neg));
-                    } else if (lane < 3 * N) {                // a parameter interval straddles zero: general products
-                        const int i = lane % N;
-                        f = ineg(imul_nl(s0, S.bpar[i]));
-                        if (i > 0)     f = isub(f, imul_nl(s1, S.cpar[i - 1]));
-                        if (i < N - 1) f = isub(f, imul_nl(s2, S.cpar[i]));
-                    } else {
-                        f = imul_nl(s0, S.cpar[lane - 3 * N]);
+                combine_phi(k);
+                if (two) {
+                    bar_pair();
+                    TRC(100 + k + 1);
+                    if (act1) {
+                        run_ends(Tf, tA, kk + 1, s1);
+                        const ival sum = acc_finish(s1);
+                        if (isA) { const mt gm = iv2mt(sum); T[0][tA.out() * KMAX + kk + 1] = gm; if (gslot >= 0) S.un.scratch[gslot] = mt2iv(gm); }
+                        else S.un.scratch[tA.out()] = sum;
                     }
-                    const ival fv = mk(__dmul_rd(f.lo, f.lo >= 0 ? il : ih), __dmul_ru(f.hi, f.hi >= 0 ? ih : il));
-                    const mt vn = iv2mt(fv);
-                    T[0][rowV + k + 1] = vn;                                                     // v[k+1] = f[k]/(k+1);  M[k+1]
-                    if (isV && k + 2 <= p) {                                                     // u[k+2] = v[k+1]/(k+2)
-                        const double jl = S.invlo[k + 2], jh = S.invhi[k + 2];
-                        const ival vi = mt2iv(vn);
-                        const ival fu = mk(__dmul_rd(vi.lo, vi.lo >= 0 ? jl : jh), __dmul_ru(vi.hi, vi.hi >= 0 ? jh : jl));
-                        const mt un = iv2mt(fu);
-                        T[0][rowU + k + 2] = un;
-                        mt zn; zn.m = -un.m; zn.t = un.t;
-                        T[0][rowZ + k + 2] = zn;
-                    }
+                    __syncwarp();
+                    TRC(300 + k + 1);
+                    combine_phi(k + 1);
                 }
             } else {
                 TRC(700 + k);
-                // variational tables: products M * Psi^u of order k -> Pv[k+1];  Pu[k+1] = Pv[k]/(k+1)
-                if (tA.kind() == 2) {          // this lane's pair of C tasks (same M-series, two columns of Psi)
-                    ival r0, r1;
-                    run_pair(Tf, tA, tB, k, r0, r1);
-                    S.un.scratch[tA.out()] = r0; S.un.scratch[tB.out()] = r1;
+                // variational tables: products M * Psi^u of orders k, k+1 (pairs of tasks sharing the M-series)
+                acc4 a0, a1, b0, b1, c0, c1, d0, d1;
+                if (tA.kind() == 2) {
+                    run_block_pair(Tf, tA, tB, k, a0, a1, b0, b1);
+                    S.un.scratch[tA.out()] = acc_finish(a0); S.un.scratch[tB.out()] = acc_finish(b0);
                 }
                 if (CROUNDS > 1 && tC.kind() == 2) {
-                    ival r0, r1;
-                    run_pair(Tf, tC, tD, k, r0, r1);
-                    S.un.scratch[tC.out()] = r0; S.un.scratch[tD.out()] = r1;
+                    run_block_pair(Tf, tC, tD, k, c0, c1, d0, d1);
+                    S.un.scratch[tC.out()] = acc_finish(c0); S.un.scratch[tD.out()] = acc_finish(d0);
                 }
                 __syncwarp();
                 TRC(800 + k);
-                if (lane < N * D) {
-                    const ival s0 = S.un.scratch[cs0], s1 = S.un.scratch[cs1], s2 = S.un.scratch[cs2];
-                    const mt pvk = Tf[rowV + k];
-                    const double il = S.invlo[k + 1], ih = S.invhi[k + 1];
-                    const ival sm = iadd(iadd(s0, s1), s2);
-                    const ival fv = mk(__dmul_rd(sm.lo, sm.lo >= 0 ? il : ih), __dmul_ru(sm.hi, sm.hi >= 0 ? ih : il));
-                    const ival vi = mt2iv(pvk);
-                    const ival fu = mk(__dmul_rd(vi.lo, vi.lo >= 0 ? il : ih), __dmul_ru(vi.hi, vi.hi >= 0 ? ih : il));
-                    T[0][rowV + k + 1] = iv2mt(fv);
-                    T[0][rowU + k + 1] = iv2mt(fu);
+                combine_psi(k);
+                if (two) {
+                    bar_pair();                                   // M[k+1] and Pu[k+1] are now in the tables
+                    TRC(700 + k + 1);
+                    if (tA.kind() == 2) {
+                        run_ends_pair(Tf, tA, tB, k + 1, a1, b1);
+                        S.un.scratch[tA.out()] = acc_finish(a1); S.un.scratch[tB.out()] = acc_finish(b1);
+                    }
+                    if (CROUNDS > 1 && tC.kind() == 2) {
+                        run_ends_pair(Tf, tC, tD, k + 1, c1, d1);
+                        S.un.scratch[tC.out()] = acc_finish(c1); S.un.scratch[tD.out()] = acc_finish(d1);
+                    }
+                    __syncwarp();
+                    TRC(800 + k + 1);
+                    combine_psi(k + 1);
                 }
             }
             PROF(9);
@@ -775,45 +842,32 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
         __syncthreads();                            // Fk complete; Psi tables and un.scratch are dead from here
         PROF(3);
         TRC(5);
-        // ---- grid loop (utils.cpp:219-252): evaluation task = (argument, frame row).  arguments:
-        //      [0, g]        point tau_i                  -> rows of F at the grid points
-        //      [g+1, 2g]     range [tau_i, tau_{i+1}]      -> rows of the range enclosure
-        //      [2g+1, 3g]    derivative over the same range
+        // ---- grid loop (utils.cpp:219-252): one Horner chain per frame ENTRY, two entries per lane.
+        //      warp 0: point enclosures F(tau_i), i = 1..g   (F(0) = Fk[0] exactly)       -> EV[i]
+        //      warp 1: range enclosures F([tau_i, tau_{i+1}]), i = 0..g-1                  -> EV[g+1+i]
+        //      The derivative enclosures are formed on demand by the deciding lane (deriv_entries), as in the reference
+        //      calculateDerivative is only reached when the rough test fails (topFrame.cpp:193-262).
         {
-            // argument 0 (tau = 0) needs no Horner pass: F(0) = F_0 exactly, read straight from Fk[0] below
-            const int nargs = 3 * g;
-            for (int t = tid; t < nargs * N; t += NT) {
-                const int arg = 1 + t / N, a = t % N;
-                const int kind = arg <= g ? 0 : (arg <= 2 * g ? 1 : 2);
-                const int gi = kind == 0 ? arg : (kind == 1 ? arg - (g + 1) : arg - (2 * g + 1));
-                const double tlo = S.gp[gi], thi = S.gp[gi < g ? gi + 1 : g];
-                ival acc[N];
-                if (kind == 0) {
-#pragma unroll
-                    for (int bb = 0; bb < N; bb++) acc[bb] = S.Fk[p][a][bb];
-                    for (int k = p - 1; k >= 0; k--) {
-#pragma unroll
-                        for (int bb = 0; bb < N; bb++) acc[bb] = horner_pt(acc[bb], tlo, S.Fk[k][a][bb]);
-                    }
-                } else if (kind == 1) {
-#pragma unroll
-                    for (int bb = 0; bb < N; bb++) acc[bb] = S.Fk[p][a][bb];
-                    for (int k = p - 1; k >= 0; k--) {
-#pragma unroll
-                        for (int bb = 0; bb < N; bb++) acc[bb] = horner_rg(acc[bb], tlo, thi, S.Fk[k][a][bb]);
-                    }
+            constexpr int NN = N * N;
+            const int E = g * NN;
+            const ival* const Fk0 = &S.Fk[0][0][0];
+            for (int e0 = lane; e0 < E; e0 += 64) {
+                const int e1 = e0 + 32;
+                const bool v1 = e1 < E;
+                const int ee1 = v1 ? e1 : e0;
+                const int c0 = e0 % NN, c1 = ee1 % NN, g0 = e0 / NN, g1 = ee1 / NN;
+                ival a0 = Fk0[p * NN + c0], a1 = Fk0[p * NN + c1];
+                if (wq == 0) {
+                    const double t0 = S.gp[g0 + 1], t1 = S.gp[g1 + 1];
+                    for (int k = p - 1; k >= 0; k--) { a0 = horner_pt(a0, t0, Fk0[k * NN + c0]); a1 = horner_pt(a1, t1, Fk0[k * NN + c1]); }
+                    EV[NN + e0] = a0;
+                    if (v1) EV[NN + e1] = a1;
                 } else {
-#pragma unroll
-                    for (int bb = 0; bb < N; bb++) acc[bb] = imulk(S.Fk[p][a][bb], p);
-                    for (int k = p - 1; k >= 1; k--) {
-#pragma unroll
-                        for (int bb = 0; bb < N; bb++) acc[bb] = horner_rg(acc[bb], tlo, thi, imulk(S.Fk[k][a][bb], k));
-                    }
-#pragma unroll
-                    for (int bb = 0; bb < N; bb++) acc[bb] = iadd(acc[bb], sym(S.rhoFd[bb]));
+                    const double l0 = S.gp[g0], h0 = S.gp[g0 + 1], l1 = S.gp[g1], h1 = S.gp[g1 + 1];
+                    for (int k = p - 1; k >= 0; k--) { a0 = horner_rg(a0, l0, h0, Fk0[k * NN + c0]); a1 = horner_rg(a1, l1, h1, Fk0[k * NN + c1]); }
+                    EV[(g + 1) * NN + e0] = a0;
+                    if (v1) EV[(g + 1) * NN + e1] = a1;
                 }
-#pragma unroll
-                for (int bb = 0; bb < N; bb++) EV[(arg * N + a) * N + bb] = acc[bb];
             }
         }
         __syncthreads();
@@ -847,7 +901,8 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
 #pragma unroll
                     for (int a = 0; a < N; a++)
 #pragma unroll
-                        for (int bb = 0; bb < N; bb++) { Fm[a][bb] = EV[((g + 1 + gi) * N + a) * N + bb]; Dm[a][bb] = EV[((2 * g + 1 + gi) * N + a) * N + bb]; }
+                        for (int bb = 0; bb < N; bb++) Fm[a][bb] = EV[((g + 1 + gi) * N + a) * N + bb];
+                    deriv_entries<N>(&S.Fk[0][0][0], S.rhoFd, p, tl, th, Dm);
                     dD = jacobi_derivative<N>(Fm, Dm);
                 }
                 decision = count_decide(timeI, dL, dR, dV, dD);

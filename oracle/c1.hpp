@@ -50,7 +50,15 @@ static inline ival acc_finish(const acc4& a) {
     if (!(R >= 0)) R = (R != R) ? R : 0.0;
     return ival(sub_rd(a.slo, R), add_ru(a.shi, R));
 }
-static inline void cauchy(acc4& a, const mt* x, const mt* y, int k) { for (int j = 0; j <= k; j++) acc_term(a, x[j], y[k - j]); }
+// Summation order of every Cauchy product sum_j x[j] y[k-j]:  interior terms j = 1..k-1 ascending, then the two end
+// terms j = 0 and j = k.  The end terms are the only ones that involve the order-k coefficients, so the GPU kernel can
+// accumulate the interior of order k+1 in the same pass (same operands in registers) as the sum of order k.
+template <class F> static inline void cauchy_order(int k, F term) {
+    for (int j = 1; j < k; j++) term(j);
+    term(0);
+    if (k >= 1) term(k);
+}
+static inline void cauchy(acc4& a, const mt* x, const mt* y, int k) { cauchy_order(k, [&](int j) { acc_term(a, x[j], y[k - j]); }); }
 // a / k for an integer k >= 1, as a product with the enclosure [rd(1/k), ru(1/k)] (no division in the hot loop:
 // a directed FP64 division is a ~100-instruction dependent chain on the GPU).  One ulp wider than a true division.
 struct InvK { double lo[MAXP + 3], hi[MAXP + 3]; InvK() { for (int k = 1; k < MAXP + 3; k++) { lo[k] = div_rd(1.0, (double)k); hi[k] = div_ru(1.0, (double)k); } } };
@@ -130,21 +138,20 @@ static inline void phi_tables(PhiTables& t, int n, int p, const ival* b, const i
         t.w0[i] = iv2mt(u0[i] - ival(0.5)); t.z0[i] = iv2mt(ival(1.0) - u0[i]);
     }
     for (int k = 0; k < p; k++) {
-        for (int i = 0; i < n; i++) {                 // g_i[k] = (u*z)[k], ascending j
+        for (int i = 0; i < n; i++) {                 // g_i[k] = (u*z)[k],  z[m] = -u[m] for m >= 1
             acc4 a;
-            for (int j = 0; j < k; j++) acc_term_neg(a, t.u[i][j], t.u[i][k - j]);
-            acc_term(a, t.u[i][k], t.z0[i]);
+            cauchy_order(k, [&](int j) { if (k - j == 0) acc_term(a, t.u[i][j], t.z0[i]); else acc_term_neg(a, t.u[i][j], t.u[i][k - j]); });
             t.g[i][k] = iv2mt(acc_finish(a));
         }
         for (int e = 0; e + 1 < n; e++) {             // q_e[k] = (w_e*w_{e+1})[k]
             acc4 a;
-            for (int j = 0; j <= k; j++) acc_term(a, j == 0 ? t.w0[e] : t.u[e][j], k - j == 0 ? t.w0[e + 1] : t.u[e + 1][k - j]);
+            cauchy_order(k, [&](int j) { acc_term(a, j == 0 ? t.w0[e] : t.u[e][j], k - j == 0 ? t.w0[e + 1] : t.u[e + 1][k - j]); });
             t.q[e][k] = iv2mt(acc_finish(a));
         }
         for (int i = 0; i < n; i++) {
             auto gw = [&](int gi) {
                 acc4 a;
-                for (int j = 0; j <= k; j++) acc_term(a, t.g[gi][j], k - j == 0 ? t.w0[i] : t.u[i][k - j]);
+                cauchy_order(k, [&](int j) { acc_term(a, t.g[gi][j], k - j == 0 ? t.w0[i] : t.u[i][k - j]); });
                 return acc_finish(a);
             };
             ival f = -(gw(i) * b[i]);

@@ -26,8 +26,8 @@ for w in range(2):
         t, m = int(a[w, i, 0] - t0), int(a[w, i, 1])
         if m >= 100:
             kind, k = m // 100, m % 100
-            if k not in (0, 1, 5, 10, 15, 19, 20): prev = t; continue
-            nm = {1: "phi loop top", 2: "phi pass done", 3: "phi B-last done", 4: "combine done (at bar)", 5: "after bar", 6: "psi start", 7: "psi M done", 8: "psi C done"}[kind] + " k=%d" % k
+            if k not in (0, 1, 4, 5, 10, 11, 14, 15, 18, 19, 20): prev = t; continue
+            nm = {1: "phi pass start", 2: "phi pass done", 3: "phi sums stored (combine start)", 4: "combine done (at bar)", 5: "after bar", 6: "psi start", 7: "psi pass start", 8: "psi sums stored (combine start)"}[kind] + " k=%d" % k
         else:
             nm = names[m]
         print("  %8d  (+%6d)  %s" % (t, t - (prev if prev is not None else t), nm))
