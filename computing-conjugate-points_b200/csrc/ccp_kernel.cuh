@@ -209,6 +209,7 @@ __device__ inline Majorant majorant(const ival* b, const ival* c, int p, double 
 
 __device__ __forceinline__ ival eval_pt(const mt* s, int p, double tau) {
     ival acc = mt2iv(s[p]);
+#pragma unroll 4
     for (int k = p - 1; k >= 0; k--) acc = horner_pt(acc, tau, mt2iv(s[k]));
     return acc;
 }
@@ -369,10 +370,12 @@ __device__ __forceinline__ void run_block(const mt* __restrict__ Tf, const TaskR
         const mt* pa = Tf + t.offA() + 1;
         const mt* pb = Tf + t.offB() + kk;
         mt xp = *pa;
-        acc_term(s1, xp, *pb);                                   // j = 1
-        pa++; pb--;
+        const mt y1 = *pb;
+        mt x = pa[1], y = pb[-1];                                // operands of the NEXT term are loaded one term ahead; the
+        acc_term(s1, xp, y1);                                    // j = 1     // last prefetch reads a valid, unused table slot
+        pa += 2; pb -= 2;
 #pragma unroll 2
-        for (int j = 2; j <= kk; j++) { const mt x = *pa, y = *pb; acc_term(s0, xp, y); acc_term(s1, x, y); xp = x; pa++; pb--; }
+        for (int j = 2; j <= kk; j++) { const mt xn = *pa, yn = *pb; acc_term(s0, xp, y); acc_term(s1, x, y); xp = x; x = xn; y = yn; pa++; pb--; }
         acc_term(s0, Tf[t.offa0()], Tf[t.offB() + kk]);
         acc_term(s0, xp, Tf[t.offb0()]);                         // xp = a[kk]
     } else {
@@ -393,13 +396,14 @@ __device__ __forceinline__ void run_block_pair(const mt* __restrict__ Tf, const 
         const mt* pa = Tf + t0.offA() + 1; const mt* pb = Tf + t0.offB() + kk; const mt* qb = Tf + t1.offB() + kk;
         mt xp = *pa;
         const mt yk = *pb, zk = *qb;
+        mt x = pa[1], y = pb[-1], z = qb[-1];
         acc_term(a1, xp, yk); acc_term(b1, xp, zk);              // j = 1
-        pa++; pb--; qb--;
+        pa += 2; pb -= 2; qb -= 2;
 #pragma unroll 2
         for (int j = 2; j <= kk; j++) {
-            const mt x = *pa, y = *pb, z = *qb;
+            const mt xn = *pa, yn = *pb, zn = *qb;
             acc_term(a0, xp, y); acc_term(b0, xp, z); acc_term(a1, x, y); acc_term(b1, x, z);
-            xp = x; pa++; pb--; qb--;
+            xp = x; x = xn; y = yn; z = zn; pa++; pb--; qb--;
         }
         acc_term(a0, x0, yk); acc_term(b0, x0, zk);
         acc_term(a0, xp, Tf[t0.offb0()]); acc_term(b0, xp, Tf[t1.offb0()]);
@@ -859,11 +863,13 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
                 ival a0 = Fk0[p * NN + c0], a1 = Fk0[p * NN + c1];
                 if (wq == 0) {
                     const double t0 = S.gp[g0 + 1], t1 = S.gp[g1 + 1];
+#pragma unroll 4
                     for (int k = p - 1; k >= 0; k--) { a0 = horner_pt(a0, t0, Fk0[k * NN + c0]); a1 = horner_pt(a1, t1, Fk0[k * NN + c1]); }
                     EV[NN + e0] = a0;
                     if (v1) EV[NN + e1] = a1;
                 } else {
                     const double l0 = S.gp[g0], h0 = S.gp[g0 + 1], l1 = S.gp[g1], h1 = S.gp[g1 + 1];
+#pragma unroll 4
                     for (int k = p - 1; k >= 0; k--) { a0 = horner_rg(a0, l0, h0, Fk0[k * NN + c0]); a1 = horner_rg(a1, l1, h1, Fk0[k * NN + c1]); }
                     EV[(g + 1) * NN + e0] = a0;
                     if (v1) EV[(g + 1) * NN + e1] = a1;

@@ -5,11 +5,11 @@ cp $L /tmp/new.so
 for rep in 1 2; do
   for v in "$@" new; do
     if [ $v = new ]; then cp /tmp/new.so $L; else cp ab/$v.so $L; fi
-    echo -n "$v: "; python scripts/gpu_one.py 1024 | cut -d' ' -f1-8
+    echo -n "$v: "; CCP_REPS=3 python scripts/gpu_one.py 1024 | cut -d' ' -f1-14
   done
 done
 for v in "$@" new; do
   if [ $v = new ]; then cp /tmp/new.so $L; else cp ab/$v.so $L; fi
-  echo -n "$v 148: "; python scripts/gpu_one.py 148 | cut -d' ' -f1-8
+  echo -n "$v 148: "; CCP_REPS=3 python scripts/gpu_one.py 148 | cut -d' ' -f1-14
 done
 cp /tmp/new.so $L
