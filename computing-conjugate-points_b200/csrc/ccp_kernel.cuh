@@ -846,34 +846,45 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
         __syncthreads();                            // Fk complete; Psi tables and un.scratch are dead from here
         PROF(3);
         TRC(5);
-        // ---- grid loop (utils.cpp:219-252): one Horner chain per frame ENTRY, two entries per lane.
+        // ---- grid loop (utils.cpp:219-252).  A lane owns ONE frame entry c and every (32/N^2)-th grid point: each coefficient
+        //      Fk[k][c] is loaded once and feeds PPL independent Horner chains (shared-memory loads, not DFMAs, bound this loop).
         //      warp 0: point enclosures F(tau_i), i = 1..g   (F(0) = Fk[0] exactly)       -> EV[i]
         //      warp 1: range enclosures F([tau_i, tau_{i+1}]), i = 0..g-1                  -> EV[g+1+i]
         //      The derivative enclosures are formed on demand by the deciding lane (deriv_entries), as in the reference
         //      calculateDerivative is only reached when the rough test fails (topFrame.cpp:193-262).
         {
-            constexpr int NN = N * N;
-            const int E = g * NN;
-            const ival* const Fk0 = &S.Fk[0][0][0];
-            for (int e0 = lane; e0 < E; e0 += 64) {
-                const int e1 = e0 + 32;
-                const bool v1 = e1 < E;
-                const int ee1 = v1 ? e1 : e0;
-                const int c0 = e0 % NN, c1 = ee1 % NN, g0 = e0 / NN, g1 = ee1 / NN;
-                ival a0 = Fk0[p * NN + c0], a1 = Fk0[p * NN + c1];
-                if (wq == 0) {
-                    const double t0 = S.gp[g0 + 1], t1 = S.gp[g1 + 1];
-#pragma unroll 4
-                    for (int k = p - 1; k >= 0; k--) { a0 = horner_pt(a0, t0, Fk0[k * NN + c0]); a1 = horner_pt(a1, t1, Fk0[k * NN + c1]); }
-                    EV[NN + e0] = a0;
-                    if (v1) EV[NN + e1] = a1;
-                } else {
-                    const double l0 = S.gp[g0], h0 = S.gp[g0 + 1], l1 = S.gp[g1], h1 = S.gp[g1 + 1];
-#pragma unroll 4
-                    for (int k = p - 1; k >= 0; k--) { a0 = horner_rg(a0, l0, h0, Fk0[k * NN + c0]); a1 = horner_rg(a1, l1, h1, Fk0[k * NN + c1]); }
-                    EV[(g + 1) * NN + e0] = a0;
-                    if (v1) EV[(g + 1) * NN + e1] = a1;
+            constexpr int NN = N * N, NGRP = 32 / NN, PPL = (GMAX + NGRP - 1) / NGRP;
+            const int c = lane % NN, grp = lane / NN;
+            if (grp < NGRP) {
+                const ival* q = &S.Fk[0][0][0] + p * NN + c;
+                ival acc[PPL];
+                double tl[PPL], th[PPL];
+                const ival top = *q;
+#pragma unroll
+                for (int j = 0; j < PPL; j++) {
+                    const int i = grp + j * NGRP, ic = i < g ? i : g - 1;       // point ic+1 (warp 0) / range [ic, ic+1] (warp 1)
+                    acc[j] = top; tl[j] = S.gp[ic]; th[j] = S.gp[ic + 1];
                 }
+                if (wq == 0) {
+#pragma unroll 2
+                    for (int k = p - 1; k >= 0; k--) {
+                        q -= NN;
+                        const ival ck = *q;
+#pragma unroll
+                        for (int j = 0; j < PPL; j++) acc[j] = horner_pt(acc[j], th[j], ck);
+                    }
+                } else {
+#pragma unroll 2
+                    for (int k = p - 1; k >= 0; k--) {
+                        q -= NN;
+                        const ival ck = *q;
+#pragma unroll
+                        for (int j = 0; j < PPL; j++) acc[j] = horner_rg(acc[j], tl[j], th[j], ck);
+                    }
+                }
+                const int base = (wq == 0 ? 1 : g + 1) * NN + c;
+#pragma unroll
+                for (int j = 0; j < PPL; j++) { const int i = grp + j * NGRP; if (i < g) EV[base + i * NN] = acc[j]; }
             }
         }
         __syncthreads();
