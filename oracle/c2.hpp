@@ -1,0 +1,417 @@
+// oracle/c2.hpp -- TEST INFRASTRUCTURE (CPU oracle, mode "c2").  Not part of the product path.
+//
+// Mode c1 plus FIRST-ORDER TRACKING of the dependence of the frame on the initial box of the front
+// (the reference gets this from the off-diagonal block of the 4n x 4n Jacobian of f_linearize that
+// CAPD's C0Rect2Set carries along, propagateManifold.cpp:110-114).
+//
+//   phi-set     x + C r0 + r                                   (as c1)
+//   Psi tables  at the CENTRE x (thin), order p                (c1: over the hull)
+//   step Jacobian over the set, mean-value form in the r0-directions c_j = C e_j:
+//       J(phi) in Jc + sum_j Xi_j[X] r0_j + E_r ,   Xi_j[X] = enclosure over the hull of D(DPhi_h)[c_j]
+//     Xi_j is the second variation; with N(t) = DM(u(t))[Psi^u(t) c_j] its Taylor expansion to h^3 is closed:
+//       Xi^u = [ h^2 N0/2 + h^3 N1/6                     | h^3 N0/6          ]
+//       Xi^v = [ h N0 + h^2 N1/2 + h^3 (N2 + (M0 N0 + N0 M0)/2)/3 | h^2 N0/2 + h^3 N1/3 ]
+//     plus a majorant remainder gamma_4 h^4 |c_j|_1 per entry (c2_majorant).
+//   unstable columns of P = Dphi_t A_u:   T = Tc + sum_j Theta_j r0_j + R   (Tc, Theta_j points, R interval)
+//       T+ = J(phi) T  =>  Tc+ = mid(Jc Tc),  Theta_j+ = mid(Jc Theta_j + Xi_j Tc),  R+ = everything else
+//   stable columns Ps (they only enter through Err ~ 1e-5): interval matrix, Ps+ = J[X] Ps  (as c1)
+//   frame  W = T + Ps Err ;  frame tables F_k = Psi_c^u_k W + one box for (Psi(phi) - Psi(x)) W.
+#pragma once
+#include "c1.hpp"
+
+namespace orc {
+namespace c2 {
+
+using namespace c1;
+
+struct Maj2 { double g1, g5; };     // per unit |c|_1: |Xi(tau)| <= g1 tau ;  |Xi(tau) - sum_{k<=4} Xi_k tau^k| <= g5 tau^5
+
+// Scalar majorant of the second variation xi' = Df xi + D^2f[Psi c, psi] on the a-priori box G (see c1_majorant
+// for w, g, Mh, be).  |N(d)|_inf <= 6 (bh+cs) |w| |d|,  |d| <= beta |c|_1.
+static inline Maj2 c2_majorant(int n, const ival* b, const ival* c, double h) {
+    double bh = 0, cs = 0;
+    for (int i = 0; i < n; i++) bh = std::max(bh, mag(b[i]));
+    for (int i = 0; i < n; i++) { double s = 0; if (i > 0) s = add_ru(s, mag(c[i - 1])); if (i < n - 1) s = add_ru(s, mag(c[i])); cs = std::max(cs, s); }
+    const double W0 = 0.5625, G0 = 0.25, V0 = 0.5;
+    const int K = 5;
+    double bc = add_ru(bh, cs);
+    double F0 = mul_ru(mul_ru(bc, G0), W0);
+    double w[K + 2], g[K + 2], be[K + 2], Mh[K + 2], ga[K + 2];
+    w[0] = W0; g[0] = G0; w[1] = std::max(V0, F0);
+    for (int k = 1; k <= K; k++) {
+        double s = 0; for (int j = 0; j <= k; j++) s = fma_ru(w[j], w[k - j], s);
+        g[k] = s;
+        double f = 0; for (int j = 0; j <= k; j++) f = fma_ru(g[j], w[k - j], f);
+        f = mul_ru(bc, f);
+        w[k + 1] = div_ru(std::max(w[k], f), (double)(k + 1));
+    }
+    double M0 = add_ru(add_ru(mul_ru(bh, 0.75), mul_ru(cs, 0.25)), mul_ru(mul_ru(2.0, cs), mul_ru(W0, W0)));
+    double a = std::max(1.0, M0), ah = mul_ru(a, h);
+    be[0] = add_ru(add_ru(1.0, ah), mul_ru(ah, ah));
+    Mh[0] = M0;
+    double k3 = mul_ru(3.0, bc);
+    for (int k = 1; k <= K; k++) Mh[k] = mul_ru(k3, g[k]);
+    for (int k = 0; k <= K; k++) {
+        double s = 0; for (int j = 0; j <= k; j++) s = fma_ru(Mh[j], be[k - j], s);
+        be[k + 1] = div_ru(std::max(be[k], s), (double)(k + 1));
+    }
+    const double H6 = mul_ru(6.0, bc);
+    // a-priori bound of |xi(tau)|, tau in [0,h]:  tau e^{a tau} (6 bc W0) beta0^2 <= h beta0^3 6 bc W0
+    ga[0] = mul_ru(mul_ru(h, mul_ru(be[0], mul_ru(be[0], be[0]))), mul_ru(H6, W0));
+    double bb[K + 2];                                       // (beta*beta)_k
+    for (int k = 0; k <= K; k++) { double s = 0; for (int j = 0; j <= k; j++) s = fma_ru(be[j], be[k - j], s); bb[k] = s; }
+    for (int k = 0; k < K; k++) {
+        double s = 0; for (int j = 0; j <= k; j++) s = fma_ru(Mh[j], ga[k - j], s);
+        double f = 0; for (int j = 0; j <= k; j++) f = fma_ru(w[j], bb[k - j], f);
+        s = fma_ru(H6, f, s);
+        ga[k + 1] = div_ru(std::max(ga[k], s), (double)(k + 1));
+    }
+    Maj2 m; m.g1 = ga[1]; m.g5 = ga[5];
+    return m;
+}
+
+
+static inline ival half(const ival& a) { return ival(0.5 * a.lo, 0.5 * a.hi); }
+// entry (i,k) of the symmetric tridiagonal matrix (diag dg, off-diagonal od); zero elsewhere
+static inline ival tri(const ival* dg, const ival* od, int i, int k) {
+    if (i == k) return dg[i];
+    if (k == i + 1) return od[i];
+    if (k == i - 1) return od[k];
+    return ival(0.0);
+}
+// row i of (tridiagonal) * vector
+static inline ival tri_row(const ival* dg, const ival* od, const ival* v, int n, int i) {
+    ival a = dg[i] * v[i];
+    if (i > 0)     a = a + od[i - 1] * v[i - 1];
+    if (i < n - 1) a = a + od[i] * v[i + 1];
+    return a;
+}
+// entry (i,k) of the product of two tridiagonal matrices: l runs over max(i,k)-1 .. min(i,k)+1 ascending
+static inline ival tri_mul(const ival* ad, const ival* ao, const ival* bd, const ival* bo, int n, int i, int k) {
+    ival a(0.0);
+    for (int l = 0; l < n; l++) {
+        if (l < i - 1 || l > i + 1 || l < k - 1 || l > k + 1) continue;
+        a = a + tri(ad, ao, i, l) * tri(bd, bo, l, k);
+    }
+    return a;
+}
+// acc*h + c for a point h > 0
+static inline ival horner_hp(const ival& acc, double h, const ival& c) { return ival(fma_rd(acc.lo, h, c.lo), fma_ru(acc.hi, h, c.hi)); }
+
+// S0 = sum_j Theta_j r0_j ;  W = ((Tc + S0) + R) + Ps Err
+static inline void frame_of_state(int n, const double (*Tc)[MAXN], const double (*Th)[MAXD][MAXN], const ival (*R)[MAXN], const ival (*Ps)[MAXN],
+                                  const ival* r0, const ival (*Err)[MAXN], ival (*S0)[MAXN], ival (*W)[MAXN]) {
+    const int D = 2 * n;
+    for (int cc = 0; cc < D; cc++) for (int bb = 0; bb < n; bb++) {
+        ival a(0.0);
+        for (int j = 0; j < D; j++) a = a + ival(Th[j][cc][bb]) * r0[j];
+        S0[cc][bb] = a;
+        ival w = (ival(Tc[cc][bb]) + a) + R[cc][bb];
+        for (int j = 0; j < n; j++) w = w + Ps[cc][j] * Err[j][bb];
+        W[cc][bb] = w;
+    }
+}
+
+static inline void run_front(const ccp_front_desc& d, ccp_front_result& res, std::vector<ccp_series_rec>* series) {
+    std::memset(&res, 0, sizeof(res));
+    res.first_failure = -1;
+    const int n = d.n, D = 2 * n, p = d.order, g = d.grid;
+    if (n < 2 || n > MAXN || p < 2 || p > MAXP || g < 1 || g > MAXG || d.step_log2 < 1 || d.step_log2 > 20 || !(d.L_minus > 0) || !std::isfinite(d.L_minus)) {
+        res.status = CCP_ST_BAD_DESC; return;
+    }
+    const double h = std::ldexp(1.0, -d.step_log2);
+    ival b[MAXN], c[MAXN];
+    for (int i = 0; i < n; i++) b[i] = fromc(d.b[i]);
+    for (int i = 0; i < n - 1; i++) c[i] = fromc(d.c[i]);
+    const int S = step_count(d.L_minus, h);
+    res.steps = S; res.series_length = S * g;
+    Majorant mj = c1_majorant(n, b, c, p, h);
+    if (!mj.ok) { res.status = CCP_ST_ENCLOSURE; return; }
+    const Maj2 m2 = c2_majorant(n, b, c, h);
+
+    double x[MAXD], C[MAXD][MAXD];
+    ival r0[MAXD], r[MAXD], Err[MAXN][MAXN];
+    double Tc[MAXD][MAXN], Th[MAXD][MAXD][MAXN];           // Th[j] = Theta_j
+    ival R[MAXD][MAXN], Ps[MAXD][MAXN];
+    for (int i = 0; i < D; i++) {
+        ival pi = fromc(d.p_i[i]);
+        x[i] = mid_ru(pi); r[i] = pi - ival(x[i]); r0[i] = fromc(d.Uxy[i]);
+        for (int j = 0; j < D; j++) C[i][j] = d.A_u[i * CCP_MAX_DIM + j];
+        for (int k = 0; k < n; k++) { Tc[i][k] = C[i][k]; Ps[i][k] = ival(C[i][n + k]); R[i][k] = ival(0.0); }
+        for (int j = 0; j < D; j++) for (int k = 0; k < n; k++) Th[j][i][k] = 0.0;
+    }
+    for (int j = 0; j < n; j++) for (int k = 0; k < n; k++) Err[j][k] = fromc(d.Eu_err[j * CCP_MAX_N + k]);
+
+    Counter cnt;
+    ival tprev(0.0);
+    static thread_local PhiTables ct;
+    static thread_local PsiTables ps;
+    ival Fk[MAXP + 1][MAXN][MAXN];
+    ival FRprev[MAXN][MAXN];
+
+    for (int s = 0; s < S; s++) {
+        const bool last = (s == S - 1);
+        const double hs = last ? sub_ru(d.L_minus, tprev.hi) : h;
+        ival X[MAXD];
+        for (int i = 0; i < D; i++) {
+            ival a(x[i]);
+            for (int j = 0; j < D; j++) a = a + ival(C[i][j]) * r0[j];
+            X[i] = a + r[i];
+        }
+        bool inside = true, fin = true;
+        for (int i = 0; i < n; i++) {
+            inside = inside && subset(X[i], mj.Gs_u) && subset(X[n + i], mj.Gs_v);
+            fin = fin && finite(X[i]) && finite(X[n + i]);
+        }
+        if (!fin) { res.status = CCP_ST_NONFINITE; break; }
+        if (!inside) { res.status = CCP_ST_ENCLOSURE; break; }
+        // ---- centre tables (order p): phi and Psi along the centre trajectory ----
+        ival xc[MAXD]; for (int i = 0; i < D; i++) xc[i] = ival(x[i]);
+        phi_tables(ct, n, p, b, c, xc, xc + n);
+        psi_tables(ps, ct, n, p, b, c);
+        // ---- hull, low order (plain inf-sup arithmetic): w_k = Taylor coefficients of u - 1/2 (k <= 3), M0, M1 over [X] ----
+        ival w[4][MAXN], g0[MAXN], Md0[MAXN], Mo0[MAXN], Md1[MAXN], Mo1[MAXN];
+        for (int i = 0; i < n; i++) { w[0][i] = X[i] - ival(0.5); g0[i] = X[i] * (ival(1.0) - X[i]); w[1][i] = X[n + i]; }
+        for (int i = 0; i < n; i++) {
+            ival f = -((g0[i] * w[0][i]) * b[i]);
+            if (i > 0)     f = f - (g0[i - 1] * w[0][i]) * c[i - 1];
+            if (i < n - 1) f = f - (g0[i + 1] * w[0][i]) * c[i];
+            w[2][i] = half(f);
+            ival dd = -(b[i] * (mulk(g0[i], 3) - ival(0.5)));
+            if (i > 0)     dd = dd - c[i - 1] * g0[i - 1];
+            if (i < n - 1) dd = dd - c[i] * g0[i + 1];
+            Md0[i] = dd;
+            if (i < n - 1) Mo0[i] = mulk(w[0][i] * w[0][i + 1], 2) * c[i];
+            ival m1 = mulk(b[i] * (w[0][i] * w[1][i]), 6);
+            if (i > 0)     m1 = m1 + mulk(c[i - 1] * (w[0][i - 1] * w[1][i - 1]), 2);
+            if (i < n - 1) m1 = m1 + mulk(c[i] * (w[0][i + 1] * w[1][i + 1]), 2);
+            Md1[i] = m1;
+            if (i < n - 1) Mo1[i] = mulk(c[i] * (w[0][i] * w[1][i + 1] + w[1][i] * w[0][i + 1]), 2);
+        }
+        for (int i = 0; i < n; i++) w[3][i] = divk(tri_row(Md0, Mo0, w[1], n, i), 6);
+        double rnorm = 0; for (int i = 0; i < D; i++) rnorm = add_ru(rnorm, mag(r[i]));
+        const double hs2 = mul_ru(hs, hs), hs5 = mul_ru(mul_ru(hs2, hs2), hs);
+        // ---- second variation over the hull: directions c_j (weight r0_j, tracked), j < D, and the box r (weight 1) ----
+        static thread_local ival Xi[MAXD + 1][MAXD][MAXD];     // Xi[j][row][col]
+        ival dJ[MAXD][MAXD];                                    // sum_j Xi_j r0_j + Xi_D  : encloses DPhi(phi) - DPhi(x) on the set
+        double magXu[MAXN][MAXD], magXv[MAXN][MAXD];            // sup over tau in [0,hs] of |Psi(tau;phi) - Psi(tau;x)|, u rows / v rows
+        for (int i = 0; i < D; i++) for (int k = 0; k < D; k++) dJ[i][k] = ival(0.0);
+        for (int i = 0; i < n; i++) for (int k = 0; k < D; k++) { magXu[i][k] = 0.0; magXv[i][k] = 0.0; }
+        for (int j = 0; j <= D; j++) {
+            ival dd[4][MAXN];
+            double c1n = 0;
+            if (j < D) { for (int i = 0; i < D; i++) c1n = add_ru(c1n, std::fabs(C[i][j])); for (int i = 0; i < n; i++) { dd[0][i] = ival(C[i][j]); dd[1][i] = ival(C[n + i][j]); } }
+            else       { c1n = rnorm; for (int i = 0; i < n; i++) { dd[0][i] = r[i]; dd[1][i] = r[n + i]; } }
+            for (int i = 0; i < n; i++) dd[2][i] = half(tri_row(Md0, Mo0, dd[0], n, i));
+            for (int i = 0; i < n; i++) dd[3][i] = divk(tri_row(Md1, Mo1, dd[0], n, i) + tri_row(Md0, Mo0, dd[1], n, i), 6);
+            auto wd = [&](int i, int m, int k) -> ival {          // (w_i d_m)_k
+                ival a = w[0][i] * dd[k][m];
+                for (int q = 1; q <= k; q++) a = a + w[q][i] * dd[k - q][m];
+                return a;
+            };
+            ival Nd[4][MAXN], No[4][MAXN];
+            for (int k = 0; k < 4; k++) for (int i = 0; i < n; i++) {
+                ival a = mulk(b[i] * wd(i, i, k), 6);
+                if (i > 0)     a = a + mulk(c[i - 1] * wd(i - 1, i - 1, k), 2);
+                if (i < n - 1) a = a + mulk(c[i] * wd(i + 1, i + 1, k), 2);
+                Nd[k][i] = a;
+                if (i < n - 1) No[k][i] = mulk(c[i] * (wd(i + 1, i, k) + wd(i, i + 1, k)), 2);
+            }
+            const double rem = mul_ru(mul_ru(m2.g5, hs5), c1n);
+            const ival wj = j < D ? r0[j] : ival(1.0);
+            const double wm = mag(wj);
+            for (int i = 0; i < n; i++) for (int k = 0; k < n; k++) {
+                const int dk = i > k ? i - k : k - i;
+                ival cf[4][4];                                    // cf[block][order-1]: blocks 0 UU, 1 UV, 2 VU, 3 VV
+                for (int q = 0; q < 4; q++) for (int e = 0; e < 4; e++) cf[q][e] = ival(0.0);
+                if (dk <= 2) {
+                    const ival N0 = tri(Nd[0], No[0], i, k), N1 = tri(Nd[1], No[1], i, k), N2 = tri(Nd[2], No[2], i, k), N3 = tri(Nd[3], No[3], i, k);
+                    const ival P00 = tri_mul(Md0, Mo0, Nd[0], No[0], n, i, k) + tri_mul(Nd[0], No[0], Md0, Mo0, n, i, k);
+                    const ival P01 = tri_mul(Md0, Mo0, Nd[1], No[1], n, i, k) + tri_mul(Nd[0], No[0], Md1, Mo1, n, i, k);
+                    const ival P10 = tri_mul(Md1, Mo1, Nd[0], No[0], n, i, k) + tri_mul(Nd[1], No[1], Md0, Mo0, n, i, k);
+                    const ival X3 = divk(N2 + half(P00), 3);      // Xi^v_3, u columns
+                    cf[0][1] = half(N0); cf[0][2] = divk(N1, 6); cf[0][3] = divk(X3, 4);
+                    cf[1][2] = divk(N0, 6); cf[1][3] = divk(N1, 12);
+                    cf[2][0] = N0; cf[2][1] = half(N1); cf[2][2] = X3; cf[2][3] = divk(N3 + divk(P01, 6) + half(P10), 4);
+                    cf[3][1] = half(N0); cf[3][2] = divk(N1, 3); cf[3][3] = divk(N2 + divk(P00, 6), 4);
+                }
+                for (int q = 0; q < 4; q++) {
+                    ival acc = cf[q][3]; double am = mag(cf[q][3]);
+                    for (int e = 2; e >= 0; e--) { acc = horner_hp(acc, hs, cf[q][e]); am = fma_ru(am, hs, mag(cf[q][e])); }
+                    acc = horner_hp(acc, hs, ival(0.0)); am = mul_ru(am, hs);
+                    const int row = (q >> 1) * n + i, col = (q & 1) * n + k;
+                    Xi[j][row][col] = acc + sym(rem);
+                    dJ[row][col] = dJ[row][col] + Xi[j][row][col] * wj;
+                    double& mg = (q >> 1) ? magXv[i][col] : magXu[i][col];
+                    mg = fma_ru(add_ru(am, rem), wm, mg);
+                }
+            }
+        }
+        // ---- frame at step start:  W = (Tc + sum_j Theta_j r0_j + R) + Ps Err ----
+        ival S0[MAXD][MAXN], Ws[MAXD][MAXN]; mt Wm[MAXD][MAXN];
+        frame_of_state(n, Tc, Th, R, Ps, r0, Err, S0, Ws);
+        for (int cc = 0; cc < D; cc++) for (int bb = 0; bb < n; bb++) Wm[cc][bb] = iv2mt(Ws[cc][bb]);
+        // truncation box of the centre tables and box for (Psi(tau;phi) - Psi(tau;x)) W, tau in [0,hs]; same for the derivative
+        double boxF[MAXN][MAXN], boxFd[MAXN][MAXN];
+        for (int bb = 0; bb < n; bb++) {
+            double sm = 0; for (int cc = 0; cc < D; cc++) sm = add_ru(sm, mag(Ws[cc][bb]));
+            const double rhoF = mul_ru(mj.rho_psi, sm), rhoFd = mul_ru(mj.rho_psi_d, sm);
+            for (int a = 0; a < n; a++) {
+                double s0 = rhoF, s1 = rhoFd;
+                for (int cc = 0; cc < D; cc++) { s0 = fma_ru(magXu[a][cc], mag(Ws[cc][bb]), s0); s1 = fma_ru(magXv[a][cc], mag(Ws[cc][bb]), s1); }
+                boxF[a][bb] = s0; boxFd[a][bb] = s1;
+            }
+        }
+        for (int k = 0; k <= p; k++) for (int a = 0; a < n; a++) for (int bb = 0; bb < n; bb++) {
+            acc4 ac; for (int cc = 0; cc < D; cc++) acc_term(ac, ps.Pu[a][cc][k], Wm[cc][bb]);
+            ival f = acc_finish(ac);
+            if (k == 0) f = f + sym(boxF[a][bb]);
+            Fk[k][a][bb] = f;
+        }
+        // ---- grid loop + topFrame (as c1) ----
+        double gp[MAXG + 1]; grid_points(hs, g, gp);
+        Frame FL, FR, FV, FD;
+        for (int i = 0; i < g; i++) {
+            const double tl = gp[i], th = gp[i + 1];
+            for (int a = 0; a < n; a++) for (int bb = 0; bb < n; bb++) {
+                if (i == 0) {
+                    ival acc = Fk[p][a][bb];
+                    for (int k = p - 1; k >= 0; k--) acc = horner_pt(acc, tl, Fk[k][a][bb]);
+                    FL[a][bb] = acc;
+                } else FL[a][bb] = FRprev[a][bb];
+                ival acc = Fk[p][a][bb];
+                for (int k = p - 1; k >= 0; k--) acc = horner_pt(acc, th, Fk[k][a][bb]);
+                FR[a][bb] = acc; FRprev[a][bb] = acc;
+                acc = Fk[p][a][bb];
+                for (int k = p - 1; k >= 0; k--) acc = horner_rg(acc, tl, th, Fk[k][a][bb]);
+                FV[a][bb] = acc;
+                acc = mulk(Fk[p][a][bb], p);
+                for (int k = p - 1; k >= 1; k--) acc = horner_rg(acc, tl, th, mulk(Fk[k][a][bb], k));
+                FD[a][bb] = acc + sym(boxFd[a][bb]);
+            }
+            ival time(add_rd(tprev.lo, tl), add_ru(tprev.hi, th));
+            ival dL = detN(FL, n), dR = detN(FR, n), dV = detN(FV, n);
+            const ival LR = dL * dR;
+            const bool need_D = (series != nullptr) || !(LR.lo > 0 && definite(dV));
+            ival dD = need_D ? jacobi_derivative(FV, FD, n) : ival(0.0);
+            int idx = s * g + i;
+            count_step(cnt, idx, time, dL, dR, dV, dD);
+            if (series) { ccp_series_rec rec; rec.time = toc(time); rec.det_L = toc(dL); rec.det_R = toc(dR); rec.det_V = toc(dV); rec.det_D = toc(dD); series->push_back(rec); }
+            if (idx == 0) res.det_first = toc(dV);
+            if (idx == S * g - 1) res.det_last = toc(dV);
+            if (!(finite(dL) && finite(dR) && finite(dV) && finite(dD))) res.status = CCP_ST_NONFINITE;
+        }
+        // ---- step: y = Phi(x), Jc = DPhi(x) ----
+        ival y[MAXD], Jc[MAXD][MAXD], J[MAXD][MAXD];
+        for (int i = 0; i < n; i++) {
+            y[i] = eval_pt(ct.u[i], p, hs) + sym(mj.rho_phi);
+            y[n + i] = eval_pt(ct.v[i], p, hs) + sym(mj.rho_phi);
+            for (int cc = 0; cc < D; cc++) {
+                Jc[i][cc] = eval_pt(ps.Pu[i][cc], p, hs) + sym(mj.rho_psi);
+                Jc[n + i][cc] = eval_pt(ps.Pv[i][cc], p, hs) + sym(mj.rho_psi);
+            }
+        }
+        // the mean-value form of the phi-set update needs DPhi on the segments [x, phi]: Jc + s dJ, s in [0,1]
+        for (int i = 0; i < D; i++) for (int k = 0; k < D; k++) J[i][k] = Jc[i][k] + hull(dJ[i][k], ival(0.0));
+        // phi' = (v, F(u)) over a sub-interval [tl,th] of the step and over the whole set (last column of the first/last frame,
+        // topFrame.cpp:265-331):  phi(tau) in phi_c(tau) + Psi(tau; xi)(phi0 - x),  |Psi(tau;xi) - Psi_c(tau)| <= g1 tau |phi0 - x|_1
+        auto phi_prime = [&](double tl, double th, ival* du, ival* dv) {
+            ival dev[MAXD]; double dn = 0;
+            for (int i = 0; i < D; i++) { ival a(0.0); for (int j = 0; j < D; j++) a = a + ival(C[i][j]) * r0[j]; dev[i] = a + r[i]; dn = add_ru(dn, mag(dev[i])); }
+            const double pb = add_ru(mj.rho_psi, mul_ru(mul_ru(m2.g1, hs), dn));
+            ival uu[MAXN], gg[MAXN];
+            for (int i = 0; i < n; i++) {
+                ival a = eval_rg(ct.u[i], p, tl, th) + sym(mj.rho_phi), bq = eval_rg(ct.v[i], p, tl, th) + sym(mj.rho_phi);
+                for (int cc = 0; cc < D; cc++) {
+                    a = a + (eval_rg(ps.Pu[i][cc], p, tl, th) + sym(pb)) * dev[cc];
+                    bq = bq + (eval_rg(ps.Pv[i][cc], p, tl, th) + sym(pb)) * dev[cc];
+                }
+                uu[i] = a; du[i] = bq; gg[i] = a * (ival(1.0) - a);
+            }
+            for (int i = 0; i < n; i++) {
+                const ival wi = uu[i] - ival(0.5);
+                ival f = -((gg[i] * wi) * b[i]);
+                if (i > 0)     f = f - (gg[i - 1] * wi) * c[i - 1];
+                if (i < n - 1) f = f - (gg[i + 1] * wi) * c[i];
+                dv[i] = f;
+            }
+        };
+        if (s == 0) {     // topFrame::getFirstFrame (topFrame.cpp:301-331)
+            for (int rr = 0; rr < D; rr++) for (int k = 0; k < n; k++) res.first_frame[rr * (CCP_MAX_N + 1) + k] = toc(Ws[rr][k]);
+            ival du[MAXN], dv[MAXN]; phi_prime(gp[0], gp[1], du, dv);
+            for (int i = 0; i < n; i++) {
+                res.first_frame[i * (CCP_MAX_N + 1) + n] = toc(du[i]);
+                res.first_frame[(n + i) * (CCP_MAX_N + 1) + n] = toc(dv[i]);
+            }
+        }
+        if (last) {
+            const int ld = CCP_MAX_N + 2;
+            ival du[MAXN], dv[MAXN]; phi_prime(gp[g - 1], gp[g], du, dv);
+            for (int i = 0; i < n; i++) {
+                res.last_frame[i * ld + n] = toc(du[i]);
+                res.last_frame[(n + i) * ld + n] = toc(dv[i]);
+            }
+        }
+        if (res.status != CCP_OK) break;          // non-finite determinant: stop before the set update
+        // ---- set update of the front (as c1, with J = Jc + [0,1] dJ) ----
+        double xn[MAXD], Cn[MAXD][MAXD]; ival rn[MAXD], JC[MAXD][MAXD];
+        for (int i = 0; i < D; i++) xn[i] = mid_ru(y[i]);
+        for (int i = 0; i < D; i++) for (int j = 0; j < D; j++) {
+            ival a(0.0); for (int k = 0; k < D; k++) a = a + J[i][k] * ival(C[k][j]);
+            JC[i][j] = a; Cn[i][j] = mid_ru(a);
+        }
+        for (int i = 0; i < D; i++) {
+            ival z = y[i] - ival(xn[i]);
+            for (int j = 0; j < D; j++) z = z + (JC[i][j] - ival(Cn[i][j])) * r0[j];
+            ival a(0.0); for (int j = 0; j < D; j++) a = a + J[i][j] * r[j];
+            rn[i] = a + z;
+        }
+        // ---- frame update:  T+ = (Jc + sum_j Xi_j r0_j + Xi_r)(Tc + sum_l Theta_l r0_l + R) ----
+        double Tcn[MAXD][MAXN]; ival Rn[MAXD][MAXN], Psn[MAXD][MAXN], Tdev[MAXD][MAXN];
+        static thread_local double Thn[MAXD][MAXD][MAXN];
+        for (int i = 0; i < D; i++) for (int k = 0; k < n; k++) Tdev[i][k] = S0[i][k] + R[i][k];
+        for (int i = 0; i < D; i++) for (int k = 0; k < n; k++) {
+            ival a(0.0); for (int l = 0; l < D; l++) a = a + Jc[i][l] * ival(Tc[l][k]);
+            Tcn[i][k] = mid_ru(a);
+            ival rr = a - ival(Tcn[i][k]);
+            for (int l = 0; l < D; l++) rr = rr + Jc[i][l] * R[l][k];               // Jc R
+            for (int l = 0; l < D; l++) rr = rr + dJ[i][l] * Tdev[l][k];            // second order
+            for (int l = 0; l < D; l++) rr = rr + Xi[D][i][l] * ival(Tc[l][k]);     // Xi_r Tc
+            Rn[i][k] = rr;
+        }
+        for (int j = 0; j < D; j++) for (int i = 0; i < D; i++) for (int k = 0; k < n; k++) {
+            ival a(0.0);
+            for (int l = 0; l < D; l++) a = a + Jc[i][l] * ival(Th[j][l][k]);
+            for (int l = 0; l < D; l++) a = a + Xi[j][i][l] * ival(Tc[l][k]);
+            Thn[j][i][k] = mid_ru(a);
+            Rn[i][k] = Rn[i][k] + (a - ival(Thn[j][i][k])) * r0[j];
+        }
+        for (int i = 0; i < D; i++) for (int k = 0; k < n; k++) {
+            ival a(0.0); for (int l = 0; l < D; l++) a = a + J[i][l] * Ps[l][k];
+            Psn[i][k] = a;
+        }
+        for (int i = 0; i < D; i++) {
+            x[i] = xn[i]; r[i] = rn[i];
+            for (int j = 0; j < D; j++) C[i][j] = Cn[i][j];
+            for (int k = 0; k < n; k++) { Tc[i][k] = Tcn[i][k]; R[i][k] = Rn[i][k]; Ps[i][k] = Psn[i][k]; for (int j = 0; j < D; j++) Th[j][i][k] = Thn[j][i][k]; }
+        }
+        tprev = ival(add_rd(tprev.lo, hs), add_ru(tprev.hi, hs));
+        if (last) {   // topFrame::getLastFrame (topFrame.cpp:265-299): frame and front point at the end of the last step
+            const int ld = CCP_MAX_N + 2;
+            ival S1[MAXD][MAXN], Wl[MAXD][MAXN];
+            frame_of_state(n, Tc, Th, R, Ps, r0, Err, S1, Wl);
+            for (int rr = 0; rr < D; rr++) for (int k = 0; k < n; k++) res.last_frame[rr * ld + k] = toc(Wl[rr][k]);
+            for (int i = 0; i < D; i++) {
+                ival a(x[i]);
+                for (int j = 0; j < D; j++) a = a + ival(C[i][j]) * r0[j];
+                res.last_frame[i * ld + n + 1] = toc(a + r[i]);
+            }
+        }
+    }
+    res.zero_count = cnt.zero_count; res.failure_count = cnt.failure_count; res.first_failure = cnt.first_failure;
+    res.n_conj = cnt.n_conj;
+    for (int i = 0; i < cnt.n_conj; i++) { res.conj_time[i] = cnt.conj_time[i]; res.conj_index[i] = cnt.conj_index[i]; }
+}
+
+} // namespace c2
+} // namespace orc

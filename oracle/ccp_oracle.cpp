@@ -15,6 +15,7 @@
 //   mode 1 ("c1") : structured C^1 algorithm, op-for-op what the CUDA kernel does.
 #include "ref.hpp"
 #include "c1.hpp"
+#include "c2.hpp"
 #include <thread>
 #include <atomic>
 #include <chrono>
@@ -28,6 +29,7 @@ int orc_run_front(const ccp_front_desc* d, int mode, ccp_front_result* res, ccp_
     std::vector<ccp_series_rec> ser;
     bool want = series != nullptr && cap > 0;
     if (mode == 1) c1::run_front(*d, *res, want ? &ser : nullptr);
+    else if (mode == 2) c2::run_front(*d, *res, want ? &ser : nullptr);
     else           ref::run_front(*d, *res, want ? &ser : nullptr, threads);
     if (len) *len = ser.size();
     if (want) { size_t m = std::min(cap, ser.size()); std::memcpy(series, ser.data(), m * sizeof(ccp_series_rec)); }
@@ -47,6 +49,7 @@ int orc_run_batch(const ccp_front_desc* d, size_t n_fronts, int mode, ccp_front_
             size_t i = next.fetch_add(1);
             if (i >= n_fronts) break;
             if (mode == 1) c1::run_front(d[i], res[i], nullptr);
+            else if (mode == 2) c2::run_front(d[i], res[i], nullptr);
             else           ref::run_front(d[i], res[i], nullptr, 1);
         }
     };
