@@ -41,41 +41,63 @@ constexpr int GMAX = CCP_MAX_GRID;
 // Row stride 21*16 B = 84 words => 8 consecutive rows hit 8 disjoint 4-bank groups: LDS.128 conflict-free.
 template <int N> struct Lay {
     static constexpr int D = 2 * N, NE = N - 1;
-    __host__ __device__ static constexpr int U(int set, int i) { return set * N + i; }
-    __host__ __device__ static constexpr int V(int set, int i) { return 2 * N + set * N + i; }
-    __host__ __device__ static constexpr int G(int set, int i) { return 4 * N + set * N + i; }
-    __host__ __device__ static constexpr int Q(int set, int e) { return 6 * N + set * NE + e; }     // set 0 rows hold z0 (see below)
-    __host__ __device__ static constexpr int MD(int i) { return 6 * N + 2 * NE + i; }
-    __host__ __device__ static constexpr int MO(int e) { return 7 * N + 2 * NE + e; }
-    __host__ __device__ static constexpr int PU(int i, int c) { return 7 * N + 3 * NE + i * D + c; }
-    __host__ __device__ static constexpr int PV(int i, int c) { return 7 * N + 3 * NE + N * D + i * D + c; }
-    __host__ __device__ static constexpr int Z(int set, int i) { return 7 * N + 3 * NE + 2 * N * D + set * N + i; }   // z = 1 - u
-    static constexpr int NS = 9 * N + 3 * NE + 2 * N * D;
-    // w = u - 1/2 differs from u only at order 0: w0 lives in the unused slot G(set,i)[KMAX-1] (g is only needed
+    // ONE table set: the centre trajectory x (the dependence on the set is carried by the second variation, see run_front)
+    __host__ __device__ static constexpr int U(int i) { return i; }
+    __host__ __device__ static constexpr int V(int i) { return N + i; }
+    __host__ __device__ static constexpr int G(int i) { return 2 * N + i; }
+    __host__ __device__ static constexpr int Q(int e) { return 3 * N + e; }
+    __host__ __device__ static constexpr int MD(int i) { return 3 * N + NE + i; }
+    __host__ __device__ static constexpr int MO(int e) { return 4 * N + NE + e; }
+    __host__ __device__ static constexpr int PU(int i, int c) { return 4 * N + 2 * NE + i * D + c; }
+    __host__ __device__ static constexpr int PV(int i, int c) { return 4 * N + 2 * NE + N * D + i * D + c; }
+    __host__ __device__ static constexpr int Z(int i) { return 4 * N + 2 * NE + 2 * N * D + i; }   // z = 1 - u
+    static constexpr int NS = 5 * N + 2 * NE + 2 * N * D;
+    // w = u - 1/2 differs from u only at order 0: w0 lives in the unused slot G(i)[KMAX-1] (g is only needed
     // to order p-1) and enters the products as a peeled end term.  z = 1 - u has its own rows (z_k = -u_k).
-    static constexpr int NA = 2 * N + NE;             // A tasks: g[set][i] = u*z, q[e] = w_e*w_{e+1} (hull)
-    static constexpr int NB = 2 * (3 * N - 2);        // B tasks: g_i*w_i, g_{i-1}*w_i, g_{i+1}*w_i per set
+    static constexpr int NA = N + NE;                 // A tasks: g[i] = u*z, q[e] = w_e*w_{e+1}
+    static constexpr int NB = 3 * N - 2;              // B tasks: g_i*w_i, g_{i-1}*w_i, g_{i+1}*w_i
     static constexpr int NC = D * (3 * N - 2);        // C tasks: Md_i*Pu_i^c, Mo*Pu_{i+-1}^c
     static constexpr int NTASK = NA + NB + NC;
     static constexpr int NPH = (NTASK + 31) / 32 + ((NA + NC) <= 32 && NB > 0 && NTASK <= 32 ? 1 : 0);   // >= 2 always (A before B)
 };
 
-struct Majorant { double rho_phi, rho_phi_d, rho_psi, rho_psi_d; ival Gs_u, Gs_v; bool ok; };
+struct Majorant { double rho_phi, rho_phi_d, rho_psi, rho_psi_d, g1, g5; ival Gs_u, Gs_v; bool ok; };   // g1, g5: second variation (majorant2)
 // parameter interval as sign * [pl, ph] with 0 <= pl <= ph (see imul_par)
 struct SPar { double pl, ph; int neg, straddle; };
+
+// low-order Taylor data over the hull [X] of the phi-set (oracle/c2.hpp): w_k = coefficients of u - 1/2, M_0, M_1 (tridiagonal)
+template <int N> struct HullQ { ival w[4][N], Md0[N], Mo0[N], Md1[N], Mo1[N]; };
+
+// Overlay of the Taylor-table array once the tables of a step are dead (after the frame tables F_k are built).
+template <int N> struct PostTab {
+    static constexpr int D = 2 * N;
+    ival Xi[D + 1][D][D];                    // second variation DPhi'[c_j] over the hull, j < D; Xi[D]: direction = the box r
+    ival dJ[D][D];                           // sum_j Xi_j r0_j + Xi_D
+    ival E[D][D][N];                         // set update: (enclosure of Theta_j+ minus its midpoint) * r0_j
+    double magXu[N][D], magXv[N][D];
+    ival DT[3 * (GMAX + 1)];                 // determinants of the grid loop
+    union {
+        ival EV[(2 * GMAX + 1) * N * N];     // frame enclosures of the grid loop
+        struct { ival DD[D + 1][4][N]; ival NN[D + 1][4][2 * N - 1]; double AM[D + 1][D][D]; } x;   // transients of the second-variation phase
+    } u;
+};
 
 template <int N>
 struct FrontSmem {
     static constexpr int D = 2 * N;
     static constexpr int NE = (N > 1) ? (N - 1) : 1;
-    mt T[Lay<N>::NS][KMAX];                  // Taylor tables; dead rows double as EV / DT buffers in the grid loop
+    mt T[Lay<N>::NS][KMAX];                  // Taylor tables of the centre trajectory; PostTab overlays them once they are dead
     ival Fk[KMAX][N][N];
-    // set state (double buffered)
+    // front set x + C r0 + r (double buffered)
     double x[2][D], C[2][D][D];
-    ival r[2][D], P[2][D][D];
-    ival r0[D], Err[N][N], X[D], y[D], J[D][D], Ws[D][N], bpar[N], cpar[NE];
+    ival r[2][D];
+    // unstable columns of Dphi_t A_u:  Tc + sum_j Th[j] r0_j + R  (Tc, Th points);  stable columns Ps (interval)
+    double Tc[D][N], Th[D][D][N];
+    ival R[D][N], Ps[D][N], S0[D][N];
+    ival r0[D], Err[N][N], X[D], y[D], Jc[D][D], J[D][D], Ws[D][N], bpar[N], cpar[NE];
     mt Wm[D][N];
-    double rhoF[N], rhoFd[N];
+    HullQ<N> hq;
+    double boxFd[N][N];
     double invlo[KMAX + 2], invhi[KMAX + 2]; // [rd(1/k), ru(1/k)]
     double gp[GMAX + 1];                     // grid points of the current step (utils.cpp:219-223)
     ival dtime[GMAX];
@@ -83,6 +105,7 @@ struct FrontSmem {
     int dec[GMAX];
     int flag;
     Majorant mj;
+    double g15[2];
     union alignas(16) {
         ival scratch[Lay<N>::NB + Lay<N>::NC + 2 * N];   // table loop: Cauchy sums awaiting combination; then [0,0]; then the newest hull g, q
         ival JC[4 * N][2 * N];               // set update: rows 0..2n-1 = (J*C - C+)_ij r0_j, rows 2n..4n-1 = J_ij r_j
@@ -90,6 +113,8 @@ struct FrontSmem {
     } un;
 };
 
+static_assert(sizeof(PostTab<2>) <= sizeof(FrontSmem<2>::T) && sizeof(PostTab<3>) <= sizeof(FrontSmem<3>::T) && sizeof(PostTab<4>) <= sizeof(FrontSmem<4>::T),
+              "PostTab must fit into the table array");
 static_assert(sizeof(ccp_front_desc) % 16 == 0, "descriptors are staged with 16-byte loads");
 static_assert(sizeof(ccp_front_result) % 16 == 0, "result records are 16-byte aligned");
 
@@ -226,6 +251,42 @@ __device__ __forceinline__ ival eval_rg_deriv(const mt* s, int p, double tl, dou
 __device__ __forceinline__ ccp_interval toc(const ival& a) { ccp_interval o; o.lo = a.lo; o.hi = a.hi; return o; }
 __device__ __forceinline__ ival fromc(const ccp_interval& a) { return mk(a.lo, a.hi); }
 
+
+// ---- second variation helpers (oracle/c2.hpp, same expression order) ----
+__device__ __forceinline__ ival ihalf(const ival& a) { return mk(0.5 * a.lo, 0.5 * a.hi); }
+__device__ __forceinline__ ival idivk_tab(const ival& a, const double* ilo, const double* ihi, int k);
+// row i of (symmetric tridiagonal: diag dg, off-diagonal od) * vector
+template <int N>
+__device__ __forceinline__ ival tri_row(const ival* dg, const ival* od, const ival* v, int i) {
+    ival a = imul_nl(dg[i], v[i]);
+    if (i > 0)     a = iadd(a, imul_nl(od[i - 1], v[i - 1]));
+    if (i < N - 1) a = iadd(a, imul_nl(od[i], v[i + 1]));
+    return a;
+}
+__device__ __forceinline__ ival tri(const ival* dg, const ival* od, int i, int k) {
+    if (i == k) return dg[i];
+    if (k == i + 1) return od[i];
+    if (k == i - 1) return od[k];
+    return pt(0.0);
+}
+template <int N> __device__ __forceinline__ ival tri_e(const ival* dgod, int i, int k) { return tri(dgod, dgod + N, i, k); }
+template <int N>
+__device__ __noinline__ ival tri_mul(const ival* ad, const ival* ao, const ival* bd, const ival* bo, int i, int k) {
+    ival a = pt(0.0);
+    for (int l = 0; l < N; l++) {
+        if (l < i - 1 || l > i + 1 || l < k - 1 || l > k + 1) continue;
+        a = iadd(a, imul_nl(tri(ad, ao, i, l), tri(bd, bo, l, k)));
+    }
+    return a;
+}
+// (w_i d_m)_k = sum_{q<=k} w_q[i] d_{k-q}[m]
+template <int N>
+__device__ __noinline__ ival wd_coef(const HullQ<N>& H, const ival (*dd)[N], int i, int m, int k) {
+    ival a = imul_nl(H.w[0][i], dd[k][m]);
+    for (int q = 1; q <= k; q++) a = iadd(a, imul_nl(H.w[q][i], dd[k - q][m]));
+    return a;
+}
+
 // host-side twin of oracle/common.hpp:step_count
 __host__ __device__ inline int step_count(double L_minus, double h) {
     int S = (int)ceil(L_minus / h);
@@ -258,29 +319,29 @@ __device__ inline Task decode_task(int kind, int idx) {
     if (kind == 0) {
         if (idx >= L::NA) return t;
         t.kind = 0;
-        if (idx < 2 * N) {                     // g[set][i] = u*z
-            const int set = idx / N, i = idx % N;
-            t.iA = L::U(set, i); t.iB = L::Z(set, i);
-            t.a0r = L::U(set, i); t.a0c = 0; t.b0r = L::Z(set, i); t.b0c = 0;
-            t.out = L::G(set, i);
-        } else {                                // q[e] = w_e*w_{e+1} over the hull
-            const int e = idx - 2 * N;
-            t.iA = L::U(1, e); t.iB = L::U(1, e + 1);
-            t.a0r = L::G(1, e); t.a0c = KMAX - 1; t.b0r = L::G(1, e + 1); t.b0c = KMAX - 1;
-            t.out = L::Q(1, e);
+        if (idx < N) {                         // g[i] = u*z
+            const int i = idx;
+            t.iA = L::U(i); t.iB = L::Z(i);
+            t.a0r = L::U(i); t.a0c = 0; t.b0r = L::Z(i); t.b0c = 0;
+            t.out = L::G(i);
+        } else {                                // q[e] = w_e*w_{e+1}
+            const int e = idx - N;
+            t.iA = L::U(e); t.iB = L::U(e + 1);
+            t.a0r = L::G(e); t.a0c = KMAX - 1; t.b0r = L::G(e + 1); t.b0c = KMAX - 1;
+            t.out = L::Q(e);
         }
         return t;
     }
     if (kind == 1) {
         if (idx >= L::NB) return t;
         int c = 0;
-        for (int set = 0; set < 2; set++) for (int i = 0; i < N; i++) for (int w = 0; w < 3; w++) {
+        for (int i = 0; i < N; i++) for (int w = 0; w < 3; w++) {
             if ((w == 1 && i == 0) || (w == 2 && i == N - 1)) continue;
             if (c == idx) {
                 const int gi = (w == 0) ? i : (w == 1 ? i - 1 : i + 1);
                 t.kind = 1;
-                t.iA = L::G(set, gi); t.iB = L::U(set, i);
-                t.a0r = L::G(set, gi); t.a0c = 0; t.b0r = L::G(set, i); t.b0c = KMAX - 1;
+                t.iA = L::G(gi); t.iB = L::U(i);
+                t.a0r = L::G(gi); t.a0c = 0; t.b0r = L::G(i); t.b0c = KMAX - 1;
                 t.out = idx;
             }
             c++;
@@ -436,6 +497,120 @@ __device__ __forceinline__ ival idivk_tab(const ival& a, const double* ilo, cons
     return mk(__dmul_rd(a.lo, a.lo >= 0 ? ilo[k] : ihi[k]), __dmul_ru(a.hi, a.hi >= 0 ? ihi[k] : ilo[k]));
 }
 
+
+// oracle/c2.hpp:c2_majorant -- scalar majorant of the second variation xi' = Df xi + D^2f[Psi c, psi] on the a-priori box, per unit |c|_1:
+//   |Xi(tau)| <= g1 tau,   |Xi(tau) - sum_{k<=4} Xi_k tau^k| <= g5 tau^5      (out[0] = g1, out[1] = g5)
+template <int N>
+__device__ inline void majorant2(const ival* b, const ival* c, double h, double* out) {
+    double bh = 0, cs = 0;
+    for (int i = 0; i < N; i++) bh = dmax(bh, imag(b[i]));
+    for (int i = 0; i < N; i++) {
+        double s = 0;
+        if (i > 0) s = __dadd_ru(s, imag(c[i - 1]));
+        if (i < N - 1) s = __dadd_ru(s, imag(c[i]));
+        cs = dmax(cs, s);
+    }
+    const double W0 = 0.5625, G0 = 0.25, V0 = 0.5;
+    constexpr int K = 5;
+    double bc = __dadd_ru(bh, cs);
+    double F0 = __dmul_ru(__dmul_ru(bc, G0), W0);
+    double w[K + 2], g[K + 2], be[K + 2], Mh[K + 2], ga[K + 2], bb[K + 2];
+    w[0] = W0; g[0] = G0; w[1] = dmax(V0, F0);
+    for (int k = 1; k <= K; k++) {
+        double s = 0; for (int j = 0; j <= k; j++) s = __fma_ru(w[j], w[k - j], s);
+        g[k] = s;
+        double f = 0; for (int j = 0; j <= k; j++) f = __fma_ru(g[j], w[k - j], f);
+        f = __dmul_ru(bc, f);
+        w[k + 1] = __ddiv_ru(dmax(w[k], f), (double)(k + 1));
+    }
+    double M0 = __dadd_ru(__dadd_ru(__dmul_ru(bh, 0.75), __dmul_ru(cs, 0.25)), __dmul_ru(__dmul_ru(2.0, cs), __dmul_ru(W0, W0)));
+    double a = dmax(1.0, M0), ah = __dmul_ru(a, h);
+    be[0] = __dadd_ru(__dadd_ru(1.0, ah), __dmul_ru(ah, ah));
+    Mh[0] = M0;
+    double k3 = __dmul_ru(3.0, bc);
+    for (int k = 1; k <= K; k++) Mh[k] = __dmul_ru(k3, g[k]);
+    for (int k = 0; k <= K; k++) {
+        double s = 0; for (int j = 0; j <= k; j++) s = __fma_ru(Mh[j], be[k - j], s);
+        be[k + 1] = __ddiv_ru(dmax(be[k], s), (double)(k + 1));
+    }
+    const double H6 = __dmul_ru(6.0, bc);
+    ga[0] = __dmul_ru(__dmul_ru(h, __dmul_ru(be[0], __dmul_ru(be[0], be[0]))), __dmul_ru(H6, W0));
+    for (int k = 0; k <= K; k++) { double s = 0; for (int j = 0; j <= k; j++) s = __fma_ru(be[j], be[k - j], s); bb[k] = s; }
+    for (int k = 0; k < K; k++) {
+        double s = 0; for (int j = 0; j <= k; j++) s = __fma_ru(Mh[j], ga[k - j], s);
+        double f = 0; for (int j = 0; j <= k; j++) f = __fma_ru(w[j], bb[k - j], f);
+        s = __fma_ru(H6, f, s);
+        ga[k + 1] = __ddiv_ru(dmax(ga[k], s), (double)(k + 1));
+    }
+    out[0] = ga[1]; out[1] = ga[5];
+}
+
+template <int N> struct FrontSmem;
+// oracle/c2.hpp:frame_of_state, one entry:  S0 = sum_j Theta_j r0_j ;  W = ((Tc + S0) + R) + Ps Err
+template <int N>
+__device__ __noinline__ ival frame_entry(const FrontSmem<N>& S, int cc, int bb, ival* s0out) {
+    constexpr int D = 2 * N;
+    ival a = pt(0.0);
+    for (int j = 0; j < D; j++) a = iadd(a, imul_nl(pt(S.Th[j][cc][bb]), S.r0[j]));
+    *s0out = a;
+    ival w = iadd(iadd(pt(S.Tc[cc][bb]), a), S.R[cc][bb]);
+    for (int j = 0; j < N; j++) w = iadd(w, imul_nl(S.Ps[cc][j], S.Err[j][bb]));
+    return w;
+}
+// low-order hull data, row i (oracle/c2.hpp "hull, low order"); w_3 follows after a barrier (it needs all rows of M_0)
+template <int N>
+__device__ __noinline__ void hull_row(FrontSmem<N>& S, int i) {
+    HullQ<N>& H = S.hq;
+    auto W0 = [&](int m) { return isub(S.X[m], pt(0.5)); };
+    auto G0 = [&](int m) { return imul_nl(S.X[m], isub(pt(1.0), S.X[m])); };
+    const ival w0 = W0(i), w1 = S.X[N + i], g0 = G0(i);
+    H.w[0][i] = w0; H.w[1][i] = w1;
+    ival f = ineg(imul_nl(imul_nl(g0, w0), S.bpar[i]));
+    if (i > 0)     f = isub(f, imul_nl(imul_nl(G0(i - 1), w0), S.cpar[i - 1]));
+    if (i < N - 1) f = isub(f, imul_nl(imul_nl(G0(i + 1), w0), S.cpar[i]));
+    H.w[2][i] = ihalf(f);
+    ival dd = ineg(imul_nl(S.bpar[i], isub(imulk(g0, 3), pt(0.5))));
+    if (i > 0)     dd = isub(dd, imul_nl(S.cpar[i - 1], G0(i - 1)));
+    if (i < N - 1) dd = isub(dd, imul_nl(S.cpar[i], G0(i + 1)));
+    H.Md0[i] = dd;
+    if (i < N - 1) H.Mo0[i] = imul_nl(imulk(imul_nl(w0, W0(i + 1)), 2), S.cpar[i]);
+    ival m1 = imulk(imul_nl(S.bpar[i], imul_nl(w0, w1)), 6);
+    if (i > 0)     m1 = iadd(m1, imulk(imul_nl(S.cpar[i - 1], imul_nl(W0(i - 1), S.X[N + i - 1])), 2));
+    if (i < N - 1) m1 = iadd(m1, imulk(imul_nl(S.cpar[i], imul_nl(W0(i + 1), S.X[N + i + 1])), 2));
+    H.Md1[i] = m1;
+    if (i < N - 1) H.Mo1[i] = imulk(imul_nl(S.cpar[i], iadd(imul_nl(w0, S.X[N + i + 1]), imul_nl(w1, W0(i + 1)))), 2);
+}
+// phi' = (v, F(u)) over the sub-interval [tl,th] of the step and over the whole set (last column of the first / last frame,
+// topFrame.cpp:265-331), row i:  phi(tau) in phi_c(tau) + Psi(tau;xi)(phi0 - x),  |Psi(tau;xi) - Psi_c(tau)| <= g1 tau |phi0 - x|_1
+template <int N>
+__device__ __noinline__ void phi_prime(const FrontSmem<N>& S, const mt* Tf, int i, int p, int cur, double hs, double tl, double th, const Majorant& mj, ival& du, ival& dv) {
+    using L = Lay<N>;
+    constexpr int D = 2 * N;
+    ival dev[D]; double dn = 0;
+    for (int q = 0; q < D; q++) {
+        ival a = pt(0.0);
+        for (int j = 0; j < D; j++) a = iadd(a, imul_nl(pt(S.C[cur][q][j]), S.r0[j]));
+        dev[q] = iadd(a, S.r[cur][q]); dn = __dadd_ru(dn, imag(dev[q]));
+    }
+    const double pb = __dadd_ru(mj.rho_psi, __dmul_ru(__dmul_ru(mj.g1, hs), dn));
+    ival uu[N], gg[N];
+    for (int m = 0; m < N; m++) {
+        ival a = iadd(eval_rg(Tf + L::U(m) * KMAX, p, tl, th), sym(mj.rho_phi));
+        for (int cc = 0; cc < D; cc++) a = iadd(a, imul_nl(iadd(eval_rg(Tf + L::PU(m, cc) * KMAX, p, tl, th), sym(pb)), dev[cc]));
+        uu[m] = a; gg[m] = imul_nl(a, isub(pt(1.0), a));
+    }
+    {
+        ival bq = iadd(eval_rg(Tf + L::V(i) * KMAX, p, tl, th), sym(mj.rho_phi));
+        for (int cc = 0; cc < D; cc++) bq = iadd(bq, imul_nl(iadd(eval_rg(Tf + L::PV(i, cc) * KMAX, p, tl, th), sym(pb)), dev[cc]));
+        du = bq;
+    }
+    const ival wi = isub(uu[i], pt(0.5));
+    ival f = ineg(imul_nl(imul_nl(gg[i], wi), S.bpar[i]));
+    if (i > 0)     f = isub(f, imul_nl(imul_nl(gg[i - 1], wi), S.cpar[i - 1]));
+    if (i < N - 1) f = isub(f, imul_nl(imul_nl(gg[i + 1], wi), S.cpar[i]));
+    dv = f;
+}
+
 // Enclosure of F'(tau) over [tl, th] for every frame entry: Horner on the derivative series k*F_k, plus the tail bound
 // (the reference's rangeEnclosure of the vector field along the frame, utils.cpp:243-251).  Cold: only sub-intervals whose
 // rough test fails reach it.
@@ -447,7 +622,7 @@ __device__ __noinline__ void deriv_entries(const ival* __restrict__ Fk0, const d
             const int c = a * N + bb;
             ival acc = imulk(Fk0[p * NN + c], p);
             for (int k = p - 1; k >= 1; k--) acc = horner_rg(acc, tl, th, imulk(Fk0[k * NN + c], k));
-            Dm[a][bb] = iadd(acc, sym(rhoFd[bb]));
+            Dm[a][bb] = iadd(acc, sym(rhoFd[c]));
         }
 }
 
@@ -493,13 +668,15 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
             double xm = mid_ru(pi);
             S.x[0][tid] = xm; S.r[0][tid] = isub(pi, pt(xm)); S.r0[tid] = fromc(d.Uxy[tid]);
         }
-        for (int t = tid; t < D * D; t += NT) { int i = t / D, j = t % D; double a = d.A_u[i * CCP_MAX_DIM + j]; S.C[0][i][j] = a; S.P[0][i][j] = pt(a); }
+        for (int t = tid; t < D * D; t += NT) { int i = t / D, j = t % D; double a = d.A_u[i * CCP_MAX_DIM + j]; S.C[0][i][j] = a; if (j < N) { S.Tc[i][j] = a; S.R[i][j] = pt(0.0); } else S.Ps[i][j - N] = pt(a); }
+        for (int t = tid; t < D * D * N; t += NT) (&S.Th[0][0][0])[t] = 0.0;
         for (int t = tid; t < N * N; t += NT) { int j = t / N, k = t % N; S.Err[j][k] = fromc(d.Eu_err[j * CCP_MAX_N + k]); }
         if (tid >= 32 && tid < 32 + KMAX + 2) { const int k = tid - 32; if (k >= 1) { S.invlo[k] = __ddiv_rd(1.0, (double)k); S.invhi[k] = __ddiv_ru(1.0, (double)k); } else { S.invlo[0] = S.invhi[0] = 0.0; } }
     }
     for (int t = tid; t < (int)(sizeof(ccp_front_result) / 8); t += NT) reinterpret_cast<double*>(gres)[t] = 0.0;
     __syncthreads();                                // the descriptor (un.desc) is dead from here on
     if (tid == 0) { S.mj = majorant<N>(S.bpar, S.cpar, p, h); S.flag = 0; }
+    if (tid == 32) majorant2<N>(S.bpar, S.cpar, h, S.g15);
     if (tid < 3 * N - 1) {
         SPar q; q.pl = 0; q.ph = 0; q.neg = 0; q.straddle = 0;                       // index 2N-1: zero parameter
         if (tid < N) q = make_spar(S.bpar[tid]);
@@ -508,7 +685,7 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
         S.par[tid] = q;
     }
     __syncthreads();
-    const Majorant mj = S.mj;
+    Majorant mj = S.mj; mj.g1 = S.g15[0]; mj.g5 = S.g15[1];
     if (!mj.ok) status = CCP_ST_ENCLOSURE;
 
     // slot = task handled by this lane pair; consecutive slots go to different warps so that every phase is spread
@@ -540,23 +717,23 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
     int ap0 = PZ, ap1 = PZ, ap2 = PZ, mscale = 1, gslot = -1;
     double mcst = 0;
     if (wq == 0) {
-        if (lane < 2 * N) {                                  // v, u, z of the centre (set 0) and the hull (set 1)
-            const int set = lane / N, i = lane % N;
-            int b0 = set * (3 * N - 2) + (i == 0 ? 0 : 3 * i - 1);
+        if (lane < N) {                                      // v, u, z
+            const int i = lane;
+            int b0 = (i == 0 ? 0 : 3 * i - 1);
             cs0 = b0++; ap0 = i;
             if (i > 0)     { cs1 = b0++; ap1 = N + i - 1; }
             if (i < N - 1) { cs2 = b0;   ap2 = N + i; }
-            rowV = L::V(set, i) * KMAX; rowU = L::U(set, i) * KMAX; rowZ = L::Z(set, i) * KMAX;
-        } else if (lane < 3 * N) {                           // Md_i
-            const int i = lane - 2 * N;
+            rowV = L::V(i) * KMAX; rowU = L::U(i) * KMAX; rowZ = L::Z(i) * KMAX;
+        } else if (lane < 2 * N) {                           // Md_i
+            const int i = lane - N;
             cs0 = GS + i; ap0 = i; mscale = 3; mcst = 0.5; rowV = L::MD(i) * KMAX;
             if (i > 0)     { cs1 = GS + i - 1; ap1 = N + i - 1; }
             if (i < N - 1) { cs2 = GS + i + 1; ap2 = N + i; }
-        } else if (lane < 4 * N - 1) {                       // Mo_e = c_e * 2 q_e  (P0 = -c_e)
-            const int e = lane - 3 * N;
+        } else if (lane < 3 * N - 1) {                       // Mo_e = c_e * 2 q_e  (P0 = -c_e)
+            const int e = lane - 2 * N;
             cs0 = GS + N + e; ap0 = 2 * N + e; mscale = 2; rowV = L::MO(e) * KMAX;
         }
-        if (lane >= N && lane < L::NA) gslot = GS + (lane - N);    // A lanes of the hull g (task N+i) and q (task 2N+e)
+        if (lane < L::NA) gslot = GS + lane;                 // A lanes: g (task i) and q (task N+e)
     } else if (lane < N * D) {
         const int i = lane / D, cc = lane % D;
         int c0 = L::NB + (i == 0 ? 0 : (3 * i - 1) * D) + cc * ((i == 0 || i == N - 1) ? 2 : 3);
@@ -573,9 +750,10 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
     ival tprev = pt(0.0);
     int cur = 0;
     ival det_first = pt(0.0), det_last = pt(0.0);                                // thread 0
-    // views of dead table rows used by the grid loop: EV[arg][row][col] frame enclosures, DT[.] determinants
-    ival* const EV = reinterpret_cast<ival*>(&T[L::PU(0, 0)][0]);
-    ival* const DT = reinterpret_cast<ival*>(&T[L::MD(0)][0]);                  // 3*(GMAX+1) intervals << N rows of 21
+    // PT overlays the Taylor tables once they are dead: second-variation data, EV[arg][row][col] frame enclosures, DT[.] determinants
+    PostTab<N>& PT = *reinterpret_cast<PostTab<N>*>(&T[0][0]);
+    ival* const EV = PT.u.EV;
+    ival* const DT = PT.DT;
 
     for (int s = 0; s < Stot && status == CCP_OK; s++) {
         PROF_T0();
@@ -603,18 +781,18 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
             if (fl & 2) { status = CCP_ST_ENCLOSURE; break; }
         }
         // ---- order 0 of all tables: set 0 = centre x, set 1 = hull X; Psi = identity ----
-        if (tid < 2 * N) {
-            const int set = tid / N, i = tid % N;
-            ival u0 = set ? S.X[i] : pt(S.x[cur][i]);
-            ival v0 = set ? S.X[N + i] : pt(S.x[cur][N + i]);
-            T[L::U(set, i)][0] = iv2mt(u0); T[L::V(set, i)][0] = iv2mt(v0);
-            T[L::G(set, i)][KMAX - 1] = iv2mt(isub(u0, pt(0.5)));          // w0
-            T[L::Z(set, i)][0] = iv2mt(isub(pt(1.0), u0));                 // z0
+        if (tid < N) {
+            const int i = tid;
+            const ival u0 = pt(S.x[cur][i]), v0 = pt(S.x[cur][N + i]);
+            T[L::U(i)][0] = iv2mt(u0); T[L::V(i)][0] = iv2mt(v0);
+            T[L::G(i)][KMAX - 1] = iv2mt(isub(u0, pt(0.5)));               // w0
+            T[L::Z(i)][0] = iv2mt(isub(pt(1.0), u0));                      // z0
             const mt u1 = iv2mt(idivk_tab(mt2iv(iv2mt(v0)), S.invlo, S.invhi, 1));   // u[1] = v[0]/1
-            T[L::U(set, i)][1] = u1;
+            T[L::U(i)][1] = u1;
             mt z1; z1.m = -u1.m; z1.t = u1.t;
-            T[L::Z(set, i)][1] = z1;
+            T[L::Z(i)][1] = z1;
         }
+        if (tid >= 32 && tid < 32 + N) hull_row<N>(S, tid - 32);              // low-order hull quantities for the second variation
         for (int t = tid; t < N * D; t += NT) {
             const int i = t / D, cc = t % D;
             T[L::PU(i, cc)][0] = iv2mt(pt(cc == i ? 1.0 : 0.0));
@@ -640,7 +818,7 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
                 if (gslot >= 0) S.un.scratch[gslot] = mt2iv(g0);
             }
             __syncwarp();
-            if (lane >= 2 * N && lane < 4 * N - 1) {
+            if (lane >= N && lane < 3 * N - 1) {
                 ival x0 = imulk(S.un.scratch[cs0], mscale);
                 x0 = isub(x0, pt(mcst));
                 const ival x1 = S.un.scratch[cs1], x2 = S.un.scratch[cs2];
@@ -650,13 +828,13 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
                     dd = ineg(imul_pos3(x0, q0.pl, q0.ph, q0.neg));
                     dd = isub(dd, imul_pos3(x1, q1.pl, q1.ph, q1.neg));
                     dd = isub(dd, imul_pos3(x2, q2.pl, q2.ph, q2.neg));
-                } else if (lane < 3 * N) {
-                    const int i = lane - 2 * N;
+                } else if (lane < 2 * N) {
+                    const int i = lane - N;
                     dd = ineg(imul_nl(x0, S.bpar[i]));
                     if (i > 0)     dd = isub(dd, imul_nl(x1, S.cpar[i - 1]));
                     if (i < N - 1) dd = isub(dd, imul_nl(x2, S.cpar[i]));
                 } else {
-                    dd = imul_nl(x0, S.cpar[lane - 3 * N]);
+                    dd = imul_nl(x0, S.cpar[lane - 2 * N]);
                 }
                 T[0][rowV] = iv2mt(dd);
             }
@@ -664,8 +842,8 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
         bar_pair();
         // phi warp: scratch sums of order kc -> v[kc+1], u[kc+2], z[kc+2] (lanes < 2N);  hull g, q of order kc+1 -> M[kc+1]
         auto combine_phi = [&](int kc) {
-            const bool isV = lane < 2 * N;
-            if (isV || (lane < 4 * N - 1 && kc + 1 <= p - 1)) {
+            const bool isV = lane < N;
+            if (isV || (lane < 3 * N - 1 && kc + 1 <= p - 1)) {
                 const ival s0 = imulk(S.un.scratch[cs0], mscale), s1 = S.un.scratch[cs1], s2 = S.un.scratch[cs2];
                 const double il = isV ? S.invlo[kc + 1] : 1.0, ih = isV ? S.invhi[kc + 1] : 1.0;
                 ival f;
@@ -674,13 +852,13 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
                     f = ineg(imul_pos3(s0, q0.pl, q0.ph, q0.neg));
                     f = isub(f, imul_pos3(s1, q1.pl, q1.ph, q1.neg));
                     f = isub(f, imul_pos3(s2, q2.pl, q2.ph, q2.neg));
-                } else if (lane < 3 * N) {                // a parameter interval straddles zero: general products
+                } else if (lane < 2 * N) {                // a parameter interval straddles zero: general products
                     const int i = lane % N;
                     f = ineg(imul_nl(s0, S.bpar[i]));
                     if (i > 0)     f = isub(f, imul_nl(s1, S.cpar[i - 1]));
                     if (i < N - 1) f = isub(f, imul_nl(s2, S.cpar[i]));
                 } else {
-                    f = imul_nl(s0, S.cpar[lane - 3 * N]);
+                    f = imul_nl(s0, S.cpar[lane - 2 * N]);
                 }
                 const ival fv = mk(__dmul_rd(f.lo, f.lo >= 0 ? il : ih), __dmul_ru(f.hi, f.hi >= 0 ? ih : il));
                 const mt vn = iv2mt(fv);
@@ -783,69 +961,158 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
         }
         PROF(1);
         TRC(3);
-        // ---- step image: y = Phi(x) (centre tables), J = DPhi over the hull (Psi tables); frame at step start ----
+        // ---- step image: y = Phi(x), Jc = DPhi(x) (centre tables); frame at step start W = ((Tc + sum_j Theta_j r0_j) + R) + Ps Err ----
         for (int t = tid; t < D + D * D + D * N; t += NT) {
             if (t < D) {
                 const int i = t % N;
-                S.y[t] = iadd(eval_pt(t < N ? T[L::U(0, i)] : T[L::V(0, i)], p, hs), sym(mj.rho_phi));
+                S.y[t] = iadd(eval_pt(t < N ? T[L::U(i)] : T[L::V(i)], p, hs), sym(mj.rho_phi));
             } else if (t < D + D * D) {
                 const int e = t - D, row = e / D, cc = e % D, i = row % N;
-                S.J[row][cc] = iadd(eval_pt(row < N ? T[L::PU(i, cc)] : T[L::PV(i, cc)], p, hs), sym(mj.rho_psi));
+                S.Jc[row][cc] = iadd(eval_pt(row < N ? T[L::PU(i, cc)] : T[L::PV(i, cc)], p, hs), sym(mj.rho_psi));
             } else {
                 const int e = t - D - D * D, cc = e / N, bb = e % N;
-                ival a = S.P[cur][cc][bb];
-                for (int j = 0; j < N; j++) a = iadd(a, imul_nl(S.P[cur][cc][N + j], S.Err[j][bb]));
-                S.Ws[cc][bb] = a; S.Wm[cc][bb] = iv2mt(a);
+                const ival w = frame_entry<N>(S, cc, bb, &S.S0[cc][bb]);
+                S.Ws[cc][bb] = w; S.Wm[cc][bb] = iv2mt(w);
             }
         }
         __syncthreads();
         PROF(2);
         TRC(4);
-        if (tid < N) {
-            double sm = 0; for (int cc = 0; cc < D; cc++) sm = __dadd_ru(sm, imag(S.Ws[cc][tid]));
-            S.rhoF[tid] = __dmul_ru(mj.rho_psi, sm); S.rhoFd[tid] = __dmul_ru(mj.rho_psi_d, sm);
-        }
-        __syncthreads();
-        // ---- frame tables F_k = Psi^u_k * Ws ----
+        // ---- frame tables F_k = Psi^u_k * Ws (the box for truncation and for Psi(phi) - Psi(x) is added to F_0 below) ----
         for (int t = tid; t < (p + 1) * N * N; t += NT) {
             const int k = t / (N * N), a = (t / N) % N, bb = t % N;
             acc4 ac = acc_zero();
 #pragma unroll
             for (int cc = 0; cc < D; cc++) acc_term(ac, T[L::PU(a, cc)][k], S.Wm[cc][bb]);
-            ival f = acc_finish(ac);
-            if (k == 0) f = iadd(f, sym(S.rhoF[bb]));
-            S.Fk[k][a][bb] = f;
+            S.Fk[k][a][bb] = acc_finish(ac);
         }
         // ---- first / last frame data (topFrame::getFirstFrame / getLastFrame): rare ----
         if (s == 0) {
-            const double t0 = 0.0, t1 = (1 < g) ? __ddiv_rd(__dmul_rd(1.0, hs), (double)g) : hs;
             for (int t = tid; t < D * N; t += NT) { const int rr = t / N, k = t % N; gres->first_frame[rr * (CCP_MAX_N + 1) + k] = toc(S.Ws[rr][k]); }
             if (tid < N) {
-                ival du = iadd(eval_rg(T[L::V(1, tid)], p, t0, t1), sym(mj.rho_phi));
-                ival dv = iadd(eval_rg_deriv(T[L::V(1, tid)], p, t0, t1), sym(mj.rho_phi_d));
+                const double t1 = (1 < g) ? __ddiv_rd(__dmul_rd(1.0, hs), (double)g) : hs;
+                ival du, dv; phi_prime<N>(S, Tf, tid, p, cur, hs, 0.0, t1, mj, du, dv);
                 gres->first_frame[tid * (CCP_MAX_N + 1) + N] = toc(du);
                 gres->first_frame[(N + tid) * (CCP_MAX_N + 1) + N] = toc(dv);
             }
         }
-        if (last) {
+        if (last && tid < N) {
             constexpr int ld = CCP_MAX_N + 2;
-            for (int t = tid; t < D * N; t += NT) {
-                const int rr = t / N, k = t % N;
-                ival a = pt(0.0);
-                for (int cc = 0; cc < D; cc++) a = iadd(a, imul_nl(S.J[rr][cc], S.Ws[cc][k]));
-                gres->last_frame[rr * ld + k] = toc(a);
-            }
-            if (tid < N) {
-                const double tl = __ddiv_rd(__dmul_rd((double)(g - 1), hs), (double)g);
-                ival du = iadd(eval_rg(T[L::V(1, tid)], p, tl, hs), sym(mj.rho_phi));
-                ival dv = iadd(eval_rg_deriv(T[L::V(1, tid)], p, tl, hs), sym(mj.rho_phi_d));
-                gres->last_frame[tid * ld + N] = toc(du);
-                gres->last_frame[(N + tid) * ld + N] = toc(dv);
-            }
+            const double tl = __ddiv_rd(__dmul_rd((double)(g - 1), hs), (double)g);
+            ival du, dv; phi_prime<N>(S, Tf, tid, p, cur, hs, tl, hs, mj, du, dv);
+            gres->last_frame[tid * ld + N] = toc(du);
+            gres->last_frame[(N + tid) * ld + N] = toc(dv);
         }
-        __syncthreads();                            // Fk complete; Psi tables and un.scratch are dead from here
+        __syncthreads();                            // Fk complete; all Taylor tables and un.scratch are dead from here (PT overlays them)
         PROF(3);
         TRC(5);
+        // ---- second variation over the hull (oracle/c2.hpp): directions c_j = C e_j (j < D) and the box r (j = D) ----
+        {
+            const HullQ<N>& H = S.hq;
+            // X1: w_3;  d_2, d_3 of every direction
+            if (tid < N) S.hq.w[3][tid] = idivk_tab(tri_row<N>(H.Md0, H.Mo0, H.w[1], tid), S.invlo, S.invhi, 6);
+            for (int t = tid; t < (D + 1) * N; t += NT) {
+                const int j = t / N, m = t % N;
+                ival d0[N], d1[N];
+#pragma unroll
+                for (int i = 0; i < N; i++) { d0[i] = j < D ? pt(S.C[cur][i][j]) : S.r[cur][i]; d1[i] = j < D ? pt(S.C[cur][N + i][j]) : S.r[cur][N + i]; }
+                PT.u.x.DD[j][0][m] = d0[m]; PT.u.x.DD[j][1][m] = d1[m];
+                PT.u.x.DD[j][2][m] = ihalf(tri_row<N>(H.Md0, H.Mo0, d0, m));
+                PT.u.x.DD[j][3][m] = idivk_tab(iadd(tri_row<N>(H.Md1, H.Mo1, d0, m), tri_row<N>(H.Md0, H.Mo0, d1, m)), S.invlo, S.invhi, 6);
+            }
+            __syncthreads();
+            TRC(10);
+            // X2: Taylor coefficients N_0..N_3 of DM(u)[Psi^u c_j] (tridiagonal: N diagonal + N-1 off-diagonal entries per order)
+            for (int t = tid; t < (D + 1) * (2 * N - 1); t += NT) {
+                const int j = t / (2 * N - 1), e = t % (2 * N - 1);
+                const ival (*dd)[N] = PT.u.x.DD[j];
+#pragma unroll 1
+                for (int k = 0; k < 4; k++) {
+                    ival a;
+                    if (e < N) {
+                        const int i = e;
+                        a = imulk(imul_nl(S.bpar[i], wd_coef<N>(H, dd, i, i, k)), 6);
+                        if (i > 0)     a = iadd(a, imulk(imul_nl(S.cpar[i - 1], wd_coef<N>(H, dd, i - 1, i - 1, k)), 2));
+                        if (i < N - 1) a = iadd(a, imulk(imul_nl(S.cpar[i], wd_coef<N>(H, dd, i + 1, i + 1, k)), 2));
+                    } else {
+                        const int i = e - N;
+                        a = imulk(imul_nl(S.cpar[i], iadd(wd_coef<N>(H, dd, i + 1, i, k), wd_coef<N>(H, dd, i, i + 1, k))), 2);
+                    }
+                    PT.u.x.NN[j][k][e] = a;
+                }
+            }
+            __syncthreads();
+            TRC(11);
+            // X3: the four n x n blocks of Xi_j(hs) = sum_{k<=4} Xi_k hs^k + remainder, one (j, i, k) entry of each block per thread
+            const double hs2 = __dmul_ru(hs, hs), hs5 = __dmul_ru(__dmul_ru(hs2, hs2), hs);
+            for (int t = tid; t < (D + 1) * N * N; t += NT) {
+                const int j = t / (N * N), i = (t / N) % N, k = t % N;
+                double c1n = 0;
+                for (int q = 0; q < D; q++) c1n = __dadd_ru(c1n, j < D ? fabs(S.C[cur][q][j]) : imag(S.r[cur][q]));
+                const double rem = __dmul_ru(__dmul_ru(mj.g5, hs5), c1n);
+                const ival (*NN)[2 * N - 1] = PT.u.x.NN[j];
+                const int dk = i > k ? i - k : k - i;
+                ival cf[4][4];
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+#pragma unroll
+                    for (int e = 0; e < 4; e++) cf[q][e] = pt(0.0);
+                if (dk <= 2) {
+                    const ival* M0 = H.Md0; const ival* M1 = H.Md1;     // diag followed by off-diagonal in HullQ: Md0[N], Mo0[N]
+                    const ival N0 = tri_e<N>(NN[0], i, k), N1 = tri_e<N>(NN[1], i, k), N2 = tri_e<N>(NN[2], i, k), N3 = tri_e<N>(NN[3], i, k);
+                    const ival P00 = iadd(tri_mul<N>(M0, H.Mo0, NN[0], NN[0] + N, i, k), tri_mul<N>(NN[0], NN[0] + N, M0, H.Mo0, i, k));
+                    const ival P01 = iadd(tri_mul<N>(M0, H.Mo0, NN[1], NN[1] + N, i, k), tri_mul<N>(NN[0], NN[0] + N, M1, H.Mo1, i, k));
+                    const ival P10 = iadd(tri_mul<N>(M1, H.Mo1, NN[0], NN[0] + N, i, k), tri_mul<N>(NN[1], NN[1] + N, M0, H.Mo0, i, k));
+                    const ival X3 = idivk_tab(iadd(N2, ihalf(P00)), S.invlo, S.invhi, 3);
+                    cf[0][1] = ihalf(N0); cf[0][2] = idivk_tab(N1, S.invlo, S.invhi, 6); cf[0][3] = idivk_tab(X3, S.invlo, S.invhi, 4);
+                    cf[1][2] = idivk_tab(N0, S.invlo, S.invhi, 6); cf[1][3] = idivk_tab(N1, S.invlo, S.invhi, 12);
+                    cf[2][0] = N0; cf[2][1] = ihalf(N1); cf[2][2] = X3;
+                    cf[2][3] = idivk_tab(iadd(iadd(N3, idivk_tab(P01, S.invlo, S.invhi, 6)), ihalf(P10)), S.invlo, S.invhi, 4);
+                    cf[3][1] = ihalf(N0); cf[3][2] = idivk_tab(N1, S.invlo, S.invhi, 3);
+                    cf[3][3] = idivk_tab(iadd(N2, idivk_tab(P00, S.invlo, S.invhi, 6)), S.invlo, S.invhi, 4);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    ival acc = cf[q][3]; double am = imag(cf[q][3]);
+#pragma unroll
+                    for (int e = 2; e >= 0; e--) { acc = horner_pt(acc, hs, cf[q][e]); am = __fma_ru(am, hs, imag(cf[q][e])); }
+                    acc = horner_pt(acc, hs, pt(0.0)); am = __dmul_ru(am, hs);
+                    const int row = (q >> 1) * N + i, col = (q & 1) * N + k;
+                    PT.Xi[j][row][col] = iadd(acc, sym(rem));
+                    PT.u.x.AM[j][row][col] = __dadd_ru(am, rem);
+                }
+            }
+            __syncthreads();
+            TRC(12);
+            // X4: dJ = sum_j Xi_j r0_j + Xi_r encloses DPhi(phi) - DPhi(x) on the set; J = Jc + [0,1] dJ for the mean-value form of the
+            //     phi-set update; magX >= sup over [0,hs] of |Psi(tau;phi) - Psi(tau;x)|
+            for (int t = tid; t < D * D; t += NT) {
+                const int row = t / D, col = t % D;
+                ival dj = pt(0.0); double mg = 0.0;
+                for (int j = 0; j <= D; j++) {
+                    const ival wj = j < D ? S.r0[j] : pt(1.0);
+                    dj = iadd(dj, imul_nl(PT.Xi[j][row][col], wj));
+                    mg = __fma_ru(PT.u.x.AM[j][row][col], imag(wj), mg);
+                }
+                PT.dJ[row][col] = dj;
+                S.J[row][col] = iadd(S.Jc[row][col], ihull(dj, pt(0.0)));
+                if (row < N) PT.magXu[row][col] = mg; else PT.magXv[row - N][col] = mg;
+            }
+            __syncthreads();
+            TRC(13);
+            // truncation box of the centre tables + box for (Psi(tau;phi) - Psi(tau;x)) W on [0,hs]; same for the derivative
+            if (tid < N * N) {
+                const int a = tid / N, bb = tid % N;
+                double sm = 0; for (int cc = 0; cc < D; cc++) sm = __dadd_ru(sm, imag(S.Ws[cc][bb]));
+                double s0 = __dmul_ru(mj.rho_psi, sm), s1 = __dmul_ru(mj.rho_psi_d, sm);
+                for (int cc = 0; cc < D; cc++) { const double wm = imag(S.Ws[cc][bb]); s0 = __fma_ru(PT.magXu[a][cc], wm, s0); s1 = __fma_ru(PT.magXv[a][cc], wm, s1); }
+                S.Fk[0][a][bb] = iadd(S.Fk[0][a][bb], sym(s0));
+                S.boxFd[a][bb] = s1;
+            }
+            __syncthreads();
+        }
+        PROF(11);
+        TRC(9);
         // ---- grid loop (utils.cpp:219-252).  A lane owns ONE frame entry c and every (32/N^2)-th grid point: each coefficient
         //      Fk[k][c] is loaded once and feeds PPL independent Horner chains (shared-memory loads, not DFMAs, bound this loop).
         //      warp 0: point enclosures F(tau_i), i = 1..g   (F(0) = Fk[0] exactly)       -> EV[i]
@@ -919,7 +1186,7 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
                     for (int a = 0; a < N; a++)
 #pragma unroll
                         for (int bb = 0; bb < N; bb++) Fm[a][bb] = EV[((g + 1 + gi) * N + a) * N + bb];
-                    deriv_entries<N>(&S.Fk[0][0][0], S.rhoFd, p, tl, th, Dm);
+                    deriv_entries<N>(&S.Fk[0][0][0], &S.boxFd[0][0], p, tl, th, Dm);
                     dD = jacobi_derivative<N>(Fm, Dm);
                 }
                 decision = count_decide(timeI, dL, dR, dV, dD);
@@ -951,11 +1218,11 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
         }
         PROF(5);
         TRC(7);
-        // ---- set update (oracle/c1.hpp, same products and the same order of additions; the products of the r-update are
-        //      formed in the wide first phase so that the second phase is additions only) ----
+        // ---- set update (oracle/c2.hpp, same products and the same order of additions) ----
         if (tid < D) S.x[nxt][tid] = mid_ru(S.y[tid]);
         {
-            for (int t = tid; t < 3 * D * D; t += NT) {
+            // front:  C+ = mid(J C),  r+ = J r + (y - x+) + (J C - C+) r0      with J = Jc + [0,1] dJ
+            for (int t = tid; t < 2 * D * D; t += NT) {
                 const int e = t % (D * D), i = e / D, j = e % D;
                 if (t < D * D) {
                     ival a = pt(0.0);
@@ -964,17 +1231,63 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
                     const double cm = mid_ru(a);
                     S.C[nxt][i][j] = cm;
                     S.un.JC[i][j] = imul_nl(isub(a, pt(cm)), S.r0[j]);                 // (JC - C+)_ij * r0_j
-                } else if (t < 2 * D * D) {
-                    ival b = pt(0.0);
-#pragma unroll
-                    for (int k = 0; k < D; k++) b = iadd(b, imul_nl(S.J[i][k], S.P[cur][k][j]));
-                    S.P[nxt][i][j] = b;
                 } else {
                     S.un.JC[D + i][j] = imul_nl(S.J[i][j], S.r[cur][j]);
                 }
             }
+            // frame:  T+ = (Jc + sum_j Xi_j r0_j + Xi_r)(Tc + sum_l Theta_l r0_l + R):  Tc+ = mid(Jc Tc),
+            //         Theta_j+ = mid(Jc Theta_j + Xi_j Tc), R+ = everything else;  Ps+ = J Ps.  New values stay in registers until
+            //         every thread has read the old state.
+            constexpr int NTH = D * D * N, NR = D * N, NIT = NTH + 2 * NR, ROUNDS = (NIT + NT - 1) / NT;
+            double pv[ROUNDS]; ival iv[ROUNDS];
+#pragma unroll
+            for (int rd = 0; rd < ROUNDS; rd++) {
+                const int t = tid + rd * NT;
+                pv[rd] = 0.0; iv[rd] = pt(0.0);
+                if (t < NTH) {
+                    const int j = t / (D * N), i = (t / N) % D, k = t % N;
+                    ival a = pt(0.0);
+                    for (int l = 0; l < D; l++) a = iadd(a, imul_nl(S.Jc[i][l], pt(S.Th[j][l][k])));
+                    for (int l = 0; l < D; l++) a = iadd(a, imul_nl(PT.Xi[j][i][l], pt(S.Tc[l][k])));
+                    const double th = mid_ru(a);
+                    pv[rd] = th;
+                    PT.E[j][i][k] = imul_nl(isub(a, pt(th)), S.r0[j]);
+                } else if (t < NTH + NR) {
+                    const int e = t - NTH, i = e / N, k = e % N;
+                    ival a = pt(0.0);
+                    for (int l = 0; l < D; l++) a = iadd(a, imul_nl(S.Jc[i][l], pt(S.Tc[l][k])));
+                    const double tc = mid_ru(a);
+                    pv[rd] = tc;
+                    ival rr = isub(a, pt(tc));
+                    for (int l = 0; l < D; l++) rr = iadd(rr, imul_nl(S.Jc[i][l], S.R[l][k]));
+                    for (int l = 0; l < D; l++) rr = iadd(rr, imul_nl(PT.dJ[i][l], iadd(S.S0[l][k], S.R[l][k])));
+                    for (int l = 0; l < D; l++) rr = iadd(rr, imul_nl(PT.Xi[D][i][l], pt(S.Tc[l][k])));
+                    iv[rd] = rr;
+                } else if (t < NIT) {
+                    const int e = t - NTH - NR, i = e / N, k = e % N;
+                    ival a = pt(0.0);
+                    for (int l = 0; l < D; l++) a = iadd(a, imul_nl(S.J[i][l], S.Ps[l][k]));
+                    iv[rd] = a;
+                }
+            }
             __syncthreads();
             if (S.flag & 1) status = CCP_ST_NONFINITE;
+#pragma unroll
+            for (int rd = 0; rd < ROUNDS; rd++) {
+                const int t = tid + rd * NT;
+                if (t < NTH) {
+                    const int j = t / (D * N), i = (t / N) % D, k = t % N;
+                    S.Th[j][i][k] = pv[rd];
+                } else if (t < NTH + NR) {
+                    const int e = t - NTH, i = e / N, k = e % N;
+                    ival rr = iv[rd];
+                    for (int j = 0; j < D; j++) rr = iadd(rr, PT.E[j][i][k]);
+                    S.R[i][k] = rr; S.Tc[i][k] = pv[rd];
+                } else if (t < NIT) {
+                    const int e = t - NTH - NR, i = e / N, k = e % N;
+                    S.Ps[i][k] = iv[rd];
+                }
+            }
             if (tid < D) {
                 const int i = tid;
                 ival z = isub(S.y[i], pt(S.x[nxt][i]));
@@ -989,11 +1302,14 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
         TRC(8);
         tprev = mk(__dadd_rd(tprev.lo, hs), __dadd_ru(tprev.hi, hs));
         cur = nxt;
-        if (last && status == CCP_OK && tid < D) {
+        if (last && status == CCP_OK) {            // topFrame::getLastFrame: frame and front point at the end of the last step
             constexpr int ld = CCP_MAX_N + 2;
-            ival a = pt(S.x[cur][tid]);
-            for (int j = 0; j < D; j++) a = iadd(a, imul_nl(pt(S.C[cur][tid][j]), S.r0[j]));
-            gres->last_frame[tid * ld + N + 1] = toc(iadd(a, S.r[cur][tid]));
+            for (int t = tid; t < D * N; t += NT) { const int rr = t / N, k = t % N; ival s0; gres->last_frame[rr * ld + k] = toc(frame_entry<N>(S, rr, k, &s0)); }
+            if (tid < D) {
+                ival a = pt(S.x[cur][tid]);
+                for (int j = 0; j < D; j++) a = iadd(a, imul_nl(pt(S.C[cur][tid][j]), S.r0[j]));
+                gres->last_frame[tid * ld + N + 1] = toc(iadd(a, S.r[cur][tid]));
+            }
         }
     }
     __syncthreads();

@@ -12,7 +12,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "_build", "liboracle.so")
-MODE_REF, MODE_C1 = 0, 1
+MODE_REF, MODE_C1, MODE_C2 = 0, 1, 2      # c2 = twin of the CUDA kernel
 _lib = None
 
 

@@ -18,7 +18,7 @@ lib.ccp_debug_trace(buf, n)
 a = np.array(buf).reshape(2, 256, 2)
 print("fronts", nf, "kernel ms", eng.last_kernel_ms())
 t0 = a[0, 0, 0]
-names = {1: "step start", 2: "after hull+order0", 3: "after table loop", 4: "after y,J,Ws", 5: "after Fk", 6: "after eval", 7: "after dets+decide", 8: "after set update"}
+names = {1: "step start", 2: "after hull+order0", 3: "after table loop", 4: "after y,J,Ws", 5: "after Fk", 6: "after eval", 7: "after dets+decide", 8: "after set update", 9: "after boxF", 10: "after X1 (d2,d3)", 11: "after X2 (N_k)", 12: "after X3 (Xi)", 13: "after X4 (dJ)"}
 for w in range(2):
     print("warp", w)
     prev = None

@@ -57,5 +57,5 @@ def config1_ref(pkg, orc, config1_desc):
 
 
 @pytest.fixture(scope="session")
-def config1_c1(pkg, orc, config1_desc):
-    return orc.run_front(pkg.abi, config1_desc[0], orc.MODE_C1, series=True)
+def config1_c2(pkg, orc, config1_desc):
+    return orc.run_front(pkg.abi, config1_desc[0], orc.MODE_C2, series=True)

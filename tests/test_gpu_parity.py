@@ -2,8 +2,8 @@
 
 Bar (BASELINE.json north_star): conjugate-point counts and pass/fail exact; every GPU enclosure contains the
 oracle's point values; widths of the pinned quantities within 2x.  Because the kernel performs the same
-directed-rounding operations in the same order as oracle mode c1, GPU == c1 is checked BIT FOR BIT, and
-c1 <-> ref <-> plot_det.txt is checked by tests/test_oracle_golden.py on the CPU.
+directed-rounding operations in the same order as oracle mode c2, GPU == c2 is checked BIT FOR BIT, and
+c2 <-> ref <-> plot_det.txt is checked by tests/test_oracle_golden.py on the CPU.
 """
 import ctypes as C
 import os
@@ -74,13 +74,13 @@ def test_smoke(ge):
     ge.smoke()
 
 
-def test_config1_gpu_bit_identical_to_c1_and_pinned_to_reference(engine, pkg, orc, config1_desc, config1_c1, config1_ref):
+def test_config1_gpu_bit_identical_to_c2_and_pinned_to_reference(engine, pkg, orc, config1_desc, config1_c2, config1_ref):
     desc, _ = config1_desc
     res, ser = engine.frame_count_series(desc)
-    cr, cs = config1_c1
+    cr, cs = config1_c2
     assert ser.shape == cs.shape == (15176, 10)
-    assert _same_bits(ser, cs), "per-sub-interval series differ from oracle c1"
-    assert _same_bits(_raw(res), _raw(cr)), "result record differs from oracle c1"
+    assert _same_bits(ser, cs), "per-sub-interval series differ from oracle c2"
+    assert _same_bits(_raw(res), _raw(cr)), "result record differs from oracle c2"
     # counts / pass-fail exact against the reference-structured oracle
     rr, rs = config1_ref
     assert (res.status, res.zero_count, res.failure_count, res.steps) == (rr.status, rr.zero_count, rr.failure_count, rr.steps) == (0, 2, 0, 1084)
@@ -107,12 +107,12 @@ def test_batch_equals_series_path(engine, pkg, config1_desc):
     assert _same_bits(_raw(batch[0]), _raw(single))
 
 
-def test_reference_sweep_gpu_bit_identical_to_c1(engine, pkg, orc):
+def test_reference_sweep_gpu_bit_identical_to_c2(engine, pkg, orc):
     """The reference's own 96-point sweep (SampleParameters, heteroclinic.cpp:437-443)."""
     params = pkg.parameter_list(24, 4)
     descs, infos = pkg.setup_sweep(3, params)
     gpu = engine.frame_count_batch(descs)
-    cpu, _ = orc.run_batch(pkg.abi, descs, orc.MODE_C1)
+    cpu, _ = orc.run_batch(pkg.abi, descs, orc.MODE_C2)
     a = np.frombuffer(gpu, dtype=np.float64).reshape(96, -1)
     b = np.frombuffer(cpu, dtype=np.float64).reshape(96, -1)
     assert _same_bits(a, b)
@@ -148,7 +148,7 @@ def test_counts_match_reference_structured_oracle_on_sweep_sample(engine, pkg, o
 def test_other_dimensions_bit_identical(engine, pkg, orc, n, params, expected):
     desc, _ = pkg.setup_front(n, params)
     g, gs = engine.frame_count_series(desc)
-    c, cs = orc.run_front(pkg.abi, desc, orc.MODE_C1, series=True)
+    c, cs = orc.run_front(pkg.abi, desc, orc.MODE_C2, series=True)
     assert _same_bits(gs, cs) and _same_bits(_raw(g), _raw(c))
     assert (g.status, g.failure_count, g.zero_count) == (0, 0, expected)
 
@@ -164,7 +164,7 @@ def test_mixed_batch_and_edge_cases(engine, pkg, orc):
         far.p_i[i].lo, far.p_i[i].hi = 3.0, 3.0
     batch = (abi.FrontDesc * 6)(d3, d2, d4, bad, far, d2)
     gpu = engine.frame_count_batch(batch)
-    cpu, _ = orc.run_batch(abi, batch, orc.MODE_C1, threads=2)
+    cpu, _ = orc.run_batch(abi, batch, orc.MODE_C2, threads=2)
     assert [r.status for r in gpu] == [0, 0, 0, abi.CCP_ST_BAD_DESC, abi.CCP_ST_ENCLOSURE, 0]
     for g, c in zip(gpu, cpu):
         assert _same_bits(_raw(g), _raw(c))
@@ -216,7 +216,7 @@ def test_config4_subboxes(engine, pkg, orc):
     desc, _ = pkg.setup_front(3, [1.0, .98, .96, .04, .02], pkg.abi.SetupOpts.default(L_minus_override=26.0))
     subs = pkg.subdivide_front(desc, 4)
     gpu = engine.frame_count_batch(subs)
-    cpu, _ = orc.run_batch(pkg.abi, subs, orc.MODE_C1)
+    cpu, _ = orc.run_batch(pkg.abi, subs, orc.MODE_C2)
     a = np.frombuffer(gpu, dtype=np.float64).reshape(len(subs), -1)
     b = np.frombuffer(cpu, dtype=np.float64).reshape(len(subs), -1)
     assert _same_bits(a, b)
@@ -237,7 +237,7 @@ def test_config5_n4_throughput_path(engine, pkg, orc):
     descs, infos = pkg.setup_sweep(4, np.array(params))
     assert all(i.converged == 1 for i in infos)
     gpu = engine.frame_count_batch(descs)
-    cpu, _ = orc.run_batch(pkg.abi, descs, orc.MODE_C1)
+    cpu, _ = orc.run_batch(pkg.abi, descs, orc.MODE_C2)
     assert _same_bits(np.frombuffer(gpu, dtype=np.float64), np.frombuffer(cpu, dtype=np.float64))
     assert [r.status for r in gpu] == [0, 0, 0]
     assert gpu[0].zero_count == 3 and gpu[0].failure_count == 0
@@ -250,7 +250,7 @@ def test_non_default_order_step_grid(engine, pkg, orc, order, step_log2, grid):
     opts = pkg.abi.SetupOpts.default(L_minus_override=3.3, order=order, step_log2=step_log2, grid=grid)
     desc, _ = pkg.setup_front(3, [1.0, .98, .96, .04, .02], opts)
     g, gs = engine.frame_count_series(desc)
-    c, cs = orc.run_front(pkg.abi, desc, orc.MODE_C1, series=True)
+    c, cs = orc.run_front(pkg.abi, desc, orc.MODE_C2, series=True)
     assert gs.shape == cs.shape and gs.shape[0] == g.steps * grid
     assert _same_bits(gs, cs) and _same_bits(_raw(g), _raw(c))
     assert g.status == c.status
