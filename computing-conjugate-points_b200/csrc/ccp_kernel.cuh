@@ -65,8 +65,11 @@ struct Majorant { double rho_phi, rho_phi_d, rho_psi, rho_psi_d, g1, g5; ival Gs
 // parameter interval as sign * [pl, ph] with 0 <= pl <= ph (see imul_par)
 struct SPar { double pl, ph; int neg, straddle; };
 
-// low-order Taylor data over the hull [X] of the phi-set (oracle/c2.hpp): w_k = coefficients of u - 1/2, M_0, M_1 (tridiagonal)
-template <int N> struct HullQ { ival w[4][N], Md0[N], Mo0[N], Md1[N], Mo1[N]; };
+// low-order Taylor data over the hull [X] of the phi-set (oracle/c2.hpp:HullM): W[q] = coefficients of u - 1/2 (q <= 3),
+// G = u(1-u), Pw = w_0 w_1, dense tridiagonal M_0, M_1 -- all in (mid,t) form
+template <int N> struct HullM { mt W[4][N], G[N], Pw[N], M0[N][N], M1[N][N]; };
+// parameter tables of a front (oracle/c2.hpp:ParM); missing chain neighbours are zero parameters
+template <int N> struct ParM { mt B[N], B3[N], B6[N], Cm[N], Cp[N], C2m[N], C2p[N], C2[N]; ival halfB[N]; mt PN[N][N][3]; };
 
 // Overlay of the Taylor-table array once the tables of a step are dead (after the frame tables F_k are built).
 template <int N> struct PostTab {
@@ -78,7 +81,10 @@ template <int N> struct PostTab {
     ival DT[3 * (GMAX + 1)];                 // determinants of the grid loop
     union {
         ival EV[(2 * GMAX + 1) * N * N];     // frame enclosures of the grid loop
-        struct { ival DD[D + 1][4][N]; ival NN[D + 1][4][2 * N - 1]; double AM[D + 1][D][D]; } x;   // transients of the second-variation phase
+        struct {                             // transients of the second-variation phase (AM reuses WD, NN reuses DD)
+            union { mt WD[D + 1][4][N][N]; double AM[D + 1][D][D]; };
+            union { mt DD[D + 1][4][N]; mt NN[D + 1][4][N][N]; };
+        } x;
     } u;
 };
 
@@ -86,7 +92,8 @@ template <int N>
 struct FrontSmem {
     static constexpr int D = 2 * N;
     static constexpr int NE = (N > 1) ? (N - 1) : 1;
-    mt T[Lay<N>::NS][KMAX];                  // Taylor tables of the centre trajectory; PostTab overlays them once they are dead
+    static constexpr int TROWS = (int)((sizeof(PostTab<N>) + KMAX * sizeof(mt) - 1) / (KMAX * sizeof(mt))) > Lay<N>::NS ? (int)((sizeof(PostTab<N>) + KMAX * sizeof(mt) - 1) / (KMAX * sizeof(mt))) : Lay<N>::NS;
+    mt T[TROWS][KMAX];                       // Taylor tables of the centre trajectory; PostTab overlays them once they are dead
     ival Fk[KMAX][N][N];
     // front set x + C r0 + r (double buffered)
     double x[2][D], C[2][D][D];
@@ -96,7 +103,9 @@ struct FrontSmem {
     ival R[D][N], Ps[D][N], S0[D][N];
     ival r0[D], Err[N][N], X[D], y[D], Jc[D][D], J[D][D], Ws[D][N], bpar[N], cpar[NE];
     mt Wm[D][N];
-    HullQ<N> hq;
+    HullM<N> hm;
+    ParM<N> pm;
+    mt r0m[D + 1], Errm[N][N];               // (mid,t) forms; r0m[D] = 1 weights the direction "box r"
     double boxFd[N][N];
     double invlo[KMAX + 2], invhi[KMAX + 2]; // [rd(1/k), ru(1/k)]
     double gp[GMAX + 1];                     // grid points of the current step (utils.cpp:219-223)
@@ -108,13 +117,14 @@ struct FrontSmem {
     double g15[2];
     union alignas(16) {
         ival scratch[Lay<N>::NB + Lay<N>::NC + 2 * N];   // table loop: Cauchy sums awaiting combination; then [0,0]; then the newest hull g, q
-        ival JC[4 * N][2 * N];               // set update: rows 0..2n-1 = (J*C - C+)_ij r0_j, rows 2n..4n-1 = J_ij r_j
+        mt JCr[2 * N][2 * N];                // set update: J*C - C+
         ccp_front_desc desc;                 // start of the front only
     } un;
 };
 
 static_assert(sizeof(PostTab<2>) <= sizeof(FrontSmem<2>::T) && sizeof(PostTab<3>) <= sizeof(FrontSmem<3>::T) && sizeof(PostTab<4>) <= sizeof(FrontSmem<4>::T),
               "PostTab must fit into the table array");
+static_assert(FrontSmem<3>::TROWS == Lay<3>::NS, "n = 3: the overlay must not enlarge the table array (7 CTAs per SM)");
 static_assert(sizeof(ccp_front_desc) % 16 == 0, "descriptors are staged with 16-byte loads");
 static_assert(sizeof(ccp_front_result) % 16 == 0, "result records are 16-byte aligned");
 
@@ -252,39 +262,14 @@ __device__ __forceinline__ ccp_interval toc(const ival& a) { ccp_interval o; o.l
 __device__ __forceinline__ ival fromc(const ccp_interval& a) { return mk(a.lo, a.hi); }
 
 
-// ---- second variation helpers (oracle/c2.hpp, same expression order) ----
+// ---- helpers of the second-variation / set-update phases (oracle/c2.hpp, same expression order) ----
 __device__ __forceinline__ ival ihalf(const ival& a) { return mk(0.5 * a.lo, 0.5 * a.hi); }
 __device__ __forceinline__ ival idivk_tab(const ival& a, const double* ilo, const double* ihi, int k);
-// row i of (symmetric tridiagonal: diag dg, off-diagonal od) * vector
-template <int N>
-__device__ __forceinline__ ival tri_row(const ival* dg, const ival* od, const ival* v, int i) {
-    ival a = imul_nl(dg[i], v[i]);
-    if (i > 0)     a = iadd(a, imul_nl(od[i - 1], v[i - 1]));
-    if (i < N - 1) a = iadd(a, imul_nl(od[i], v[i + 1]));
-    return a;
-}
-__device__ __forceinline__ ival tri(const ival* dg, const ival* od, int i, int k) {
-    if (i == k) return dg[i];
-    if (k == i + 1) return od[i];
-    if (k == i - 1) return od[k];
-    return pt(0.0);
-}
-template <int N> __device__ __forceinline__ ival tri_e(const ival* dgod, int i, int k) { return tri(dgod, dgod + N, i, k); }
-template <int N>
-__device__ __noinline__ ival tri_mul(const ival* ad, const ival* ao, const ival* bd, const ival* bo, int i, int k) {
-    ival a = pt(0.0);
-    for (int l = 0; l < N; l++) {
-        if (l < i - 1 || l > i + 1 || l < k - 1 || l > k + 1) continue;
-        a = iadd(a, imul_nl(tri(ad, ao, i, l), tri(bd, bo, l, k)));
-    }
-    return a;
-}
-// (w_i d_m)_k = sum_{q<=k} w_q[i] d_{k-q}[m]
-template <int N>
-__device__ __noinline__ ival wd_coef(const HullQ<N>& H, const ival (*dd)[N], int i, int m, int k) {
-    ival a = imul_nl(H.w[0][i], dd[k][m]);
-    for (int q = 1; q <= k; q++) a = iadd(a, imul_nl(H.w[q][i], dd[k - q][m]));
-    return a;
+__device__ __forceinline__ mt ptm(double v) { mt o; o.m = v; o.t = fabs(v); return o; }      // iv2mt of a point
+// a += x * p for a point p: one directed FMA per bound (tighter than a rounded product plus a rounded sum)
+__device__ __forceinline__ void ipfma(ival& a, const ival& x, double p) {
+    const double l = p >= 0 ? x.lo : x.hi, h = p >= 0 ? x.hi : x.lo;
+    a.lo = __fma_rd(l, p, a.lo); a.hi = __fma_ru(h, p, a.hi);
 }
 
 // host-side twin of oracle/common.hpp:step_count
@@ -545,41 +530,283 @@ __device__ inline void majorant2(const ival* b, const ival* c, double h, double*
     out[0] = ga[1]; out[1] = ga[5];
 }
 
-template <int N> struct FrontSmem;
 // oracle/c2.hpp:frame_of_state, one entry:  S0 = sum_j Theta_j r0_j ;  W = ((Tc + S0) + R) + Ps Err
 template <int N>
-__device__ __noinline__ ival frame_entry(const FrontSmem<N>& S, int cc, int bb, ival* s0out) {
+__device__ __forceinline__ ival frame_entry(const FrontSmem<N>& S, int cc, int bb, ival* s0out) {
     constexpr int D = 2 * N;
     ival a = pt(0.0);
-    for (int j = 0; j < D; j++) a = iadd(a, imul_nl(pt(S.Th[j][cc][bb]), S.r0[j]));
+#pragma unroll
+    for (int j = 0; j < D; j++) ipfma(a, S.r0[j], S.Th[j][cc][bb]);
     *s0out = a;
-    ival w = iadd(iadd(pt(S.Tc[cc][bb]), a), S.R[cc][bb]);
-    for (int j = 0; j < N; j++) w = iadd(w, imul_nl(S.Ps[cc][j], S.Err[j][bb]));
-    return w;
+    acc4 e = acc_zero();
+#pragma unroll
+    for (int j = 0; j < N; j++) acc_term(e, iv2mt(S.Ps[cc][j]), S.Errm[j][bb]);
+    return iadd(iadd(iadd(pt(S.Tc[cc][bb]), a), S.R[cc][bb]), acc_finish(e));
 }
-// low-order hull data, row i (oracle/c2.hpp "hull, low order"); w_3 follows after a barrier (it needs all rows of M_0)
+
+// ---- second variation over the hull (oracle/c2.hpp): directions c_j = C e_j (j < D, weight r0_j) and the box r (j = D, weight 1).
+//      All sums are dense fixed-length dot products in (mid,t) form (missing chain neighbours = zero parameters), so every stage is
+//      one branch-free instruction stream over (direction, entry) items.  Called by all threads of the CTA. ----
 template <int N>
-__device__ __noinline__ void hull_row(FrontSmem<N>& S, int i) {
-    HullQ<N>& H = S.hq;
-    auto W0 = [&](int m) { return isub(S.X[m], pt(0.5)); };
-    auto G0 = [&](int m) { return imul_nl(S.X[m], isub(pt(1.0), S.X[m])); };
-    const ival w0 = W0(i), w1 = S.X[N + i], g0 = G0(i);
-    H.w[0][i] = w0; H.w[1][i] = w1;
-    ival f = ineg(imul_nl(imul_nl(g0, w0), S.bpar[i]));
-    if (i > 0)     f = isub(f, imul_nl(imul_nl(G0(i - 1), w0), S.cpar[i - 1]));
-    if (i < N - 1) f = isub(f, imul_nl(imul_nl(G0(i + 1), w0), S.cpar[i]));
-    H.w[2][i] = ihalf(f);
-    ival dd = ineg(imul_nl(S.bpar[i], isub(imulk(g0, 3), pt(0.5))));
-    if (i > 0)     dd = isub(dd, imul_nl(S.cpar[i - 1], G0(i - 1)));
-    if (i < N - 1) dd = isub(dd, imul_nl(S.cpar[i], G0(i + 1)));
-    H.Md0[i] = dd;
-    if (i < N - 1) H.Mo0[i] = imul_nl(imulk(imul_nl(w0, W0(i + 1)), 2), S.cpar[i]);
-    ival m1 = imulk(imul_nl(S.bpar[i], imul_nl(w0, w1)), 6);
-    if (i > 0)     m1 = iadd(m1, imulk(imul_nl(S.cpar[i - 1], imul_nl(W0(i - 1), S.X[N + i - 1])), 2));
-    if (i < N - 1) m1 = iadd(m1, imulk(imul_nl(S.cpar[i], imul_nl(W0(i + 1), S.X[N + i + 1])), 2));
-    H.Md1[i] = m1;
-    if (i < N - 1) H.Mo1[i] = imulk(imul_nl(S.cpar[i], iadd(imul_nl(w0, S.X[N + i + 1]), imul_nl(w1, W0(i + 1)))), 2);
+__device__ __noinline__ void second_variation(FrontSmem<N>& S, PostTab<N>& PT, int cur, double hs, double g5) {
+    constexpr int D = 2 * N;
+    const int tid = threadIdx.x;
+    HullM<N>& H = S.hm;
+    // H-A: W_0, W_1, G = u(1-u), Pw = w_0 w_1;  off-diagonals of M_0, M_1
+    if (tid < N) {
+        const int m = tid;
+        const ival u = S.X[m];
+        const mt w0 = iv2mt(isub(u, pt(0.5))), w1 = iv2mt(S.X[N + m]);
+        H.W[0][m] = w0; H.W[1][m] = w1; H.G[m] = iv2mt(imul(u, isub(pt(1.0), u)));
+        acc4 a = acc_zero(); acc_term(a, w0, w1); H.Pw[m] = iv2mt(acc_finish(a));
+    } else if (tid >= 32 && tid < 32 + N - 1) {
+        const int e = tid - 32;
+        const mt w0a = iv2mt(isub(S.X[e], pt(0.5))), w0b = iv2mt(isub(S.X[e + 1], pt(0.5))), w1a = iv2mt(S.X[N + e]), w1b = iv2mt(S.X[N + e + 1]);
+        acc4 a = acc_zero(); acc_term(a, w0a, w0b);
+        acc4 a2 = acc_zero(); acc_term(a2, S.pm.C2[e], iv2mt(acc_finish(a)));
+        const mt m0 = iv2mt(acc_finish(a2));
+        H.M0[e][e + 1] = m0; H.M0[e + 1][e] = m0;
+        acc4 u = acc_zero(); acc_term(u, w0a, w1b); acc_term(u, w1a, w0b);
+        acc4 u2 = acc_zero(); acc_term(u2, S.pm.C2[e], iv2mt(acc_finish(u)));
+        const mt m1 = iv2mt(acc_finish(u2));
+        H.M1[e][e + 1] = m1; H.M1[e + 1][e] = m1;
+    }
+    __syncthreads();
+    // H-B: u_2 = F(u)/2, diagonals of M_0, M_1
+    if (tid < N) {
+        const int i = tid, im = i > 0 ? i - 1 : 0, ip = i < N - 1 ? i + 1 : N - 1;
+        const mt gi = H.G[i], gm = H.G[im], gp = H.G[ip];
+        acc4 sa = acc_zero(); acc_term(sa, S.pm.B[i], gi); acc_term(sa, S.pm.Cm[i], gm); acc_term(sa, S.pm.Cp[i], gp);
+        H.W[2][i] = iv2mt(ihalf(ineg(imul(isub(S.X[i], pt(0.5)), acc_finish(sa)))));
+        acc4 ta = acc_zero(); acc_term(ta, S.pm.B3[i], gi); acc_term(ta, S.pm.Cm[i], gm); acc_term(ta, S.pm.Cp[i], gp);
+        H.M0[i][i] = iv2mt(isub(S.pm.halfB[i], acc_finish(ta)));
+        acc4 ma = acc_zero(); acc_term(ma, S.pm.B6[i], H.Pw[i]); acc_term(ma, S.pm.C2m[i], H.Pw[im]); acc_term(ma, S.pm.C2p[i], H.Pw[ip]);
+        H.M1[i][i] = iv2mt(acc_finish(ma));
+    }
+    __syncthreads();
+    // X1: u_3 = M_0 u_1 / 6;  d_0..d_3 of every direction
+    if (tid >= 32 && tid < 32 + N) {
+        const int i = tid - 32;
+        acc4 a = acc_zero();
+#pragma unroll
+        for (int l = 0; l < N; l++) acc_term(a, H.M0[i][l], H.W[1][l]);
+        H.W[3][i] = iv2mt(idivk_tab(acc_finish(a), S.invlo, S.invhi, 6));
+    }
+    for (int t = tid; t < (D + 1) * N; t += NT) {
+        const int j = t / N, m = t % N;
+        mt d0[N], d1[N];
+#pragma unroll
+        for (int l = 0; l < N; l++) {
+            if (j < D) { d0[l] = ptm(S.C[cur][l][j]); d1[l] = ptm(S.C[cur][N + l][j]); }
+            else       { d0[l] = iv2mt(S.r[cur][l]);  d1[l] = iv2mt(S.r[cur][N + l]); }
+        }
+        acc4 a2 = acc_zero(), a3 = acc_zero();
+#pragma unroll
+        for (int l = 0; l < N; l++) acc_term(a2, H.M0[m][l], d0[l]);
+#pragma unroll
+        for (int l = 0; l < N; l++) acc_term(a3, H.M1[m][l], d0[l]);
+#pragma unroll
+        for (int l = 0; l < N; l++) acc_term(a3, H.M0[m][l], d1[l]);
+        mt dm0 = d0[0], dm1 = d1[0];
+#pragma unroll
+        for (int l = 1; l < N; l++) if (l == m) { dm0 = d0[l]; dm1 = d1[l]; }
+        PT.u.x.DD[j][0][m] = dm0; PT.u.x.DD[j][1][m] = dm1;
+        PT.u.x.DD[j][2][m] = iv2mt(ihalf(acc_finish(a2)));
+        PT.u.x.DD[j][3][m] = iv2mt(idivk_tab(acc_finish(a3), S.invlo, S.invhi, 6));
+    }
+    __syncthreads();
+    // X2a: product series (w_i d_m)_k, k <= 3, all N x N pairs
+    for (int t = tid; t < (D + 1) * 4 * N * N; t += NT) {
+        const int j = t / (4 * N * N), k = (t / (N * N)) % 4, i = (t / N) % N, m = t % N;
+        acc4 a = acc_zero();
+#pragma unroll
+        for (int q = 0; q < 4; q++) if (q <= k) acc_term(a, H.W[q][i], PT.u.x.DD[j][k - q][m]);
+        PT.u.x.WD[j][k][i][m] = iv2mt(acc_finish(a));
+    }
+    __syncthreads();
+    // X2b: Taylor coefficients N_k of DM(u)[Psi^u c_j] (dense): three parameter * product-series slots per entry
+    for (int t = tid; t < (D + 1) * 4 * N * N; t += NT) {
+        const int j = t / (4 * N * N), k = (t / (N * N)) % 4, i = (t / N) % N, l = t % N;
+        acc4 a = acc_zero();
+#pragma unroll
+        for (int sl = 0; sl < 3; sl++) {
+            int ia, ib;
+            if (i == l) { ia = ib = sl == 0 ? i : (sl == 1 ? (i > 0 ? i - 1 : 0) : (i < N - 1 ? i + 1 : N - 1)); }
+            else { const int e = i < l ? i : l; const int e1 = e + 1 < N ? e + 1 : N - 1; if (sl == 0) { ia = e1; ib = e; } else { ia = e; ib = e1; } }
+            acc_term(a, S.pm.PN[i][l][sl], PT.u.x.WD[j][k][ia][ib]);
+        }
+        PT.u.x.NN[j][k][i][l] = iv2mt(acc_finish(a));          // NN overlays DD (dead since X2a)
+    }
+    __syncthreads();
+    // X3: the four n x n blocks of Xi_j(hs) = sum_{k<=4} Xi_k hs^k + remainder, one (j, i, k) entry of each block per item
+    const double hs2 = __dmul_ru(hs, hs), hs5 = __dmul_ru(__dmul_ru(hs2, hs2), hs);
+    for (int t = tid; t < (D + 1) * N * N; t += NT) {
+        const int j = t / (N * N), i = (t / N) % N, k = t % N;
+        double c1n = 0;
+#pragma unroll
+        for (int q = 0; q < D; q++) c1n = __dadd_ru(c1n, j < D ? fabs(S.C[cur][q][j]) : imag(S.r[cur][q]));
+        const double rem = __dmul_ru(__dmul_ru(g5, hs5), c1n);
+        const mt (*NN)[N][N] = PT.u.x.NN[j];
+        acc4 p00 = acc_zero(), p01 = acc_zero(), p10 = acc_zero();
+#pragma unroll
+        for (int l = 0; l < N; l++) acc_term(p00, H.M0[i][l], NN[0][l][k]);
+#pragma unroll
+        for (int l = 0; l < N; l++) acc_term(p00, NN[0][i][l], H.M0[l][k]);
+#pragma unroll
+        for (int l = 0; l < N; l++) acc_term(p01, H.M0[i][l], NN[1][l][k]);
+#pragma unroll
+        for (int l = 0; l < N; l++) acc_term(p01, NN[0][i][l], H.M1[l][k]);
+#pragma unroll
+        for (int l = 0; l < N; l++) acc_term(p10, H.M1[i][l], NN[0][l][k]);
+#pragma unroll
+        for (int l = 0; l < N; l++) acc_term(p10, NN[1][i][l], H.M0[l][k]);
+        const ival P00 = acc_finish(p00), P01 = acc_finish(p01), P10 = acc_finish(p10);
+        const ival N0 = mt2iv(NN[0][i][k]), N1 = mt2iv(NN[1][i][k]), N2 = mt2iv(NN[2][i][k]), N3 = mt2iv(NN[3][i][k]);
+        const double* il = S.invlo; const double* ih = S.invhi;
+        const ival X3 = idivk_tab(iadd(N2, ihalf(P00)), il, ih, 3);
+        const ival Z = pt(0.0);
+        const ival hN0 = ihalf(N0);
+        // cf[block][order-1]: blocks 0 UU, 1 UV, 2 VU, 3 VV
+        const ival c3[4] = { idivk_tab(X3, il, ih, 4), idivk_tab(N1, il, ih, 12),
+                             idivk_tab(iadd(iadd(N3, idivk_tab(P01, il, ih, 6)), ihalf(P10)), il, ih, 4), idivk_tab(iadd(N2, idivk_tab(P00, il, ih, 6)), il, ih, 4) };
+        const ival c2[4] = { idivk_tab(N1, il, ih, 6), idivk_tab(N0, il, ih, 6), X3, idivk_tab(N1, il, ih, 3) };
+        const ival c1[4] = { hN0, Z, ihalf(N1), hN0 };
+        const ival c0[4] = { Z, Z, N0, Z };
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            ival acc = c3[q]; double am = imag(c3[q]);
+            acc = horner_pt(acc, hs, c2[q]); am = __fma_ru(am, hs, imag(c2[q]));
+            acc = horner_pt(acc, hs, c1[q]); am = __fma_ru(am, hs, imag(c1[q]));
+            acc = horner_pt(acc, hs, c0[q]); am = __fma_ru(am, hs, imag(c0[q]));
+            acc = horner_pt(acc, hs, Z); am = __dmul_ru(am, hs);
+            const int row = (q >> 1) * N + i, col = (q & 1) * N + k;
+            PT.Xi[j][row][col] = iadd(acc, sym(rem));
+            PT.u.x.AM[j][row][col] = __dadd_ru(am, rem);        // AM overlays WD (dead since X2b)
+        }
+    }
+    __syncthreads();
+    // X4: dJ = sum_j Xi_j r0_j + Xi_r encloses DPhi(phi) - DPhi(x) on the set; J = Jc + [0,1] dJ for the mean-value form of the
+    //     phi-set update; magX >= sup over [0,hs] of |Psi(tau;phi) - Psi(tau;x)|
+    for (int t = tid; t < D * D; t += NT) {
+        const int row = t / D, col = t % D;
+        acc4 a = acc_zero(); double mg = 0.0;
+#pragma unroll
+        for (int j = 0; j <= D; j++) {
+            acc_term(a, iv2mt(PT.Xi[j][row][col]), S.r0m[j]);
+            mg = __fma_ru(PT.u.x.AM[j][row][col], j < D ? imag(S.r0[j]) : 1.0, mg);
+        }
+        const ival dj = acc_finish(a);
+        PT.dJ[row][col] = dj;
+        S.J[row][col] = iadd(S.Jc[row][col], ihull(dj, pt(0.0)));
+        if (row < N) PT.magXu[row][col] = mg; else PT.magXv[row - N][col] = mg;
+    }
+    __syncthreads();
+    // truncation box of the centre tables + box for (Psi(tau;phi) - Psi(tau;x)) W on [0,hs]; same for the derivative
+    if (tid < N * N) {
+        const int a = tid / N, bb = tid % N;
+        double sm = 0;
+#pragma unroll
+        for (int cc = 0; cc < D; cc++) sm = __dadd_ru(sm, imag(S.Ws[cc][bb]));
+        double s0 = __dmul_ru(S.mj.rho_psi, sm), s1 = __dmul_ru(S.mj.rho_psi_d, sm);
+#pragma unroll
+        for (int cc = 0; cc < D; cc++) { const double wm = imag(S.Ws[cc][bb]); s0 = __fma_ru(PT.magXu[a][cc], wm, s0); s1 = __fma_ru(PT.magXv[a][cc], wm, s1); }
+        S.Fk[0][a][bb] = iadd(S.Fk[0][a][bb], sym(s0));
+        S.boxFd[a][bb] = s1;
+    }
+    __syncthreads();
 }
+
+// ---- set update (oracle/c2.hpp, same products and the same order of additions).  Called by all threads of the CTA.
+//   front:  C+ = mid(J C),  r+ = J r + (y - x+) + (J C - C+) r0      with J = Jc + [0,1] dJ
+//   frame:  T+ = (Jc + sum_j Xi_j r0_j + Xi_r)(Tc + sum_l Theta_l r0_l + R):  Tc+ = mid(Jc Tc), Theta_j+ = mid(Jc Theta_j + Xi_j Tc),
+//           R+ = everything else;  Ps+ = J Ps.  Products with a point factor are fused interval*point accumulations (one rounding per
+//           bound and term: the rounding noise of Jc Tc goes straight into R); the rest are (mid,t) dot products.
+//   New values stay in registers until every thread has read the old state.  Returns the non-finite flag. ----
+template <int N>
+__device__ __noinline__ int set_update(FrontSmem<N>& S, PostTab<N>& PT, int cur, int nxt) {
+    constexpr int D = 2 * N;
+    const int tid = threadIdx.x;
+    if (tid < D) S.x[nxt][tid] = mid_ru(S.y[tid]);
+    constexpr int NJC = D * D, NTH = D * D * N, NR = D * N, NIT = NJC + NTH + 2 * NR, ROUNDS = (NIT + NT - 1) / NT;
+    double pv[ROUNDS]; ival iv[ROUNDS];
+#pragma unroll
+    for (int rd = 0; rd < ROUNDS; rd++) {
+        const int t = tid + rd * NT;
+        pv[rd] = 0.0; iv[rd] = pt(0.0);
+        if (t < NTH) {
+            const int j = t / (D * N), i = (t / N) % D, k = t % N;
+            ival a = pt(0.0);
+#pragma unroll
+            for (int l = 0; l < D; l++) ipfma(a, S.Jc[i][l], S.Th[j][l][k]);
+#pragma unroll
+            for (int l = 0; l < D; l++) ipfma(a, PT.Xi[j][i][l], S.Tc[l][k]);
+            const double th = mid_ru(a);
+            pv[rd] = th;
+            PT.E[j][i][k] = imul(isub(a, pt(th)), S.r0[j]);
+        } else if (t < NTH + NJC) {
+            const int e = t - NTH, i = e / D, j = e % D;
+            ival a = pt(0.0);
+#pragma unroll
+            for (int k = 0; k < D; k++) ipfma(a, S.J[i][k], S.C[cur][k][j]);
+            const double cm = mid_ru(a);
+            S.C[nxt][i][j] = cm;
+            S.un.JCr[i][j] = iv2mt(isub(a, pt(cm)));
+        } else if (t < NTH + NJC + NR) {
+            const int e = t - NTH - NJC, i = e / N, k = e % N;
+            ival jt = pt(0.0);
+#pragma unroll
+            for (int l = 0; l < D; l++) ipfma(jt, S.Jc[i][l], S.Tc[l][k]);
+            const double tc = mid_ru(jt);
+            pv[rd] = tc;
+            acc4 ea = acc_zero();
+#pragma unroll
+            for (int l = 0; l < D; l++) acc_term(ea, iv2mt(S.Jc[i][l]), iv2mt(S.R[l][k]));
+#pragma unroll
+            for (int l = 0; l < D; l++) acc_term(ea, iv2mt(PT.dJ[i][l]), iv2mt(iadd(S.S0[l][k], S.R[l][k])));
+            ival xr = pt(0.0);
+#pragma unroll
+            for (int l = 0; l < D; l++) ipfma(xr, PT.Xi[D][i][l], S.Tc[l][k]);
+            iv[rd] = iadd(iadd(isub(jt, pt(tc)), acc_finish(ea)), xr);
+        } else if (t < NIT) {
+            const int e = t - NTH - NJC - NR, i = e / N, k = e % N;
+            acc4 a = acc_zero();
+#pragma unroll
+            for (int l = 0; l < D; l++) acc_term(a, iv2mt(S.J[i][l]), iv2mt(S.Ps[l][k]));
+            iv[rd] = acc_finish(a);
+        }
+    }
+    __syncthreads();
+    const int nonfinite = S.flag & 1;
+#pragma unroll
+    for (int rd = 0; rd < ROUNDS; rd++) {
+        const int t = tid + rd * NT;
+        if (t < NTH) {
+            const int j = t / (D * N), i = (t / N) % D, k = t % N;
+            S.Th[j][i][k] = pv[rd];
+        } else if (t >= NTH + NJC && t < NTH + NJC + NR) {
+            const int e = t - NTH - NJC, i = e / N, k = e % N;
+            ival rr = iv[rd];
+#pragma unroll
+            for (int j = 0; j < D; j++) rr = iadd(rr, PT.E[j][i][k]);
+            S.R[i][k] = rr; S.Tc[i][k] = pv[rd];
+        } else if (t >= NTH + NJC + NR && t < NIT) {
+            const int e = t - NTH - NJC - NR, i = e / N, k = e % N;
+            S.Ps[i][k] = iv[rd];
+        }
+    }
+    if (tid < D) {
+        const int i = tid;
+        acc4 a = acc_zero();
+#pragma unroll
+        for (int j = 0; j < D; j++) acc_term(a, S.un.JCr[i][j], S.r0m[j]);
+#pragma unroll
+        for (int j = 0; j < D; j++) acc_term(a, iv2mt(S.J[i][j]), iv2mt(S.r[cur][j]));
+        S.r[nxt][i] = iadd(isub(S.y[i], pt(S.x[nxt][i])), acc_finish(a));
+    }
+    __syncthreads();
+    return nonfinite;
+}
+
 // phi' = (v, F(u)) over the sub-interval [tl,th] of the step and over the whole set (last column of the first / last frame,
 // topFrame.cpp:265-331), row i:  phi(tau) in phi_c(tau) + Psi(tau;xi)(phi0 - x),  |Psi(tau;xi) - Psi_c(tau)| <= g1 tau |phi0 - x|_1
 template <int N>
@@ -670,6 +897,9 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
         }
         for (int t = tid; t < D * D; t += NT) { int i = t / D, j = t % D; double a = d.A_u[i * CCP_MAX_DIM + j]; S.C[0][i][j] = a; if (j < N) { S.Tc[i][j] = a; S.R[i][j] = pt(0.0); } else S.Ps[i][j - N] = pt(a); }
         for (int t = tid; t < D * D * N; t += NT) (&S.Th[0][0][0])[t] = 0.0;
+        for (int t = tid; t < N * N; t += NT) { mt z; z.m = 0.0; z.t = 0.0; S.hm.M0[t / N][t % N] = z; S.hm.M1[t / N][t % N] = z; }
+        if (tid >= 32 && tid < 32 + D + 1) { const int j = tid - 32; S.r0m[j] = j < D ? iv2mt(fromc(d.Uxy[j])) : ptm(1.0); }
+        for (int t = tid; t < N * N; t += NT) { const int j = t / N, k = t % N; S.Errm[j][k] = iv2mt(fromc(d.Eu_err[j * CCP_MAX_N + k])); }
         for (int t = tid; t < N * N; t += NT) { int j = t / N, k = t % N; S.Err[j][k] = fromc(d.Eu_err[j * CCP_MAX_N + k]); }
         if (tid >= 32 && tid < 32 + KMAX + 2) { const int k = tid - 32; if (k >= 1) { S.invlo[k] = __ddiv_rd(1.0, (double)k); S.invhi[k] = __ddiv_ru(1.0, (double)k); } else { S.invlo[0] = S.invhi[0] = 0.0; } }
     }
@@ -677,6 +907,22 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
     __syncthreads();                                // the descriptor (un.desc) is dead from here on
     if (tid == 0) { S.mj = majorant<N>(S.bpar, S.cpar, p, h); S.flag = 0; }
     if (tid == 32) majorant2<N>(S.bpar, S.cpar, h, S.g15);
+    if (tid < N) {                                  // oracle/c2.hpp:make_par
+        const int i = tid;
+        mt z; z.m = 0.0; z.t = 0.0;
+        const ival b = S.bpar[i];
+        S.pm.B[i] = iv2mt(b); S.pm.B3[i] = iv2mt(imulk(b, 3)); S.pm.B6[i] = iv2mt(imulk(b, 6)); S.pm.halfB[i] = ihalf(b);
+        S.pm.Cm[i] = i > 0 ? iv2mt(S.cpar[i > 0 ? i - 1 : 0]) : z;                 S.pm.Cp[i] = i < N - 1 ? iv2mt(S.cpar[i < N - 1 ? i : 0]) : z;
+        S.pm.C2m[i] = i > 0 ? iv2mt(imulk(S.cpar[i > 0 ? i - 1 : 0], 2)) : z;      S.pm.C2p[i] = i < N - 1 ? iv2mt(imulk(S.cpar[i < N - 1 ? i : 0], 2)) : z;
+        S.pm.C2[i] = S.pm.C2p[i];
+        for (int l = 0; l < N; l++) for (int sl = 0; sl < 3; sl++) {
+            mt v = z;
+            if (i == l) v = sl == 0 ? S.pm.B6[i] : (sl == 1 ? S.pm.C2m[i] : S.pm.C2p[i]);
+            else if (l == i + 1) v = sl < 2 ? S.pm.C2p[i] : z;                    // 2 c_i
+            else if (l == i - 1) v = sl < 2 ? S.pm.C2m[i] : z;                    // 2 c_{i-1}
+            S.pm.PN[i][l][sl] = v;
+        }
+    }
     if (tid < 3 * N - 1) {
         SPar q; q.pl = 0; q.ph = 0; q.neg = 0; q.straddle = 0;                       // index 2N-1: zero parameter
         if (tid < N) q = make_spar(S.bpar[tid]);
@@ -792,7 +1038,6 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
             mt z1; z1.m = -u1.m; z1.t = u1.t;
             T[L::Z(i)][1] = z1;
         }
-        if (tid >= 32 && tid < 32 + N) hull_row<N>(S, tid - 32);              // low-order hull quantities for the second variation
         for (int t = tid; t < N * D; t += NT) {
             const int i = t / D, cc = t % D;
             T[L::PU(i, cc)][0] = iv2mt(pt(cc == i ? 1.0 : 0.0));
@@ -1006,111 +1251,7 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
         __syncthreads();                            // Fk complete; all Taylor tables and un.scratch are dead from here (PT overlays them)
         PROF(3);
         TRC(5);
-        // ---- second variation over the hull (oracle/c2.hpp): directions c_j = C e_j (j < D) and the box r (j = D) ----
-        {
-            const HullQ<N>& H = S.hq;
-            // X1: w_3;  d_2, d_3 of every direction
-            if (tid < N) S.hq.w[3][tid] = idivk_tab(tri_row<N>(H.Md0, H.Mo0, H.w[1], tid), S.invlo, S.invhi, 6);
-            for (int t = tid; t < (D + 1) * N; t += NT) {
-                const int j = t / N, m = t % N;
-                ival d0[N], d1[N];
-#pragma unroll
-                for (int i = 0; i < N; i++) { d0[i] = j < D ? pt(S.C[cur][i][j]) : S.r[cur][i]; d1[i] = j < D ? pt(S.C[cur][N + i][j]) : S.r[cur][N + i]; }
-                PT.u.x.DD[j][0][m] = d0[m]; PT.u.x.DD[j][1][m] = d1[m];
-                PT.u.x.DD[j][2][m] = ihalf(tri_row<N>(H.Md0, H.Mo0, d0, m));
-                PT.u.x.DD[j][3][m] = idivk_tab(iadd(tri_row<N>(H.Md1, H.Mo1, d0, m), tri_row<N>(H.Md0, H.Mo0, d1, m)), S.invlo, S.invhi, 6);
-            }
-            __syncthreads();
-            TRC(10);
-            // X2: Taylor coefficients N_0..N_3 of DM(u)[Psi^u c_j] (tridiagonal: N diagonal + N-1 off-diagonal entries per order)
-            for (int t = tid; t < (D + 1) * (2 * N - 1); t += NT) {
-                const int j = t / (2 * N - 1), e = t % (2 * N - 1);
-                const ival (*dd)[N] = PT.u.x.DD[j];
-#pragma unroll 1
-                for (int k = 0; k < 4; k++) {
-                    ival a;
-                    if (e < N) {
-                        const int i = e;
-                        a = imulk(imul_nl(S.bpar[i], wd_coef<N>(H, dd, i, i, k)), 6);
-                        if (i > 0)     a = iadd(a, imulk(imul_nl(S.cpar[i - 1], wd_coef<N>(H, dd, i - 1, i - 1, k)), 2));
-                        if (i < N - 1) a = iadd(a, imulk(imul_nl(S.cpar[i], wd_coef<N>(H, dd, i + 1, i + 1, k)), 2));
-                    } else {
-                        const int i = e - N;
-                        a = imulk(imul_nl(S.cpar[i], iadd(wd_coef<N>(H, dd, i + 1, i, k), wd_coef<N>(H, dd, i, i + 1, k))), 2);
-                    }
-                    PT.u.x.NN[j][k][e] = a;
-                }
-            }
-            __syncthreads();
-            TRC(11);
-            // X3: the four n x n blocks of Xi_j(hs) = sum_{k<=4} Xi_k hs^k + remainder, one (j, i, k) entry of each block per thread
-            const double hs2 = __dmul_ru(hs, hs), hs5 = __dmul_ru(__dmul_ru(hs2, hs2), hs);
-            for (int t = tid; t < (D + 1) * N * N; t += NT) {
-                const int j = t / (N * N), i = (t / N) % N, k = t % N;
-                double c1n = 0;
-                for (int q = 0; q < D; q++) c1n = __dadd_ru(c1n, j < D ? fabs(S.C[cur][q][j]) : imag(S.r[cur][q]));
-                const double rem = __dmul_ru(__dmul_ru(mj.g5, hs5), c1n);
-                const ival (*NN)[2 * N - 1] = PT.u.x.NN[j];
-                const int dk = i > k ? i - k : k - i;
-                ival cf[4][4];
-#pragma unroll
-                for (int q = 0; q < 4; q++)
-#pragma unroll
-                    for (int e = 0; e < 4; e++) cf[q][e] = pt(0.0);
-                if (dk <= 2) {
-                    const ival* M0 = H.Md0; const ival* M1 = H.Md1;     // diag followed by off-diagonal in HullQ: Md0[N], Mo0[N]
-                    const ival N0 = tri_e<N>(NN[0], i, k), N1 = tri_e<N>(NN[1], i, k), N2 = tri_e<N>(NN[2], i, k), N3 = tri_e<N>(NN[3], i, k);
-                    const ival P00 = iadd(tri_mul<N>(M0, H.Mo0, NN[0], NN[0] + N, i, k), tri_mul<N>(NN[0], NN[0] + N, M0, H.Mo0, i, k));
-                    const ival P01 = iadd(tri_mul<N>(M0, H.Mo0, NN[1], NN[1] + N, i, k), tri_mul<N>(NN[0], NN[0] + N, M1, H.Mo1, i, k));
-                    const ival P10 = iadd(tri_mul<N>(M1, H.Mo1, NN[0], NN[0] + N, i, k), tri_mul<N>(NN[1], NN[1] + N, M0, H.Mo0, i, k));
-                    const ival X3 = idivk_tab(iadd(N2, ihalf(P00)), S.invlo, S.invhi, 3);
-                    cf[0][1] = ihalf(N0); cf[0][2] = idivk_tab(N1, S.invlo, S.invhi, 6); cf[0][3] = idivk_tab(X3, S.invlo, S.invhi, 4);
-                    cf[1][2] = idivk_tab(N0, S.invlo, S.invhi, 6); cf[1][3] = idivk_tab(N1, S.invlo, S.invhi, 12);
-                    cf[2][0] = N0; cf[2][1] = ihalf(N1); cf[2][2] = X3;
-                    cf[2][3] = idivk_tab(iadd(iadd(N3, idivk_tab(P01, S.invlo, S.invhi, 6)), ihalf(P10)), S.invlo, S.invhi, 4);
-                    cf[3][1] = ihalf(N0); cf[3][2] = idivk_tab(N1, S.invlo, S.invhi, 3);
-                    cf[3][3] = idivk_tab(iadd(N2, idivk_tab(P00, S.invlo, S.invhi, 6)), S.invlo, S.invhi, 4);
-                }
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    ival acc = cf[q][3]; double am = imag(cf[q][3]);
-#pragma unroll
-                    for (int e = 2; e >= 0; e--) { acc = horner_pt(acc, hs, cf[q][e]); am = __fma_ru(am, hs, imag(cf[q][e])); }
-                    acc = horner_pt(acc, hs, pt(0.0)); am = __dmul_ru(am, hs);
-                    const int row = (q >> 1) * N + i, col = (q & 1) * N + k;
-                    PT.Xi[j][row][col] = iadd(acc, sym(rem));
-                    PT.u.x.AM[j][row][col] = __dadd_ru(am, rem);
-                }
-            }
-            __syncthreads();
-            TRC(12);
-            // X4: dJ = sum_j Xi_j r0_j + Xi_r encloses DPhi(phi) - DPhi(x) on the set; J = Jc + [0,1] dJ for the mean-value form of the
-            //     phi-set update; magX >= sup over [0,hs] of |Psi(tau;phi) - Psi(tau;x)|
-            for (int t = tid; t < D * D; t += NT) {
-                const int row = t / D, col = t % D;
-                ival dj = pt(0.0); double mg = 0.0;
-                for (int j = 0; j <= D; j++) {
-                    const ival wj = j < D ? S.r0[j] : pt(1.0);
-                    dj = iadd(dj, imul_nl(PT.Xi[j][row][col], wj));
-                    mg = __fma_ru(PT.u.x.AM[j][row][col], imag(wj), mg);
-                }
-                PT.dJ[row][col] = dj;
-                S.J[row][col] = iadd(S.Jc[row][col], ihull(dj, pt(0.0)));
-                if (row < N) PT.magXu[row][col] = mg; else PT.magXv[row - N][col] = mg;
-            }
-            __syncthreads();
-            TRC(13);
-            // truncation box of the centre tables + box for (Psi(tau;phi) - Psi(tau;x)) W on [0,hs]; same for the derivative
-            if (tid < N * N) {
-                const int a = tid / N, bb = tid % N;
-                double sm = 0; for (int cc = 0; cc < D; cc++) sm = __dadd_ru(sm, imag(S.Ws[cc][bb]));
-                double s0 = __dmul_ru(mj.rho_psi, sm), s1 = __dmul_ru(mj.rho_psi_d, sm);
-                for (int cc = 0; cc < D; cc++) { const double wm = imag(S.Ws[cc][bb]); s0 = __fma_ru(PT.magXu[a][cc], wm, s0); s1 = __fma_ru(PT.magXv[a][cc], wm, s1); }
-                S.Fk[0][a][bb] = iadd(S.Fk[0][a][bb], sym(s0));
-                S.boxFd[a][bb] = s1;
-            }
-            __syncthreads();
-        }
+        second_variation<N>(S, PT, cur, hs, mj.g5);          // Xi_j, dJ, J = Jc + [0,1] dJ, boxes added to F_0 / boxFd
         PROF(11);
         TRC(9);
         // ---- grid loop (utils.cpp:219-252).  A lane owns ONE frame entry c and every (32/N^2)-th grid point: each coefficient
@@ -1218,86 +1359,7 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
         }
         PROF(5);
         TRC(7);
-        // ---- set update (oracle/c2.hpp, same products and the same order of additions) ----
-        if (tid < D) S.x[nxt][tid] = mid_ru(S.y[tid]);
-        {
-            // front:  C+ = mid(J C),  r+ = J r + (y - x+) + (J C - C+) r0      with J = Jc + [0,1] dJ
-            for (int t = tid; t < 2 * D * D; t += NT) {
-                const int e = t % (D * D), i = e / D, j = e % D;
-                if (t < D * D) {
-                    ival a = pt(0.0);
-#pragma unroll
-                    for (int k = 0; k < D; k++) a = iadd(a, imul_nl(S.J[i][k], pt(S.C[cur][k][j])));
-                    const double cm = mid_ru(a);
-                    S.C[nxt][i][j] = cm;
-                    S.un.JC[i][j] = imul_nl(isub(a, pt(cm)), S.r0[j]);                 // (JC - C+)_ij * r0_j
-                } else {
-                    S.un.JC[D + i][j] = imul_nl(S.J[i][j], S.r[cur][j]);
-                }
-            }
-            // frame:  T+ = (Jc + sum_j Xi_j r0_j + Xi_r)(Tc + sum_l Theta_l r0_l + R):  Tc+ = mid(Jc Tc),
-            //         Theta_j+ = mid(Jc Theta_j + Xi_j Tc), R+ = everything else;  Ps+ = J Ps.  New values stay in registers until
-            //         every thread has read the old state.
-            constexpr int NTH = D * D * N, NR = D * N, NIT = NTH + 2 * NR, ROUNDS = (NIT + NT - 1) / NT;
-            double pv[ROUNDS]; ival iv[ROUNDS];
-#pragma unroll
-            for (int rd = 0; rd < ROUNDS; rd++) {
-                const int t = tid + rd * NT;
-                pv[rd] = 0.0; iv[rd] = pt(0.0);
-                if (t < NTH) {
-                    const int j = t / (D * N), i = (t / N) % D, k = t % N;
-                    ival a = pt(0.0);
-                    for (int l = 0; l < D; l++) a = iadd(a, imul_nl(S.Jc[i][l], pt(S.Th[j][l][k])));
-                    for (int l = 0; l < D; l++) a = iadd(a, imul_nl(PT.Xi[j][i][l], pt(S.Tc[l][k])));
-                    const double th = mid_ru(a);
-                    pv[rd] = th;
-                    PT.E[j][i][k] = imul_nl(isub(a, pt(th)), S.r0[j]);
-                } else if (t < NTH + NR) {
-                    const int e = t - NTH, i = e / N, k = e % N;
-                    ival a = pt(0.0);
-                    for (int l = 0; l < D; l++) a = iadd(a, imul_nl(S.Jc[i][l], pt(S.Tc[l][k])));
-                    const double tc = mid_ru(a);
-                    pv[rd] = tc;
-                    ival rr = isub(a, pt(tc));
-                    for (int l = 0; l < D; l++) rr = iadd(rr, imul_nl(S.Jc[i][l], S.R[l][k]));
-                    for (int l = 0; l < D; l++) rr = iadd(rr, imul_nl(PT.dJ[i][l], iadd(S.S0[l][k], S.R[l][k])));
-                    for (int l = 0; l < D; l++) rr = iadd(rr, imul_nl(PT.Xi[D][i][l], pt(S.Tc[l][k])));
-                    iv[rd] = rr;
-                } else if (t < NIT) {
-                    const int e = t - NTH - NR, i = e / N, k = e % N;
-                    ival a = pt(0.0);
-                    for (int l = 0; l < D; l++) a = iadd(a, imul_nl(S.J[i][l], S.Ps[l][k]));
-                    iv[rd] = a;
-                }
-            }
-            __syncthreads();
-            if (S.flag & 1) status = CCP_ST_NONFINITE;
-#pragma unroll
-            for (int rd = 0; rd < ROUNDS; rd++) {
-                const int t = tid + rd * NT;
-                if (t < NTH) {
-                    const int j = t / (D * N), i = (t / N) % D, k = t % N;
-                    S.Th[j][i][k] = pv[rd];
-                } else if (t < NTH + NR) {
-                    const int e = t - NTH, i = e / N, k = e % N;
-                    ival rr = iv[rd];
-                    for (int j = 0; j < D; j++) rr = iadd(rr, PT.E[j][i][k]);
-                    S.R[i][k] = rr; S.Tc[i][k] = pv[rd];
-                } else if (t < NIT) {
-                    const int e = t - NTH - NR, i = e / N, k = e % N;
-                    S.Ps[i][k] = iv[rd];
-                }
-            }
-            if (tid < D) {
-                const int i = tid;
-                ival z = isub(S.y[i], pt(S.x[nxt][i]));
-                for (int j = 0; j < D; j++) z = iadd(z, S.un.JC[i][j]);
-                ival a = pt(0.0);
-                for (int j = 0; j < D; j++) a = iadd(a, S.un.JC[D + i][j]);
-                S.r[nxt][i] = iadd(a, z);
-            }
-            __syncthreads();
-        }
+        if (set_update<N>(S, PT, cur, nxt)) status = CCP_ST_NONFINITE;
         PROF(6);
         TRC(8);
         tprev = mk(__dadd_rd(tprev.lo, hs), __dadd_ru(tprev.hi, hs));

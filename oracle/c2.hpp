@@ -72,43 +72,85 @@ static inline Maj2 c2_majorant(int n, const ival* b, const ival* c, double h) {
 
 
 static inline ival half(const ival& a) { return ival(0.5 * a.lo, 0.5 * a.hi); }
-// entry (i,k) of the symmetric tridiagonal matrix (diag dg, off-diagonal od); zero elsewhere
-static inline ival tri(const ival* dg, const ival* od, int i, int k) {
-    if (i == k) return dg[i];
-    if (k == i + 1) return od[i];
-    if (k == i - 1) return od[k];
-    return ival(0.0);
-}
-// row i of (tridiagonal) * vector
-static inline ival tri_row(const ival* dg, const ival* od, const ival* v, int n, int i) {
-    ival a = dg[i] * v[i];
-    if (i > 0)     a = a + od[i - 1] * v[i - 1];
-    if (i < n - 1) a = a + od[i] * v[i + 1];
-    return a;
-}
-// entry (i,k) of the product of two tridiagonal matrices: l runs over max(i,k)-1 .. min(i,k)+1 ascending
-static inline ival tri_mul(const ival* ad, const ival* ao, const ival* bd, const ival* bo, int n, int i, int k) {
-    ival a(0.0);
-    for (int l = 0; l < n; l++) {
-        if (l < i - 1 || l > i + 1 || l < k - 1 || l > k + 1) continue;
-        a = a + tri(ad, ao, i, l) * tri(bd, bo, l, k);
-    }
-    return a;
-}
 // acc*h + c for a point h > 0
 static inline ival horner_hp(const ival& acc, double h, const ival& c) { return ival(fma_rd(acc.lo, h, c.lo), fma_ru(acc.hi, h, c.hi)); }
+// a += x * p for a point p: one directed FMA per bound (tighter than a rounded product plus a rounded sum)
+static inline void ipfma(ival& a, const ival& x, double p) {
+    const double l = p >= 0 ? x.lo : x.hi, h = p >= 0 ? x.hi : x.lo;
+    a.lo = fma_rd(l, p, a.lo); a.hi = fma_ru(h, p, a.hi);
+}
+static inline mt ptm(double v) { mt o; o.m = v; o.t = std::fabs(v); return o; }      // iv2mt of a point
+static const mt MT0 = {0.0, 0.0};
+
+// Parameter tables of a front in (mid,t) form; missing chain neighbours are zero parameters so that every row has the
+// same three terms (i, i-1, i+1 with clamped indices): the GPU evaluates these sums branch-free.
+struct ParM {
+    mt B[MAXN], B3[MAXN], B6[MAXN], Cm[MAXN], Cp[MAXN], C2m[MAXN], C2p[MAXN], C2[MAXN];
+    ival halfB[MAXN];
+    mt PN[MAXN][MAXN][3];          // N_k[i][l] = sum_s PN[i][l][s] * WD[a_s][b_s]   (slot indices: slot_ab)
+};
+static inline void make_par(ParM& P, int n, const ival* b, const ival* c) {
+    for (int i = 0; i < n; i++) {
+        P.B[i] = iv2mt(b[i]); P.B3[i] = iv2mt(mulk(b[i], 3)); P.B6[i] = iv2mt(mulk(b[i], 6)); P.halfB[i] = half(b[i]);
+        P.Cm[i] = i > 0 ? iv2mt(c[i - 1]) : MT0;                 P.Cp[i] = i < n - 1 ? iv2mt(c[i]) : MT0;
+        P.C2m[i] = i > 0 ? iv2mt(mulk(c[i - 1], 2)) : MT0;       P.C2p[i] = i < n - 1 ? iv2mt(mulk(c[i], 2)) : MT0;
+        P.C2[i] = i < n - 1 ? iv2mt(mulk(c[i], 2)) : MT0;
+    }
+    for (int i = 0; i < n; i++) for (int l = 0; l < n; l++) for (int s = 0; s < 3; s++) {
+        mt v = MT0;
+        if (i == l) v = s == 0 ? P.B6[i] : (s == 1 ? P.C2m[i] : P.C2p[i]);
+        else if (l == i + 1 || l == i - 1) v = s < 2 ? P.C2[i < l ? i : l] : MT0;
+        P.PN[i][l][s] = v;
+    }
+}
+// indices (a,b) of the product series w_a d_b that slot s of entry (i,l) of N refers to (clamped; unused slots carry a zero parameter)
+static inline void slot_ab(int n, int i, int l, int s, int& a, int& b) {
+    if (i == l) { a = b = s == 0 ? i : (s == 1 ? (i > 0 ? i - 1 : 0) : (i < n - 1 ? i + 1 : n - 1)); }
+    else { const int e = i < l ? i : l; const int e1 = e + 1 < n ? e + 1 : n - 1; if (s == 0) { a = e1; b = e; } else { a = e; b = e1; } }
+}
+
+// low-order Taylor data over the hull [X]: W[q] = coefficients of u - 1/2 (q <= 3), G = u(1-u), dense tridiagonal M0, M1
+struct HullM { mt W[4][MAXN], G[MAXN], Pw[MAXN], M0[MAXN][MAXN], M1[MAXN][MAXN]; };
+static inline void hull_data(HullM& H, const ParM& P, int n, const ival* X) {
+    ival w0[MAXN];
+    for (int m = 0; m < n; m++) {
+        w0[m] = X[m] - ival(0.5);
+        H.W[0][m] = iv2mt(w0[m]); H.W[1][m] = iv2mt(X[n + m]); H.G[m] = iv2mt(X[m] * (ival(1.0) - X[m]));
+        acc4 a; acc_term(a, H.W[0][m], H.W[1][m]); H.Pw[m] = iv2mt(acc_finish(a));
+    }
+    for (int i = 0; i < n; i++) for (int l = 0; l < n; l++) { H.M0[i][l] = MT0; H.M1[i][l] = MT0; }
+    for (int e = 0; e + 1 < n; e++) {
+        acc4 a; acc_term(a, H.W[0][e], H.W[0][e + 1]);
+        acc4 a2; acc_term(a2, P.C2[e], iv2mt(acc_finish(a)));
+        H.M0[e][e + 1] = H.M0[e + 1][e] = iv2mt(acc_finish(a2));
+        acc4 u; acc_term(u, H.W[0][e], H.W[1][e + 1]); acc_term(u, H.W[1][e], H.W[0][e + 1]);
+        acc4 u2; acc_term(u2, P.C2[e], iv2mt(acc_finish(u)));
+        H.M1[e][e + 1] = H.M1[e + 1][e] = iv2mt(acc_finish(u2));
+    }
+    for (int i = 0; i < n; i++) {
+        const int im = i > 0 ? i - 1 : 0, ip = i < n - 1 ? i + 1 : n - 1;
+        acc4 sa; acc_term(sa, P.B[i], H.G[i]); acc_term(sa, P.Cm[i], H.G[im]); acc_term(sa, P.Cp[i], H.G[ip]);
+        H.W[2][i] = iv2mt(half(-(w0[i] * acc_finish(sa))));                                   // u_2 = F(u)/2
+        acc4 ta; acc_term(ta, P.B3[i], H.G[i]); acc_term(ta, P.Cm[i], H.G[im]); acc_term(ta, P.Cp[i], H.G[ip]);
+        H.M0[i][i] = iv2mt(P.halfB[i] - acc_finish(ta));
+        acc4 ma; acc_term(ma, P.B6[i], H.Pw[i]); acc_term(ma, P.C2m[i], H.Pw[im]); acc_term(ma, P.C2p[i], H.Pw[ip]);
+        H.M1[i][i] = iv2mt(acc_finish(ma));
+    }
+    for (int i = 0; i < n; i++) {
+        acc4 a; for (int l = 0; l < n; l++) acc_term(a, H.M0[i][l], H.W[1][l]);
+        H.W[3][i] = iv2mt(divk(acc_finish(a), 6));                                            // u_3 = M0 u_1 / 6
+    }
+}
 
 // S0 = sum_j Theta_j r0_j ;  W = ((Tc + S0) + R) + Ps Err
 static inline void frame_of_state(int n, const double (*Tc)[MAXN], const double (*Th)[MAXD][MAXN], const ival (*R)[MAXN], const ival (*Ps)[MAXN],
-                                  const ival* r0, const ival (*Err)[MAXN], ival (*S0)[MAXN], ival (*W)[MAXN]) {
+                                  const ival* r0, const mt (*Errm)[MAXN], ival (*S0)[MAXN], ival (*W)[MAXN]) {
     const int D = 2 * n;
     for (int cc = 0; cc < D; cc++) for (int bb = 0; bb < n; bb++) {
-        ival a(0.0);
-        for (int j = 0; j < D; j++) a = a + ival(Th[j][cc][bb]) * r0[j];
+        ival a(0.0); for (int j = 0; j < D; j++) ipfma(a, r0[j], Th[j][cc][bb]);
         S0[cc][bb] = a;
-        ival w = (ival(Tc[cc][bb]) + a) + R[cc][bb];
-        for (int j = 0; j < n; j++) w = w + Ps[cc][j] * Err[j][bb];
-        W[cc][bb] = w;
+        acc4 e; for (int j = 0; j < n; j++) acc_term(e, iv2mt(Ps[cc][j]), Errm[j][bb]);
+        W[cc][bb] = ((ival(Tc[cc][bb]) + S0[cc][bb]) + R[cc][bb]) + acc_finish(e);
     }
 }
 
@@ -128,6 +170,8 @@ static inline void run_front(const ccp_front_desc& d, ccp_front_result& res, std
     Majorant mj = c1_majorant(n, b, c, p, h);
     if (!mj.ok) { res.status = CCP_ST_ENCLOSURE; return; }
     const Maj2 m2 = c2_majorant(n, b, c, h);
+    static thread_local ParM PM;
+    make_par(PM, n, b, c);
 
     double x[MAXD], C[MAXD][MAXD];
     ival r0[MAXD], r[MAXD], Err[MAXN][MAXN];
@@ -141,6 +185,10 @@ static inline void run_front(const ccp_front_desc& d, ccp_front_result& res, std
         for (int j = 0; j < D; j++) for (int k = 0; k < n; k++) Th[j][i][k] = 0.0;
     }
     for (int j = 0; j < n; j++) for (int k = 0; k < n; k++) Err[j][k] = fromc(d.Eu_err[j * CCP_MAX_N + k]);
+    mt r0m[MAXD + 1], Errm[MAXN][MAXN];                      // (mid,t) forms; r0m[D] = 1 weights the direction "box r"
+    for (int j = 0; j < D; j++) r0m[j] = iv2mt(r0[j]);
+    r0m[D] = ptm(1.0);
+    for (int j = 0; j < n; j++) for (int k = 0; k < n; k++) Errm[j][k] = iv2mt(Err[j][k]);
 
     Counter cnt;
     ival tprev(0.0);
@@ -169,87 +217,78 @@ static inline void run_front(const ccp_front_desc& d, ccp_front_result& res, std
         ival xc[MAXD]; for (int i = 0; i < D; i++) xc[i] = ival(x[i]);
         phi_tables(ct, n, p, b, c, xc, xc + n);
         psi_tables(ps, ct, n, p, b, c);
-        // ---- hull, low order (plain inf-sup arithmetic): w_k = Taylor coefficients of u - 1/2 (k <= 3), M0, M1 over [X] ----
-        ival w[4][MAXN], g0[MAXN], Md0[MAXN], Mo0[MAXN], Md1[MAXN], Mo1[MAXN];
-        for (int i = 0; i < n; i++) { w[0][i] = X[i] - ival(0.5); g0[i] = X[i] * (ival(1.0) - X[i]); w[1][i] = X[n + i]; }
-        for (int i = 0; i < n; i++) {
-            ival f = -((g0[i] * w[0][i]) * b[i]);
-            if (i > 0)     f = f - (g0[i - 1] * w[0][i]) * c[i - 1];
-            if (i < n - 1) f = f - (g0[i + 1] * w[0][i]) * c[i];
-            w[2][i] = half(f);
-            ival dd = -(b[i] * (mulk(g0[i], 3) - ival(0.5)));
-            if (i > 0)     dd = dd - c[i - 1] * g0[i - 1];
-            if (i < n - 1) dd = dd - c[i] * g0[i + 1];
-            Md0[i] = dd;
-            if (i < n - 1) Mo0[i] = mulk(w[0][i] * w[0][i + 1], 2) * c[i];
-            ival m1 = mulk(b[i] * (w[0][i] * w[1][i]), 6);
-            if (i > 0)     m1 = m1 + mulk(c[i - 1] * (w[0][i - 1] * w[1][i - 1]), 2);
-            if (i < n - 1) m1 = m1 + mulk(c[i] * (w[0][i + 1] * w[1][i + 1]), 2);
-            Md1[i] = m1;
-            if (i < n - 1) Mo1[i] = mulk(c[i] * (w[0][i] * w[1][i + 1] + w[1][i] * w[0][i + 1]), 2);
-        }
-        for (int i = 0; i < n; i++) w[3][i] = divk(tri_row(Md0, Mo0, w[1], n, i), 6);
+        // ---- low-order Taylor data over the hull [X] ----
+        static thread_local HullM H;
+        hull_data(H, PM, n, X);
         double rnorm = 0; for (int i = 0; i < D; i++) rnorm = add_ru(rnorm, mag(r[i]));
         const double hs2 = mul_ru(hs, hs), hs5 = mul_ru(mul_ru(hs2, hs2), hs);
         // ---- second variation over the hull: directions c_j (weight r0_j, tracked), j < D, and the box r (weight 1) ----
         static thread_local ival Xi[MAXD + 1][MAXD][MAXD];     // Xi[j][row][col]
-        ival dJ[MAXD][MAXD];                                    // sum_j Xi_j r0_j + Xi_D  : encloses DPhi(phi) - DPhi(x) on the set
-        double magXu[MAXN][MAXD], magXv[MAXN][MAXD];            // sup over tau in [0,hs] of |Psi(tau;phi) - Psi(tau;x)|, u rows / v rows
-        for (int i = 0; i < D; i++) for (int k = 0; k < D; k++) dJ[i][k] = ival(0.0);
-        for (int i = 0; i < n; i++) for (int k = 0; k < D; k++) { magXu[i][k] = 0.0; magXv[i][k] = 0.0; }
+        static thread_local mt XiM[MAXD + 1][MAXD][MAXD];
+        static thread_local double AM[MAXD + 1][MAXD][MAXD];
         for (int j = 0; j <= D; j++) {
-            ival dd[4][MAXN];
+            mt dd[4][MAXN];
             double c1n = 0;
-            if (j < D) { for (int i = 0; i < D; i++) c1n = add_ru(c1n, std::fabs(C[i][j])); for (int i = 0; i < n; i++) { dd[0][i] = ival(C[i][j]); dd[1][i] = ival(C[n + i][j]); } }
-            else       { c1n = rnorm; for (int i = 0; i < n; i++) { dd[0][i] = r[i]; dd[1][i] = r[n + i]; } }
-            for (int i = 0; i < n; i++) dd[2][i] = half(tri_row(Md0, Mo0, dd[0], n, i));
-            for (int i = 0; i < n; i++) dd[3][i] = divk(tri_row(Md1, Mo1, dd[0], n, i) + tri_row(Md0, Mo0, dd[1], n, i), 6);
-            auto wd = [&](int i, int m, int k) -> ival {          // (w_i d_m)_k
-                ival a = w[0][i] * dd[k][m];
-                for (int q = 1; q <= k; q++) a = a + w[q][i] * dd[k - q][m];
-                return a;
-            };
-            ival Nd[4][MAXN], No[4][MAXN];
-            for (int k = 0; k < 4; k++) for (int i = 0; i < n; i++) {
-                ival a = mulk(b[i] * wd(i, i, k), 6);
-                if (i > 0)     a = a + mulk(c[i - 1] * wd(i - 1, i - 1, k), 2);
-                if (i < n - 1) a = a + mulk(c[i] * wd(i + 1, i + 1, k), 2);
-                Nd[k][i] = a;
-                if (i < n - 1) No[k][i] = mulk(c[i] * (wd(i + 1, i, k) + wd(i, i + 1, k)), 2);
+            if (j < D) { for (int i = 0; i < D; i++) c1n = add_ru(c1n, std::fabs(C[i][j])); for (int i = 0; i < n; i++) { dd[0][i] = ptm(C[i][j]); dd[1][i] = ptm(C[n + i][j]); } }
+            else       { c1n = rnorm; for (int i = 0; i < n; i++) { dd[0][i] = iv2mt(r[i]); dd[1][i] = iv2mt(r[n + i]); } }
+            for (int m = 0; m < n; m++) {
+                acc4 a2; for (int l = 0; l < n; l++) acc_term(a2, H.M0[m][l], dd[0][l]);
+                dd[2][m] = iv2mt(half(acc_finish(a2)));
+                acc4 a3; for (int l = 0; l < n; l++) acc_term(a3, H.M1[m][l], dd[0][l]);
+                for (int l = 0; l < n; l++) acc_term(a3, H.M0[m][l], dd[1][l]);
+                dd[3][m] = iv2mt(divk(acc_finish(a3), 6));
+            }
+            mt WD[4][MAXN][MAXN];                                  // (w_i d_m)_k
+            for (int k = 0; k < 4; k++) for (int i = 0; i < n; i++) for (int m = 0; m < n; m++) {
+                acc4 a; for (int q = 0; q <= k; q++) acc_term(a, H.W[q][i], dd[k - q][m]);
+                WD[k][i][m] = iv2mt(acc_finish(a));
+            }
+            mt NN[4][MAXN][MAXN];                                  // Taylor coefficients of N = DM(u)[Psi^u c_j], dense
+            for (int k = 0; k < 4; k++) for (int i = 0; i < n; i++) for (int l = 0; l < n; l++) {
+                acc4 a;
+                for (int sl = 0; sl < 3; sl++) { int ia, ib; slot_ab(n, i, l, sl, ia, ib); acc_term(a, PM.PN[i][l][sl], WD[k][ia][ib]); }
+                NN[k][i][l] = iv2mt(acc_finish(a));
             }
             const double rem = mul_ru(mul_ru(m2.g5, hs5), c1n);
-            const ival wj = j < D ? r0[j] : ival(1.0);
-            const double wm = mag(wj);
             for (int i = 0; i < n; i++) for (int k = 0; k < n; k++) {
-                const int dk = i > k ? i - k : k - i;
+                acc4 p00, p01, p10;
+                for (int l = 0; l < n; l++) acc_term(p00, H.M0[i][l], NN[0][l][k]);
+                for (int l = 0; l < n; l++) acc_term(p00, NN[0][i][l], H.M0[l][k]);
+                for (int l = 0; l < n; l++) acc_term(p01, H.M0[i][l], NN[1][l][k]);
+                for (int l = 0; l < n; l++) acc_term(p01, NN[0][i][l], H.M1[l][k]);
+                for (int l = 0; l < n; l++) acc_term(p10, H.M1[i][l], NN[0][l][k]);
+                for (int l = 0; l < n; l++) acc_term(p10, NN[1][i][l], H.M0[l][k]);
+                const ival P00 = acc_finish(p00), P01 = acc_finish(p01), P10 = acc_finish(p10);
+                const ival N0 = mt2iv(NN[0][i][k]), N1 = mt2iv(NN[1][i][k]), N2 = mt2iv(NN[2][i][k]), N3 = mt2iv(NN[3][i][k]);
                 ival cf[4][4];                                    // cf[block][order-1]: blocks 0 UU, 1 UV, 2 VU, 3 VV
-                for (int q = 0; q < 4; q++) for (int e = 0; e < 4; e++) cf[q][e] = ival(0.0);
-                if (dk <= 2) {
-                    const ival N0 = tri(Nd[0], No[0], i, k), N1 = tri(Nd[1], No[1], i, k), N2 = tri(Nd[2], No[2], i, k), N3 = tri(Nd[3], No[3], i, k);
-                    const ival P00 = tri_mul(Md0, Mo0, Nd[0], No[0], n, i, k) + tri_mul(Nd[0], No[0], Md0, Mo0, n, i, k);
-                    const ival P01 = tri_mul(Md0, Mo0, Nd[1], No[1], n, i, k) + tri_mul(Nd[0], No[0], Md1, Mo1, n, i, k);
-                    const ival P10 = tri_mul(Md1, Mo1, Nd[0], No[0], n, i, k) + tri_mul(Nd[1], No[1], Md0, Mo0, n, i, k);
-                    const ival X3 = divk(N2 + half(P00), 3);      // Xi^v_3, u columns
-                    cf[0][1] = half(N0); cf[0][2] = divk(N1, 6); cf[0][3] = divk(X3, 4);
-                    cf[1][2] = divk(N0, 6); cf[1][3] = divk(N1, 12);
-                    cf[2][0] = N0; cf[2][1] = half(N1); cf[2][2] = X3; cf[2][3] = divk(N3 + divk(P01, 6) + half(P10), 4);
-                    cf[3][1] = half(N0); cf[3][2] = divk(N1, 3); cf[3][3] = divk(N2 + divk(P00, 6), 4);
-                }
+                const ival X3 = divk(N2 + half(P00), 3);          // Xi^v_3, u columns
+                cf[0][0] = ival(0.0); cf[0][1] = half(N0); cf[0][2] = divk(N1, 6); cf[0][3] = divk(X3, 4);
+                cf[1][0] = ival(0.0); cf[1][1] = ival(0.0); cf[1][2] = divk(N0, 6); cf[1][3] = divk(N1, 12);
+                cf[2][0] = N0; cf[2][1] = half(N1); cf[2][2] = X3; cf[2][3] = divk(N3 + divk(P01, 6) + half(P10), 4);
+                cf[3][0] = ival(0.0); cf[3][1] = half(N0); cf[3][2] = divk(N1, 3); cf[3][3] = divk(N2 + divk(P00, 6), 4);
                 for (int q = 0; q < 4; q++) {
                     ival acc = cf[q][3]; double am = mag(cf[q][3]);
                     for (int e = 2; e >= 0; e--) { acc = horner_hp(acc, hs, cf[q][e]); am = fma_ru(am, hs, mag(cf[q][e])); }
                     acc = horner_hp(acc, hs, ival(0.0)); am = mul_ru(am, hs);
                     const int row = (q >> 1) * n + i, col = (q & 1) * n + k;
                     Xi[j][row][col] = acc + sym(rem);
-                    dJ[row][col] = dJ[row][col] + Xi[j][row][col] * wj;
-                    double& mg = (q >> 1) ? magXv[i][col] : magXu[i][col];
-                    mg = fma_ru(add_ru(am, rem), wm, mg);
+                    XiM[j][row][col] = iv2mt(Xi[j][row][col]);
+                    AM[j][row][col] = add_ru(am, rem);
                 }
             }
         }
+        ival dJ[MAXD][MAXD];                                    // sum_j Xi_j r0_j + Xi_D  : encloses DPhi(phi) - DPhi(x) on the set
+        mt dJm[MAXD][MAXD];
+        double magXu[MAXN][MAXD], magXv[MAXN][MAXD];            // sup over tau in [0,hs] of |Psi(tau;phi) - Psi(tau;x)|, u rows / v rows
+        for (int row = 0; row < D; row++) for (int col = 0; col < D; col++) {
+            acc4 a; double mg = 0.0;
+            for (int j = 0; j <= D; j++) { acc_term(a, XiM[j][row][col], r0m[j]); mg = fma_ru(AM[j][row][col], j < D ? mag(r0[j]) : 1.0, mg); }
+            dJ[row][col] = acc_finish(a); dJm[row][col] = iv2mt(dJ[row][col]);
+            if (row < n) magXu[row][col] = mg; else magXv[row - n][col] = mg;
+        }
         // ---- frame at step start:  W = (Tc + sum_j Theta_j r0_j + R) + Ps Err ----
         ival S0[MAXD][MAXN], Ws[MAXD][MAXN]; mt Wm[MAXD][MAXN];
-        frame_of_state(n, Tc, Th, R, Ps, r0, Err, S0, Ws);
+        frame_of_state(n, Tc, Th, R, Ps, r0, Errm, S0, Ws);
         for (int cc = 0; cc < D; cc++) for (int bb = 0; bb < n; bb++) Wm[cc][bb] = iv2mt(Ws[cc][bb]);
         // truncation box of the centre tables and box for (Psi(tau;phi) - Psi(tau;x)) W, tau in [0,hs]; same for the derivative
         double boxF[MAXN][MAXN], boxFd[MAXN][MAXN];
@@ -353,42 +392,41 @@ static inline void run_front(const ccp_front_desc& d, ccp_front_result& res, std
             }
         }
         if (res.status != CCP_OK) break;          // non-finite determinant: stop before the set update
-        // ---- set update of the front (as c1, with J = Jc + [0,1] dJ) ----
-        double xn[MAXD], Cn[MAXD][MAXD]; ival rn[MAXD], JC[MAXD][MAXD];
+        // ---- set update of the front:  C+ = mid(J C),  r+ = J r + (y - x+) + (J C - C+) r0,  J = Jc + [0,1] dJ;  dot products in (mid,t) form ----
+        double xn[MAXD], Cn[MAXD][MAXD]; ival rn[MAXD]; mt JCr[MAXD][MAXD], Jm[MAXD][MAXD], Jcm[MAXD][MAXD];
+        for (int i = 0; i < D; i++) for (int k = 0; k < D; k++) { Jm[i][k] = iv2mt(J[i][k]); Jcm[i][k] = iv2mt(Jc[i][k]); }
         for (int i = 0; i < D; i++) xn[i] = mid_ru(y[i]);
         for (int i = 0; i < D; i++) for (int j = 0; j < D; j++) {
-            ival a(0.0); for (int k = 0; k < D; k++) a = a + J[i][k] * ival(C[k][j]);
-            JC[i][j] = a; Cn[i][j] = mid_ru(a);
+            ival jc(0.0); for (int k = 0; k < D; k++) ipfma(jc, J[i][k], C[k][j]);
+            Cn[i][j] = mid_ru(jc); JCr[i][j] = iv2mt(jc - ival(Cn[i][j]));
         }
         for (int i = 0; i < D; i++) {
-            ival z = y[i] - ival(xn[i]);
-            for (int j = 0; j < D; j++) z = z + (JC[i][j] - ival(Cn[i][j])) * r0[j];
-            ival a(0.0); for (int j = 0; j < D; j++) a = a + J[i][j] * r[j];
-            rn[i] = a + z;
+            acc4 a; for (int j = 0; j < D; j++) acc_term(a, JCr[i][j], r0m[j]);
+            for (int j = 0; j < D; j++) acc_term(a, Jm[i][j], iv2mt(r[j]));
+            rn[i] = (y[i] - ival(xn[i])) + acc_finish(a);
         }
         // ---- frame update:  T+ = (Jc + sum_j Xi_j r0_j + Xi_r)(Tc + sum_l Theta_l r0_l + R) ----
-        double Tcn[MAXD][MAXN]; ival Rn[MAXD][MAXN], Psn[MAXD][MAXN], Tdev[MAXD][MAXN];
+        double Tcn[MAXD][MAXN]; ival Rn[MAXD][MAXN], Psn[MAXD][MAXN];
         static thread_local double Thn[MAXD][MAXD][MAXN];
-        for (int i = 0; i < D; i++) for (int k = 0; k < n; k++) Tdev[i][k] = S0[i][k] + R[i][k];
         for (int i = 0; i < D; i++) for (int k = 0; k < n; k++) {
-            ival a(0.0); for (int l = 0; l < D; l++) a = a + Jc[i][l] * ival(Tc[l][k]);
-            Tcn[i][k] = mid_ru(a);
-            ival rr = a - ival(Tcn[i][k]);
-            for (int l = 0; l < D; l++) rr = rr + Jc[i][l] * R[l][k];               // Jc R
-            for (int l = 0; l < D; l++) rr = rr + dJ[i][l] * Tdev[l][k];            // second order
-            for (int l = 0; l < D; l++) rr = rr + Xi[D][i][l] * ival(Tc[l][k]);     // Xi_r Tc
-            Rn[i][k] = rr;
+            ival jt(0.0); for (int l = 0; l < D; l++) ipfma(jt, Jc[i][l], Tc[l][k]);
+            Tcn[i][k] = mid_ru(jt);
+            acc4 e;
+            for (int l = 0; l < D; l++) acc_term(e, Jcm[i][l], iv2mt(R[l][k]));                    // Jc R
+            for (int l = 0; l < D; l++) acc_term(e, dJm[i][l], iv2mt(S0[l][k] + R[l][k]));         // second order
+            ival xr(0.0); for (int l = 0; l < D; l++) ipfma(xr, Xi[D][i][l], Tc[l][k]);            // Xi_r Tc
+            Rn[i][k] = ((jt - ival(Tcn[i][k])) + acc_finish(e)) + xr;
         }
         for (int j = 0; j < D; j++) for (int i = 0; i < D; i++) for (int k = 0; k < n; k++) {
-            ival a(0.0);
-            for (int l = 0; l < D; l++) a = a + Jc[i][l] * ival(Th[j][l][k]);
-            for (int l = 0; l < D; l++) a = a + Xi[j][i][l] * ival(Tc[l][k]);
-            Thn[j][i][k] = mid_ru(a);
-            Rn[i][k] = Rn[i][k] + (a - ival(Thn[j][i][k])) * r0[j];
+            ival t(0.0);
+            for (int l = 0; l < D; l++) ipfma(t, Jc[i][l], Th[j][l][k]);
+            for (int l = 0; l < D; l++) ipfma(t, Xi[j][i][l], Tc[l][k]);
+            Thn[j][i][k] = mid_ru(t);
+            Rn[i][k] = Rn[i][k] + (t - ival(Thn[j][i][k])) * r0[j];
         }
         for (int i = 0; i < D; i++) for (int k = 0; k < n; k++) {
-            ival a(0.0); for (int l = 0; l < D; l++) a = a + J[i][l] * Ps[l][k];
-            Psn[i][k] = a;
+            acc4 a; for (int l = 0; l < D; l++) acc_term(a, Jm[i][l], iv2mt(Ps[l][k]));
+            Psn[i][k] = acc_finish(a);
         }
         for (int i = 0; i < D; i++) {
             x[i] = xn[i]; r[i] = rn[i];
@@ -399,7 +437,7 @@ static inline void run_front(const ccp_front_desc& d, ccp_front_result& res, std
         if (last) {   // topFrame::getLastFrame (topFrame.cpp:265-299): frame and front point at the end of the last step
             const int ld = CCP_MAX_N + 2;
             ival S1[MAXD][MAXN], Wl[MAXD][MAXN];
-            frame_of_state(n, Tc, Th, R, Ps, r0, Err, S1, Wl);
+            frame_of_state(n, Tc, Th, R, Ps, r0, Errm, S1, Wl);
             for (int rr = 0; rr < D; rr++) for (int k = 0; k < n; k++) res.last_frame[rr * ld + k] = toc(Wl[rr][k]);
             for (int i = 0; i < D; i++) {
                 ival a(x[i]);
