@@ -97,7 +97,7 @@ def cpu_reference_sample(pkg, orc, n_fronts_total, cores, steps=1, warmup=0):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--fronts-per-gpu", type=int, default=1024)

@@ -312,18 +312,24 @@ int ccp_measure_fp64_peak(int iters, double* tflops) {
 
 // FP64 work of one front under the implemented algorithm: DFMA = 2 flop, DADD/DMUL = 1.
 double ccp_front_flops(int n, int order, int grid, int steps) {
+    // algorithmic FP64 work of one front (DFMA = 2 flop, DADD/DMUL = 1), DESIGN.md section 5
     const double p = order, g = grid, N = n, D = 2.0 * n;
     const double P2 = p * (p + 1) / 2;                                      // sum_{k<p} (k+1) Cauchy terms per product
-    const double products = 2 * (5 * N - 3) + D * (3 * N - 2);              // centre + hull phi tables, Psi tables
+    const double products = (5 * N - 3) + D * (3 * N - 2);                  // centre phi tables (g, q, g*w) + centre Psi tables
     const double terms = products * P2 + (p + 1) * N * N * D;               // + frame tables
     const double dfma_cauchy = 4 * terms;
-    const double horner_fma = 2 * ((g + 1) * N * N * p + g * N * N * p + g * N * N * (p - 1) + (D + D * D) * p);
-    const double horner_mul = 2 * g * N * N * (p - 1);
-    const double linalg = 2 * D * D * D * 10 + 4 * D * D * 10;             // J*C, J*P (8 DMUL + 2 DADD per interval MAC), hull, r update
-    const double conv = 10 * (2 * (4 * N - 1) + 2 * N * D + (2 * N - 1)) * p; // iv2mt / mt2iv / divisions per stored coefficient
-    const double det3 = (N == 2 ? 17 : N == 3 ? 82 : 360), jac = (N == 2 ? 50 : N == 3 ? 252 : 1500);
-    const double dets = g * (3 * det3 + jac);
-    const double per_step = 2 * (dfma_cauchy + horner_fma) + horner_mul + linalg + conv + dets;
+    // Horner: point + range evaluation of the frame on the grid, y and Jc; derivative enclosures are formed on demand (not counted)
+    const double horner_fma = 2 * ((g + 1) * N * N * p + g * N * N * p + (D + D * D) * p);
+    // second variation over the hull (closed form to h^4): (mid,t) dot-product terms of the stages X1, X2a, X2b, X3, X4 + Horner in h
+    const double sv_terms = (D + 1) * (3 * N * N + 10 * N * N + 12 * N * N + 6 * N * N * N) + D * D * (D + 1);
+    const double sv_fma = 4 * sv_terms + (D + 1) * N * N * 48;
+    // set update: fused interval*point accumulations (2 DFMA per term) and (mid,t) dot products (4 DFMA per term); frame at step start
+    const double su_fma = 2 * (D * D * N * 2 * D + D * D * D + D * N * 2 * D + D * N * D) + 4 * (D * N * 3 * D + 2 * D * D + D * N * N);
+    const double conv = 10 * ((4 * N - 1) + 2 * N * D + (2 * N - 1)) * p      // iv2mt / mt2iv / divisions per stored table coefficient
+                      + 10 * (D + 1) * (4 * N + 12 * N * N) + 10 * 6 * D * D;  // ... and per stored second-variation / update quantity
+    const double det3 = (N == 2 ? 17 : N == 3 ? 82 : 360);
+    const double dets = (2 * g + 1) * det3;                                 // point + range determinants; Jacobi derivative on demand
+    const double per_step = 2 * (dfma_cauchy + horner_fma + sv_fma + su_fma) + conv + dets;
     return per_step * steps;
 }
 

@@ -67,7 +67,7 @@ struct SPar { double pl, ph; int neg, straddle; };
 
 // low-order Taylor data over the hull [X] of the phi-set (oracle/c2.hpp:HullM): W[q] = coefficients of u - 1/2 (q <= 3),
 // G = u(1-u), Pw = w_0 w_1, dense tridiagonal M_0, M_1 -- all in (mid,t) form
-template <int N> struct HullM { mt W[4][N], G[N], Pw[N], M0[N][N], M1[N][N]; };
+template <int N> struct HullM { mt W[4][N], M0[N][N], M1[N][N]; };
 // parameter tables of a front (oracle/c2.hpp:ParM); missing chain neighbours are zero parameters
 template <int N> struct ParM { mt B[N], B3[N], B6[N], Cm[N], Cp[N], C2m[N], C2p[N], C2[N]; ival halfB[N]; mt PN[N][N][3]; };
 
@@ -76,11 +76,12 @@ template <int N> struct PostTab {
     static constexpr int D = 2 * N;
     ival Xi[D + 1][D][D];                    // second variation DPhi'[c_j] over the hull, j < D; Xi[D]: direction = the box r
     ival dJ[D][D];                           // sum_j Xi_j r0_j + Xi_D
-    ival E[D][D][N];                         // set update: (enclosure of Theta_j+ minus its midpoint) * r0_j
+    mt dJm[D][D], Jm[D][D], Jcm[D][D];       // (mid,t) forms of dJ, J, Jc for the set update
     double magXu[N][D], magXv[N][D];
     ival DT[3 * (GMAX + 1)];                 // determinants of the grid loop
     union {
         ival EV[(2 * GMAX + 1) * N * N];     // frame enclosures of the grid loop
+        struct { ival pad[(2 * GMAX + 1) * N * N]; ival E[D][D][N]; double Thn[D][D][N], Tcn[D][N]; ival Rn[D][N], Psn[D][N]; } e;   // set update (behind EV, which the deciding warp may still read): (enclosure of Theta_j+ minus its midpoint) * r0_j
         struct {                             // transients of the second-variation phase (AM reuses WD, NN reuses DD)
             union { mt WD[D + 1][4][N][N]; double AM[D + 1][D][D]; };
             union { mt DD[D + 1][4][N]; mt NN[D + 1][4][N][N]; };
@@ -101,6 +102,7 @@ struct FrontSmem {
     // unstable columns of Dphi_t A_u:  Tc + sum_j Th[j] r0_j + R  (Tc, Th points);  stable columns Ps (interval)
     double Tc[D][N], Th[D][D][N];
     ival R[D][N], Ps[D][N], S0[D][N];
+    mt Rm[D][N], Tdm[D][N], Psm[D][N];       // (mid,t) forms of R, S0 + R, Ps (step start) for the set update
     ival r0[D], Err[N][N], X[D], y[D], Jc[D][D], J[D][D], Ws[D][N], bpar[N], cpar[NE];
     mt Wm[D][N];
     HullM<N> hm;
@@ -552,13 +554,35 @@ __device__ __noinline__ void second_variation(FrontSmem<N>& S, PostTab<N>& PT, i
     constexpr int D = 2 * N;
     const int tid = threadIdx.x;
     HullM<N>& H = S.hm;
-    // H-A: W_0, W_1, G = u(1-u), Pw = w_0 w_1;  off-diagonals of M_0, M_1
+    // H: W_0, W_1, u_2 = F(u)/2 and the diagonals of M_0, M_1 (lane i < N; G = u(1-u) and Pw = w_0 w_1 of the chain neighbours are
+    //    recomputed, same operations => same bits);  off-diagonals of M_0, M_1 (lanes 32..32+N-2)
     if (tid < N) {
-        const int m = tid;
-        const ival u = S.X[m];
-        const mt w0 = iv2mt(isub(u, pt(0.5))), w1 = iv2mt(S.X[N + m]);
-        H.W[0][m] = w0; H.W[1][m] = w1; H.G[m] = iv2mt(imul(u, isub(pt(1.0), u)));
-        acc4 a = acc_zero(); acc_term(a, w0, w1); H.Pw[m] = iv2mt(acc_finish(a));
+        const int i = tid, im = i > 0 ? i - 1 : 0, ip = i < N - 1 ? i + 1 : N - 1;
+        mt w0i, gi, gm, gp, pi, pm_, pp;
+        {
+            const ival u = S.X[i]; const ival w0v = isub(u, pt(0.5));
+            const mt w0 = iv2mt(w0v), w1 = iv2mt(S.X[N + i]);
+            H.W[0][i] = w0; H.W[1][i] = w1; w0i = w0;
+            gi = iv2mt(imul(u, isub(pt(1.0), u)));
+            acc4 a = acc_zero(); acc_term(a, w0, w1); pi = iv2mt(acc_finish(a));
+        }
+        {
+            const ival u = S.X[im];
+            gm = iv2mt(imul(u, isub(pt(1.0), u)));
+            acc4 a = acc_zero(); acc_term(a, iv2mt(isub(u, pt(0.5))), iv2mt(S.X[N + im])); pm_ = iv2mt(acc_finish(a));
+        }
+        {
+            const ival u = S.X[ip];
+            gp = iv2mt(imul(u, isub(pt(1.0), u)));
+            acc4 a = acc_zero(); acc_term(a, iv2mt(isub(u, pt(0.5))), iv2mt(S.X[N + ip])); pp = iv2mt(acc_finish(a));
+        }
+        acc4 sa = acc_zero(); acc_term(sa, S.pm.B[i], gi); acc_term(sa, S.pm.Cm[i], gm); acc_term(sa, S.pm.Cp[i], gp);
+        H.W[2][i] = iv2mt(ihalf(ineg(imul(isub(S.X[i], pt(0.5)), acc_finish(sa)))));
+        acc4 ta = acc_zero(); acc_term(ta, S.pm.B3[i], gi); acc_term(ta, S.pm.Cm[i], gm); acc_term(ta, S.pm.Cp[i], gp);
+        H.M0[i][i] = iv2mt(isub(S.pm.halfB[i], acc_finish(ta)));
+        acc4 ma = acc_zero(); acc_term(ma, S.pm.B6[i], pi); acc_term(ma, S.pm.C2m[i], pm_); acc_term(ma, S.pm.C2p[i], pp);
+        H.M1[i][i] = iv2mt(acc_finish(ma));
+        (void)w0i;
     } else if (tid >= 32 && tid < 32 + N - 1) {
         const int e = tid - 32;
         const mt w0a = iv2mt(isub(S.X[e], pt(0.5))), w0b = iv2mt(isub(S.X[e + 1], pt(0.5))), w1a = iv2mt(S.X[N + e]), w1b = iv2mt(S.X[N + e + 1]);
@@ -570,18 +594,6 @@ __device__ __noinline__ void second_variation(FrontSmem<N>& S, PostTab<N>& PT, i
         acc4 u2 = acc_zero(); acc_term(u2, S.pm.C2[e], iv2mt(acc_finish(u)));
         const mt m1 = iv2mt(acc_finish(u2));
         H.M1[e][e + 1] = m1; H.M1[e + 1][e] = m1;
-    }
-    __syncthreads();
-    // H-B: u_2 = F(u)/2, diagonals of M_0, M_1
-    if (tid < N) {
-        const int i = tid, im = i > 0 ? i - 1 : 0, ip = i < N - 1 ? i + 1 : N - 1;
-        const mt gi = H.G[i], gm = H.G[im], gp = H.G[ip];
-        acc4 sa = acc_zero(); acc_term(sa, S.pm.B[i], gi); acc_term(sa, S.pm.Cm[i], gm); acc_term(sa, S.pm.Cp[i], gp);
-        H.W[2][i] = iv2mt(ihalf(ineg(imul(isub(S.X[i], pt(0.5)), acc_finish(sa)))));
-        acc4 ta = acc_zero(); acc_term(ta, S.pm.B3[i], gi); acc_term(ta, S.pm.Cm[i], gm); acc_term(ta, S.pm.Cp[i], gp);
-        H.M0[i][i] = iv2mt(isub(S.pm.halfB[i], acc_finish(ta)));
-        acc4 ma = acc_zero(); acc_term(ma, S.pm.B6[i], H.Pw[i]); acc_term(ma, S.pm.C2m[i], H.Pw[im]); acc_term(ma, S.pm.C2p[i], H.Pw[ip]);
-        H.M1[i][i] = iv2mt(acc_finish(ma));
     }
     __syncthreads();
     // X1: u_3 = M_0 u_1 / 6;  d_0..d_3 of every direction
@@ -616,7 +628,9 @@ __device__ __noinline__ void second_variation(FrontSmem<N>& S, PostTab<N>& PT, i
     }
     __syncthreads();
     // X2a: product series (w_i d_m)_k, k <= 3, all N x N pairs
-    for (int t = tid; t < (D + 1) * 4 * N * N; t += NT) {
+    constexpr int NWD = (D + 1) * 4 * N * N;
+#pragma unroll 1                                                // rolled: the step loop must stay inside the instruction cache
+    for (int t = tid; t < NWD; t += NT) {
         const int j = t / (4 * N * N), k = (t / (N * N)) % 4, i = (t / N) % N, m = t % N;
         acc4 a = acc_zero();
 #pragma unroll
@@ -625,16 +639,19 @@ __device__ __noinline__ void second_variation(FrontSmem<N>& S, PostTab<N>& PT, i
     }
     __syncthreads();
     // X2b: Taylor coefficients N_k of DM(u)[Psi^u c_j] (dense): three parameter * product-series slots per entry
-    for (int t = tid; t < (D + 1) * 4 * N * N; t += NT) {
+#pragma unroll 1
+    for (int t = tid; t < NWD; t += NT) {
         const int j = t / (4 * N * N), k = (t / (N * N)) % 4, i = (t / N) % N, l = t % N;
+        // slots: diagonal (i,i): 6 b_i (w_i d_i), 2 c_{i-1} (w_{i-1} d_{i-1}), 2 c_i (w_{i+1} d_{i+1});  off-diagonal e = min(i,l): 2 c_e (w_{e+1} d_e + w_e d_{e+1})
+        const int e = i < l ? i : l, e1 = e + 1 < N ? e + 1 : N - 1;
+        const int a0 = i == l ? i : e1, b0 = i == l ? i : e;
+        const int a1 = i == l ? (i > 0 ? i - 1 : 0) : e, b1 = i == l ? a1 : e1;
+        const int a2 = i == l ? (i < N - 1 ? i + 1 : N - 1) : e, b2 = i == l ? a2 : e1;
+        const mt (*WDk)[N] = PT.u.x.WD[j][k];
         acc4 a = acc_zero();
-#pragma unroll
-        for (int sl = 0; sl < 3; sl++) {
-            int ia, ib;
-            if (i == l) { ia = ib = sl == 0 ? i : (sl == 1 ? (i > 0 ? i - 1 : 0) : (i < N - 1 ? i + 1 : N - 1)); }
-            else { const int e = i < l ? i : l; const int e1 = e + 1 < N ? e + 1 : N - 1; if (sl == 0) { ia = e1; ib = e; } else { ia = e; ib = e1; } }
-            acc_term(a, S.pm.PN[i][l][sl], PT.u.x.WD[j][k][ia][ib]);
-        }
+        acc_term(a, S.pm.PN[i][l][0], WDk[a0][b0]);
+        acc_term(a, S.pm.PN[i][l][1], WDk[a1][b1]);
+        acc_term(a, S.pm.PN[i][l][2], WDk[a2][b2]);
         PT.u.x.NN[j][k][i][l] = iv2mt(acc_finish(a));          // NN overlays DD (dead since X2a)
     }
     __syncthreads();
@@ -696,8 +713,9 @@ __device__ __noinline__ void second_variation(FrontSmem<N>& S, PostTab<N>& PT, i
             mg = __fma_ru(PT.u.x.AM[j][row][col], j < D ? imag(S.r0[j]) : 1.0, mg);
         }
         const ival dj = acc_finish(a);
-        PT.dJ[row][col] = dj;
-        S.J[row][col] = iadd(S.Jc[row][col], ihull(dj, pt(0.0)));
+        PT.dJ[row][col] = dj; PT.dJm[row][col] = iv2mt(dj);
+        const ival jc = S.Jc[row][col], jf = iadd(jc, ihull(dj, pt(0.0)));
+        S.J[row][col] = jf; PT.Jm[row][col] = iv2mt(jf); PT.Jcm[row][col] = iv2mt(jc);
         if (row < N) PT.magXu[row][col] = mg; else PT.magXv[row - N][col] = mg;
     }
     __syncthreads();
@@ -727,81 +745,78 @@ __device__ __noinline__ int set_update(FrontSmem<N>& S, PostTab<N>& PT, int cur,
     constexpr int D = 2 * N;
     const int tid = threadIdx.x;
     if (tid < D) S.x[nxt][tid] = mid_ru(S.y[tid]);
-    constexpr int NJC = D * D, NTH = D * D * N, NR = D * N, NIT = NJC + NTH + 2 * NR, ROUNDS = (NIT + NT - 1) / NT;
-    double pv[ROUNDS]; ival iv[ROUNDS];
+    // item loops are rolled and every item type appears once (code size); new values are staged in the dead table space and
+    // copied back after the barrier.  Thread offsets spread the four item types over the CTA.
+    constexpr int NJC = D * D, NTH = D * D * N, NR = D * N;
+    constexpr int OFF_R = NTH % NT, OFF_PS = (OFF_R + NR) % NT, OFF_JC = (OFF_PS + NR) % NT;
+#pragma unroll 1
+    for (int t = tid; t < NTH; t += NT) {
+        const int j = t / (D * N), i = (t / N) % D, k = t % N;
+        ival a = pt(0.0);
 #pragma unroll
-    for (int rd = 0; rd < ROUNDS; rd++) {
-        const int t = tid + rd * NT;
-        pv[rd] = 0.0; iv[rd] = pt(0.0);
-        if (t < NTH) {
-            const int j = t / (D * N), i = (t / N) % D, k = t % N;
-            ival a = pt(0.0);
+        for (int l = 0; l < D; l++) ipfma(a, S.Jc[i][l], S.Th[j][l][k]);
 #pragma unroll
-            for (int l = 0; l < D; l++) ipfma(a, S.Jc[i][l], S.Th[j][l][k]);
+        for (int l = 0; l < D; l++) ipfma(a, PT.Xi[j][i][l], S.Tc[l][k]);
+        const double th = mid_ru(a);
+        PT.u.e.Thn[j][i][k] = th;
+        PT.u.e.E[j][i][k] = imul(isub(a, pt(th)), S.r0[j]);
+    }
+#pragma unroll 1
+    for (int t = (tid + NT - OFF_R) % NT; t < NR; t += NT) {
+        const int i = t / N, k = t % N;
+        ival jt = pt(0.0);
 #pragma unroll
-            for (int l = 0; l < D; l++) ipfma(a, PT.Xi[j][i][l], S.Tc[l][k]);
-            const double th = mid_ru(a);
-            pv[rd] = th;
-            PT.E[j][i][k] = imul(isub(a, pt(th)), S.r0[j]);
-        } else if (t < NTH + NJC) {
-            const int e = t - NTH, i = e / D, j = e % D;
-            ival a = pt(0.0);
+        for (int l = 0; l < D; l++) ipfma(jt, S.Jc[i][l], S.Tc[l][k]);
+        const double tc = mid_ru(jt);
+        acc4 ea = acc_zero();
 #pragma unroll
-            for (int k = 0; k < D; k++) ipfma(a, S.J[i][k], S.C[cur][k][j]);
-            const double cm = mid_ru(a);
-            S.C[nxt][i][j] = cm;
-            S.un.JCr[i][j] = iv2mt(isub(a, pt(cm)));
-        } else if (t < NTH + NJC + NR) {
-            const int e = t - NTH - NJC, i = e / N, k = e % N;
-            ival jt = pt(0.0);
+        for (int l = 0; l < D; l++) acc_term(ea, PT.Jcm[i][l], S.Rm[l][k]);
 #pragma unroll
-            for (int l = 0; l < D; l++) ipfma(jt, S.Jc[i][l], S.Tc[l][k]);
-            const double tc = mid_ru(jt);
-            pv[rd] = tc;
-            acc4 ea = acc_zero();
+        for (int l = 0; l < D; l++) acc_term(ea, PT.dJm[i][l], S.Tdm[l][k]);
+        ival xr = pt(0.0);
 #pragma unroll
-            for (int l = 0; l < D; l++) acc_term(ea, iv2mt(S.Jc[i][l]), iv2mt(S.R[l][k]));
+        for (int l = 0; l < D; l++) ipfma(xr, PT.Xi[D][i][l], S.Tc[l][k]);
+        PT.u.e.Tcn[i][k] = tc;
+        PT.u.e.Rn[i][k] = iadd(iadd(isub(jt, pt(tc)), acc_finish(ea)), xr);
+    }
+#pragma unroll 1
+    for (int t = (tid + NT - OFF_PS) % NT; t < NR; t += NT) {
+        const int i = t / N, k = t % N;
+        acc4 a = acc_zero();
 #pragma unroll
-            for (int l = 0; l < D; l++) acc_term(ea, iv2mt(PT.dJ[i][l]), iv2mt(iadd(S.S0[l][k], S.R[l][k])));
-            ival xr = pt(0.0);
+        for (int l = 0; l < D; l++) acc_term(a, PT.Jm[i][l], S.Psm[l][k]);
+        PT.u.e.Psn[i][k] = acc_finish(a);
+    }
+#pragma unroll 1
+    for (int t = (tid + NT - OFF_JC) % NT; t < NJC; t += NT) {
+        const int i = t / D, j = t % D;
+        ival a = pt(0.0);
 #pragma unroll
-            for (int l = 0; l < D; l++) ipfma(xr, PT.Xi[D][i][l], S.Tc[l][k]);
-            iv[rd] = iadd(iadd(isub(jt, pt(tc)), acc_finish(ea)), xr);
-        } else if (t < NIT) {
-            const int e = t - NTH - NJC - NR, i = e / N, k = e % N;
-            acc4 a = acc_zero();
-#pragma unroll
-            for (int l = 0; l < D; l++) acc_term(a, iv2mt(S.J[i][l]), iv2mt(S.Ps[l][k]));
-            iv[rd] = acc_finish(a);
-        }
+        for (int k = 0; k < D; k++) ipfma(a, S.J[i][k], S.C[cur][k][j]);
+        const double cm = mid_ru(a);
+        S.C[nxt][i][j] = cm;
+        S.un.JCr[i][j] = iv2mt(isub(a, pt(cm)));
     }
     __syncthreads();
     const int nonfinite = S.flag & 1;
-#pragma unroll
-    for (int rd = 0; rd < ROUNDS; rd++) {
-        const int t = tid + rd * NT;
-        if (t < NTH) {
-            const int j = t / (D * N), i = (t / N) % D, k = t % N;
-            S.Th[j][i][k] = pv[rd];
-        } else if (t >= NTH + NJC && t < NTH + NJC + NR) {
-            const int e = t - NTH - NJC, i = e / N, k = e % N;
-            ival rr = iv[rd];
-#pragma unroll
-            for (int j = 0; j < D; j++) rr = iadd(rr, PT.E[j][i][k]);
-            S.R[i][k] = rr; S.Tc[i][k] = pv[rd];
-        } else if (t >= NTH + NJC + NR && t < NIT) {
-            const int e = t - NTH - NJC - NR, i = e / N, k = e % N;
-            S.Ps[i][k] = iv[rd];
-        }
-    }
-    if (tid < D) {
-        const int i = tid;
+#pragma unroll 1
+    for (int t = tid; t < NTH; t += NT) (&S.Th[0][0][0])[t] = (&PT.u.e.Thn[0][0][0])[t];
+    if (tid >= 32 && tid < 32 + D) {
+        const int i = tid - 32;
         acc4 a = acc_zero();
 #pragma unroll
         for (int j = 0; j < D; j++) acc_term(a, S.un.JCr[i][j], S.r0m[j]);
 #pragma unroll
-        for (int j = 0; j < D; j++) acc_term(a, iv2mt(S.J[i][j]), iv2mt(S.r[cur][j]));
+        for (int j = 0; j < D; j++) acc_term(a, PT.Jm[i][j], iv2mt(S.r[cur][j]));
         S.r[nxt][i] = iadd(isub(S.y[i], pt(S.x[nxt][i])), acc_finish(a));
+    }
+#pragma unroll 1
+    for (int t = tid; t < NR; t += NT) {
+        const int i = t / N, k = t % N;
+        ival rr = PT.u.e.Rn[i][k];
+#pragma unroll
+        for (int j = 0; j < D; j++) rr = iadd(rr, PT.u.e.E[j][i][k]);
+        S.R[i][k] = rr; S.Tc[i][k] = PT.u.e.Tcn[i][k]; S.Ps[i][k] = PT.u.e.Psn[i][k];
     }
     __syncthreads();
     return nonfinite;
@@ -1216,8 +1231,11 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
                 S.Jc[row][cc] = iadd(eval_pt(row < N ? T[L::PU(i, cc)] : T[L::PV(i, cc)], p, hs), sym(mj.rho_psi));
             } else {
                 const int e = t - D - D * D, cc = e / N, bb = e % N;
-                const ival w = frame_entry<N>(S, cc, bb, &S.S0[cc][bb]);
-                S.Ws[cc][bb] = w; S.Wm[cc][bb] = iv2mt(w);
+                ival s0;
+                const ival w = frame_entry<N>(S, cc, bb, &s0);
+                S.S0[cc][bb] = s0; S.Ws[cc][bb] = w; S.Wm[cc][bb] = iv2mt(w);
+                const ival rr = S.R[cc][bb];
+                S.Rm[cc][bb] = iv2mt(rr); S.Tdm[cc][bb] = iv2mt(iadd(s0, rr)); S.Psm[cc][bb] = iv2mt(S.Ps[cc][bb]);
             }
         }
         __syncthreads();
