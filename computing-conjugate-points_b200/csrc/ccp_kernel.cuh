@@ -55,7 +55,7 @@ template <int N> struct Lay {
     // w = u - 1/2 differs from u only at order 0: w0 lives in the unused slot G(i)[KMAX-1] (g is only needed
     // to order p-1) and enters the products as a peeled end term.  z = 1 - u has its own rows (z_k = -u_k).
     static constexpr int NA = N + NE;                 // A tasks: g[i] = u*z, q[e] = w_e*w_{e+1}
-    static constexpr int NB = 3 * N - 2;              // B tasks: g_i*w_i, g_{i-1}*w_i, g_{i+1}*w_i
+    static constexpr int NB = N;                      // B tasks: H_i*w_i with H_i = -(b_i g_i + c_{i-1} g_{i-1} + c_i g_{i+1}) (rows G hold H): v' = F(u) = H w
     static constexpr int NC = D * (3 * N - 2);        // C tasks: Md_i*Pu_i^c, Mo*Pu_{i+-1}^c
     static constexpr int NTASK = NA + NB + NC;
     static constexpr int NPH = (NTASK + 31) / 32 + ((NA + NC) <= 32 && NB > 0 && NTASK <= 32 ? 1 : 0);   // >= 2 always (A before B)
@@ -322,13 +322,11 @@ __device__ inline Task decode_task(int kind, int idx) {
     if (kind == 1) {
         if (idx >= L::NB) return t;
         int c = 0;
-        for (int i = 0; i < N; i++) for (int w = 0; w < 3; w++) {
-            if ((w == 1 && i == 0) || (w == 2 && i == N - 1)) continue;
+        for (int i = 0; i < N; i++) {
             if (c == idx) {
-                const int gi = (w == 0) ? i : (w == 1 ? i - 1 : i + 1);
                 t.kind = 1;
-                t.iA = L::G(gi); t.iB = L::U(i);
-                t.a0r = L::G(gi); t.a0c = 0; t.b0r = L::G(i); t.b0c = KMAX - 1;
+                t.iA = L::G(i); t.iB = L::U(i);
+                t.a0r = L::G(i); t.a0c = 0; t.b0r = L::G(i); t.b0c = KMAX - 1;
                 t.out = idx;
             }
             c++;
@@ -977,21 +975,22 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
     int cs0 = ZSLOT, cs1 = ZSLOT, cs2 = ZSLOT, rowV = 0, rowU = 0, rowZ = 0;
     int ap0 = PZ, ap1 = PZ, ap2 = PZ, mscale = 1, gslot = -1;
     double mcst = 0;
+    // phi warp lanes: A tasks 0..NA-1 | B tasks NA..NA+N-1 (they turn their own sum into v, u, z) | MB.. : Md_i, Mo_e, H_i from the newest g, q
+    constexpr int MB = L::NA + L::NB;
+    static_assert(MB + 3 * N - 1 <= 32, "phi warp: A, B and M/H lanes side by side");
+    const int mrole = (wq == 0 && lane >= MB && lane < MB + 3 * N - 1) ? lane - MB : -1;      // < N: Md_i, < 2N-1: Mo_e, else H_i
     if (wq == 0) {
-        if (lane < N) {                                      // v, u, z
-            const int i = lane;
-            int b0 = (i == 0 ? 0 : 3 * i - 1);
-            cs0 = b0++; ap0 = i;
-            if (i > 0)     { cs1 = b0++; ap1 = N + i - 1; }
-            if (i < N - 1) { cs2 = b0;   ap2 = N + i; }
+        if (lane >= L::NA && lane < MB) {                    // B lane: v, u, z rows of component i
+            const int i = lane - L::NA;
             rowV = L::V(i) * KMAX; rowU = L::U(i) * KMAX; rowZ = L::Z(i) * KMAX;
-        } else if (lane < 2 * N) {                           // Md_i
-            const int i = lane - N;
-            cs0 = GS + i; ap0 = i; mscale = 3; mcst = 0.5; rowV = L::MD(i) * KMAX;
+        } else if (mrole >= 0 && (mrole < N || mrole >= 2 * N - 1)) {   // Md_i (3 g_i - [k = 0]/2) and H_i (g_i): -(b_i X0) - c_{i-1} g_{i-1} - c_i g_{i+1}
+            const bool isH = mrole >= 2 * N - 1;
+            const int i = isH ? mrole - (2 * N - 1) : mrole;
+            cs0 = GS + i; ap0 = i; mscale = isH ? 1 : 3; mcst = isH ? 0.0 : 0.5; rowV = (isH ? L::G(i) : L::MD(i)) * KMAX;
             if (i > 0)     { cs1 = GS + i - 1; ap1 = N + i - 1; }
             if (i < N - 1) { cs2 = GS + i + 1; ap2 = N + i; }
-        } else if (lane < 3 * N - 1) {                       // Mo_e = c_e * 2 q_e  (P0 = -c_e)
-            const int e = lane - 2 * N;
+        } else if (mrole >= N) {                             // Mo_e = c_e * 2 q_e  (P0 = -c_e)
+            const int e = mrole - N;
             cs0 = GS + N + e; ap0 = 2 * N + e; mscale = 2; rowV = L::MO(e) * KMAX;
         }
         if (lane < L::NA) gslot = GS + lane;                 // A lanes: g (task i) and q (task N+e)
@@ -1073,12 +1072,10 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
         if (wq == 0) {
             if (tA.kind() == 0) {
                 acc4 s0, s1; run_block(Tf, tA, 0, s0, s1);
-                const mt g0 = iv2mt(acc_finish(s0));
-                T[0][tA.out() * KMAX] = g0;
-                if (gslot >= 0) S.un.scratch[gslot] = mt2iv(g0);
+                S.un.scratch[gslot] = mt2iv(iv2mt(acc_finish(s0)));
             }
             __syncwarp();
-            if (lane >= N && lane < 3 * N - 1) {
+            if (mrole >= 0) {
                 ival x0 = imulk(S.un.scratch[cs0], mscale);
                 x0 = isub(x0, pt(mcst));
                 const ival x1 = S.un.scratch[cs1], x2 = S.un.scratch[cs2];
@@ -1088,50 +1085,53 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
                     dd = ineg(imul_pos3(x0, q0.pl, q0.ph, q0.neg));
                     dd = isub(dd, imul_pos3(x1, q1.pl, q1.ph, q1.neg));
                     dd = isub(dd, imul_pos3(x2, q2.pl, q2.ph, q2.neg));
-                } else if (lane < 2 * N) {
-                    const int i = lane - N;
+                } else if (mrole < N || mrole >= 2 * N - 1) {
+                    const int i = mrole < N ? mrole : mrole - (2 * N - 1);
                     dd = ineg(imul_nl(x0, S.bpar[i]));
                     if (i > 0)     dd = isub(dd, imul_nl(x1, S.cpar[i - 1]));
                     if (i < N - 1) dd = isub(dd, imul_nl(x2, S.cpar[i]));
                 } else {
-                    dd = imul_nl(x0, S.cpar[lane - 2 * N]);
+                    dd = imul_nl(x0, S.cpar[mrole - N]);
                 }
                 T[0][rowV] = iv2mt(dd);
             }
         }
         bar_pair();
-        // phi warp: scratch sums of order kc -> v[kc+1], u[kc+2], z[kc+2] (lanes < 2N);  hull g, q of order kc+1 -> M[kc+1]
+        // phi warp, M/H lanes: g, q of order kc+1 (scratch) -> Md, Mo, H of order kc+1
         auto combine_phi = [&](int kc) {
-            const bool isV = lane < N;
-            if (isV || (lane < 3 * N - 1 && kc + 1 <= p - 1)) {
+            if (mrole >= 0 && kc + 1 <= p - 1) {
                 const ival s0 = imulk(S.un.scratch[cs0], mscale), s1 = S.un.scratch[cs1], s2 = S.un.scratch[cs2];
-                const double il = isV ? S.invlo[kc + 1] : 1.0, ih = isV ? S.invhi[kc + 1] : 1.0;
                 ival f;
                 if (!anystr) {
                     const SPar q0 = S.par[ap0], q1 = S.par[ap1], q2 = S.par[ap2];
                     f = ineg(imul_pos3(s0, q0.pl, q0.ph, q0.neg));
                     f = isub(f, imul_pos3(s1, q1.pl, q1.ph, q1.neg));
                     f = isub(f, imul_pos3(s2, q2.pl, q2.ph, q2.neg));
-                } else if (lane < 2 * N) {                // a parameter interval straddles zero: general products
-                    const int i = lane % N;
+                } else if (mrole < N || mrole >= 2 * N - 1) {     // a parameter interval straddles zero: general products
+                    const int i = mrole < N ? mrole : mrole - (2 * N - 1);
                     f = ineg(imul_nl(s0, S.bpar[i]));
                     if (i > 0)     f = isub(f, imul_nl(s1, S.cpar[i - 1]));
                     if (i < N - 1) f = isub(f, imul_nl(s2, S.cpar[i]));
                 } else {
-                    f = imul_nl(s0, S.cpar[lane - 2 * N]);
+                    f = imul_nl(s0, S.cpar[mrole - N]);
                 }
-                const ival fv = mk(__dmul_rd(f.lo, f.lo >= 0 ? il : ih), __dmul_ru(f.hi, f.hi >= 0 ? ih : il));
-                const mt vn = iv2mt(fv);
-                T[0][rowV + kc + 1] = vn;                                                    // v[kc+1] = f[kc]/(kc+1);  M[kc+1]
-                if (isV && kc + 2 <= p) {                                                    // u[kc+2] = v[kc+1]/(kc+2)
-                    const double jl = S.invlo[kc + 2], jh = S.invhi[kc + 2];
-                    const ival vi = mt2iv(vn);
-                    const ival fu = mk(__dmul_rd(vi.lo, vi.lo >= 0 ? jl : jh), __dmul_ru(vi.hi, vi.hi >= 0 ? jh : jl));
-                    const mt un = iv2mt(fu);
-                    T[0][rowU + kc + 2] = un;
-                    mt zn; zn.m = -un.m; zn.t = un.t;
-                    T[0][rowZ + kc + 2] = zn;
-                }
+                T[0][rowV + kc + 1] = iv2mt(f);
+            }
+        };
+        // phi warp, B lanes: the Cauchy sum (H w)[kc] is v'[kc]:  v[kc+1] = sum/(kc+1), u[kc+2] = v[kc+1]/(kc+2), z = -u  (no scratch round trip)
+        auto store_vuz = [&](int kc, const ival& f) {
+            const double il = S.invlo[kc + 1], ih = S.invhi[kc + 1];
+            const ival fv = mk(__dmul_rd(f.lo, f.lo >= 0 ? il : ih), __dmul_ru(f.hi, f.hi >= 0 ? ih : il));
+            const mt vn = iv2mt(fv);
+            T[0][rowV + kc + 1] = vn;
+            if (kc + 2 <= p) {
+                const double jl = S.invlo[kc + 2], jh = S.invhi[kc + 2];
+                const ival vi = mt2iv(vn);
+                const ival fu = mk(__dmul_rd(vi.lo, vi.lo >= 0 ? jl : jh), __dmul_ru(vi.hi, vi.hi >= 0 ? jh : jl));
+                const mt un = iv2mt(fu);
+                T[0][rowU + kc + 2] = un;
+                mt zn; zn.m = -un.m; zn.t = un.t;
+                T[0][rowZ + kc + 2] = zn;
             }
         };
         // Psi warp: scratch sums of order kc -> Pv[kc+1];  Pu[kc+1] = Pv[kc]/(kc+1)
@@ -1162,8 +1162,8 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
                 if (act0) {
                     run_block(Tf, tA, kk, s0, s1);
                     const ival sum = acc_finish(s0);
-                    if (isA) { const mt gm = iv2mt(sum); T[0][tA.out() * KMAX + kk] = gm; if (gslot >= 0) S.un.scratch[gslot] = mt2iv(gm); }
-                    else S.un.scratch[tA.out()] = sum;
+                    if (isA) S.un.scratch[gslot] = mt2iv(iv2mt(sum));      // g, q only travel to the M/H lanes
+                    else store_vuz(kk, sum);
                 }
                 __syncwarp();
                 PROF(8);
@@ -1175,8 +1175,8 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
                     if (act1) {
                         run_ends(Tf, tA, kk + 1, s1);
                         const ival sum = acc_finish(s1);
-                        if (isA) { const mt gm = iv2mt(sum); T[0][tA.out() * KMAX + kk + 1] = gm; if (gslot >= 0) S.un.scratch[gslot] = mt2iv(gm); }
-                        else S.un.scratch[tA.out()] = sum;
+                        if (isA) S.un.scratch[gslot] = mt2iv(iv2mt(sum));
+                        else store_vuz(kk + 1, sum);
                     }
                     __syncwarp();
                     TRC(300 + k + 1);

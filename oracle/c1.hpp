@@ -118,7 +118,7 @@ static inline Majorant c1_majorant(int n, const ival* b, const ival* c, int p, d
 }
 
 struct PhiTables {               // one Taylor table set of the front ODE
-    mt u[MAXN][MAXP + 1], v[MAXN][MAXP + 1], g[MAXN][MAXP + 1], q[MAXN][MAXP + 1];
+    mt u[MAXN][MAXP + 1], v[MAXN][MAXP + 1], g[MAXN][MAXP + 1], q[MAXN][MAXP + 1], h[MAXN][MAXP + 1];
     mt w0[MAXN], z0[MAXN];       // order-0 terms of w = u - 1/2 and z = 1 - u (orders >= 1: w_k = u_k, z_k = -u_k)
 };
 static inline void acc_term_neg(acc4& a, const mt& x, const mt& y) {   // += x * (-y)
@@ -148,16 +148,16 @@ static inline void phi_tables(PhiTables& t, int n, int p, const ival* b, const i
             cauchy_order(k, [&](int j) { acc_term(a, j == 0 ? t.w0[e] : t.u[e][j], k - j == 0 ? t.w0[e + 1] : t.u[e + 1][k - j]); });
             t.q[e][k] = iv2mt(acc_finish(a));
         }
+        for (int i = 0; i < n; i++) {                 // H_i[k] = -(b_i g_i + c_{i-1} g_{i-1} + c_i g_{i+1})[k]:  v' = F(u) = H w  (one product per component)
+            ival hh = -(mt2iv(t.g[i][k]) * b[i]);
+            if (i > 0)     hh = hh - mt2iv(t.g[i - 1][k]) * c[i - 1];
+            if (i < n - 1) hh = hh - mt2iv(t.g[i + 1][k]) * c[i];
+            t.h[i][k] = iv2mt(hh);
+        }
         for (int i = 0; i < n; i++) {
-            auto gw = [&](int gi) {
-                acc4 a;
-                cauchy_order(k, [&](int j) { acc_term(a, t.g[gi][j], k - j == 0 ? t.w0[i] : t.u[i][k - j]); });
-                return acc_finish(a);
-            };
-            ival f = -(gw(i) * b[i]);
-            if (i > 0)     f = f - gw(i - 1) * c[i - 1];
-            if (i < n - 1) f = f - gw(i + 1) * c[i];
-            t.v[i][k + 1] = iv2mt(divk(f, k + 1));
+            acc4 a;
+            cauchy_order(k, [&](int j) { acc_term(a, t.h[i][j], k - j == 0 ? t.w0[i] : t.u[i][k - j]); });
+            t.v[i][k + 1] = iv2mt(divk(acc_finish(a), k + 1));
             t.u[i][k + 1] = iv2mt(divk(mt2iv(t.v[i][k]), k + 1));
         }
     }
