@@ -103,7 +103,7 @@ struct FrontSmem {
     double Tc[D][N], Th[D][D][N];
     ival R[D][N], Ps[D][N], S0[D][N];
     mt Rm[D][N], Tdm[D][N], Psm[D][N];       // (mid,t) forms of R, S0 + R, Ps (step start) for the set update
-    ival r0[D], Err[N][N], X[D], y[D], Jc[D][D], J[D][D], Ws[D][N], bpar[N], cpar[NE];
+    ival r0[D], Err[N][N], X[D], y[D], Jc[D][D], Kc[D][D], J[D][D], Ws[D][N], bpar[N], cpar[NE];   // y, Kc: increments Phi(x) - x, DPhi(x) - I
     mt Wm[D][N];
     HullM<N> hm;
     ParM<N> pm;
@@ -249,6 +249,15 @@ __device__ __forceinline__ ival eval_pt(const mt* s, int p, double tau) {
 #pragma unroll 4
     for (int k = p - 1; k >= 0; k--) acc = horner_pt(acc, tau, mt2iv(s[k]));
     return acc;
+}
+// sum_{k>=1} s_k tau^k by Horner: the INCREMENT of a series over a step.  Leaving the order-0 coefficient out keeps the rounding of
+// the increment on its own, much finer, grid (oracle/c2.hpp:eval_inc): the centres x, Tc advance by x+ = x + mid(inc) and the
+// residual (x - x+) + inc is thin, instead of carrying ~1 ulp(x) of noise per step that the unstable directions amplify by e^{0.7 t}.
+__device__ __forceinline__ ival eval_inc(const mt* s, int p, double tau) {
+    ival acc = mt2iv(s[p]);
+#pragma unroll 4
+    for (int k = p - 1; k >= 1; k--) acc = horner_pt(acc, tau, mt2iv(s[k]));
+    return mk(__dmul_rd(acc.lo, tau), __dmul_ru(acc.hi, tau));
 }
 __device__ __forceinline__ ival eval_rg(const mt* s, int p, double tl, double th) {
     ival acc = mt2iv(s[p]);
@@ -742,7 +751,7 @@ template <int N>
 __device__ __noinline__ int set_update(FrontSmem<N>& S, PostTab<N>& PT, int cur, int nxt) {
     constexpr int D = 2 * N;
     const int tid = threadIdx.x;
-    if (tid < D) S.x[nxt][tid] = mid_ru(S.y[tid]);
+    if (tid < D) S.x[nxt][tid] = __dadd_ru(S.x[cur][tid], mid_ru(S.y[tid]));          // x+ = x + mid(increment)
     // item loops are rolled and every item type appears once (code size); new values are staged in the dead table space and
     // copied back after the barrier.  Thread offsets spread the four item types over the CTA.
     constexpr int NJC = D * D, NTH = D * D * N, NR = D * N;
@@ -764,8 +773,9 @@ __device__ __noinline__ int set_update(FrontSmem<N>& S, PostTab<N>& PT, int cur,
         const int i = t / N, k = t % N;
         ival jt = pt(0.0);
 #pragma unroll
-        for (int l = 0; l < D; l++) ipfma(jt, S.Jc[i][l], S.Tc[l][k]);
-        const double tc = mid_ru(jt);
+        for (int l = 0; l < D; l++) ipfma(jt, S.Kc[i][l], S.Tc[l][k]);                 // increment (DPhi(x) - I) Tc
+        const double tc0 = S.Tc[i][k], tc = __dadd_ru(tc0, mid_ru(jt));
+        jt = iadd(isub(pt(tc0), pt(tc)), jt);                                            // Jc Tc - Tc+  (thin)
         acc4 ea = acc_zero();
 #pragma unroll
         for (int l = 0; l < D; l++) acc_term(ea, PT.Jcm[i][l], S.Rm[l][k]);
@@ -775,7 +785,7 @@ __device__ __noinline__ int set_update(FrontSmem<N>& S, PostTab<N>& PT, int cur,
 #pragma unroll
         for (int l = 0; l < D; l++) ipfma(xr, PT.Xi[D][i][l], S.Tc[l][k]);
         PT.u.e.Tcn[i][k] = tc;
-        PT.u.e.Rn[i][k] = iadd(iadd(isub(jt, pt(tc)), acc_finish(ea)), xr);
+        PT.u.e.Rn[i][k] = iadd(iadd(jt, acc_finish(ea)), xr);
     }
 #pragma unroll 1
     for (int t = (tid + NT - OFF_PS) % NT; t < NR; t += NT) {
@@ -806,7 +816,7 @@ __device__ __noinline__ int set_update(FrontSmem<N>& S, PostTab<N>& PT, int cur,
         for (int j = 0; j < D; j++) acc_term(a, S.un.JCr[i][j], S.r0m[j]);
 #pragma unroll
         for (int j = 0; j < D; j++) acc_term(a, PT.Jm[i][j], iv2mt(S.r[cur][j]));
-        S.r[nxt][i] = iadd(isub(S.y[i], pt(S.x[nxt][i])), acc_finish(a));
+        S.r[nxt][i] = iadd(iadd(isub(pt(S.x[cur][i]), pt(S.x[nxt][i])), S.y[i]), acc_finish(a));   // (x - x+) + increment + ...
     }
 #pragma unroll 1
     for (int t = tid; t < NR; t += NT) {
@@ -1225,10 +1235,11 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
         for (int t = tid; t < D + D * D + D * N; t += NT) {
             if (t < D) {
                 const int i = t % N;
-                S.y[t] = iadd(eval_pt(t < N ? T[L::U(i)] : T[L::V(i)], p, hs), sym(mj.rho_phi));
+                S.y[t] = iadd(eval_inc(t < N ? T[L::U(i)] : T[L::V(i)], p, hs), sym(mj.rho_phi));         // increment Phi(x) - x
             } else if (t < D + D * D) {
                 const int e = t - D, row = e / D, cc = e % D, i = row % N;
-                S.Jc[row][cc] = iadd(eval_pt(row < N ? T[L::PU(i, cc)] : T[L::PV(i, cc)], p, hs), sym(mj.rho_psi));
+                const ival kc = iadd(eval_inc(row < N ? T[L::PU(i, cc)] : T[L::PV(i, cc)], p, hs), sym(mj.rho_psi));  // DPhi(x) - I
+                S.Kc[row][cc] = kc; S.Jc[row][cc] = iadd(pt(row == cc ? 1.0 : 0.0), kc);
             } else {
                 const int e = t - D - D * D, cc = e / N, bb = e % N;
                 ival s0;

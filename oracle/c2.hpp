@@ -79,6 +79,12 @@ static inline void ipfma(ival& a, const ival& x, double p) {
     const double l = p >= 0 ? x.lo : x.hi, h = p >= 0 ? x.hi : x.lo;
     a.lo = fma_rd(l, p, a.lo); a.hi = fma_ru(h, p, a.hi);
 }
+// sum_{k>=1} s_k tau^k by Horner (the order-0 coefficient is left out: increments keep their own, much finer, rounding grid)
+static inline ival eval_inc(const mt* s, int p, double tau) {
+    ival acc = mt2iv(s[p]);
+    for (int k = p - 1; k >= 1; k--) acc = horner_pt(acc, tau, mt2iv(s[k]));
+    return ival(mul_rd(acc.lo, tau), mul_ru(acc.hi, tau));
+}
 static inline mt ptm(double v) { mt o; o.m = v; o.t = std::fabs(v); return o; }      // iv2mt of a point
 static const mt MT0 = {0.0, 0.0};
 
@@ -341,13 +347,15 @@ static inline void run_front(const ccp_front_desc& d, ccp_front_result& res, std
             if (!(finite(dL) && finite(dR) && finite(dV) && finite(dD))) res.status = CCP_ST_NONFINITE;
         }
         // ---- step: y = Phi(x), Jc = DPhi(x) ----
-        ival y[MAXD], Jc[MAXD][MAXD], J[MAXD][MAXD];
+        ival y[MAXD], Jc[MAXD][MAXD], Kc[MAXD][MAXD], J[MAXD][MAXD];
         for (int i = 0; i < n; i++) {
-            y[i] = eval_pt(ct.u[i], p, hs) + sym(mj.rho_phi);
-            y[n + i] = eval_pt(ct.v[i], p, hs) + sym(mj.rho_phi);
+            y[i] = eval_inc(ct.u[i], p, hs) + sym(mj.rho_phi);                 // here: the INCREMENT Phi(x) - x
+            y[n + i] = eval_inc(ct.v[i], p, hs) + sym(mj.rho_phi);
             for (int cc = 0; cc < D; cc++) {
-                Jc[i][cc] = eval_pt(ps.Pu[i][cc], p, hs) + sym(mj.rho_psi);
-                Jc[n + i][cc] = eval_pt(ps.Pv[i][cc], p, hs) + sym(mj.rho_psi);
+                Kc[i][cc] = eval_inc(ps.Pu[i][cc], p, hs) + sym(mj.rho_psi);   // DPhi(x) - I
+                Kc[n + i][cc] = eval_inc(ps.Pv[i][cc], p, hs) + sym(mj.rho_psi);
+                Jc[i][cc] = ival(cc == i ? 1.0 : 0.0) + Kc[i][cc];
+                Jc[n + i][cc] = ival(cc == n + i ? 1.0 : 0.0) + Kc[n + i][cc];
             }
         }
         // the mean-value form of the phi-set update needs DPhi on the segments [x, phi]: Jc + s dJ, s in [0,1]
@@ -395,7 +403,8 @@ static inline void run_front(const ccp_front_desc& d, ccp_front_result& res, std
         // ---- set update of the front:  C+ = mid(J C),  r+ = J r + (y - x+) + (J C - C+) r0,  J = Jc + [0,1] dJ;  dot products in (mid,t) form ----
         double xn[MAXD], Cn[MAXD][MAXD]; ival rn[MAXD]; mt JCr[MAXD][MAXD], Jm[MAXD][MAXD], Jcm[MAXD][MAXD];
         for (int i = 0; i < D; i++) for (int k = 0; k < D; k++) { Jm[i][k] = iv2mt(J[i][k]); Jcm[i][k] = iv2mt(Jc[i][k]); }
-        for (int i = 0; i < D; i++) xn[i] = mid_ru(y[i]);
+        ival zc[MAXD];
+        for (int i = 0; i < D; i++) { xn[i] = add_ru(x[i], mid_ru(y[i])); zc[i] = (ival(x[i]) - ival(xn[i])) + y[i]; }
         for (int i = 0; i < D; i++) for (int j = 0; j < D; j++) {
             ival jc(0.0); for (int k = 0; k < D; k++) ipfma(jc, J[i][k], C[k][j]);
             Cn[i][j] = mid_ru(jc); JCr[i][j] = iv2mt(jc - ival(Cn[i][j]));
@@ -403,19 +412,20 @@ static inline void run_front(const ccp_front_desc& d, ccp_front_result& res, std
         for (int i = 0; i < D; i++) {
             acc4 a; for (int j = 0; j < D; j++) acc_term(a, JCr[i][j], r0m[j]);
             for (int j = 0; j < D; j++) acc_term(a, Jm[i][j], iv2mt(r[j]));
-            rn[i] = (y[i] - ival(xn[i])) + acc_finish(a);
+            rn[i] = zc[i] + acc_finish(a);
         }
         // ---- frame update:  T+ = (Jc + sum_j Xi_j r0_j + Xi_r)(Tc + sum_l Theta_l r0_l + R) ----
         double Tcn[MAXD][MAXN]; ival Rn[MAXD][MAXN], Psn[MAXD][MAXN];
         static thread_local double Thn[MAXD][MAXD][MAXN];
         for (int i = 0; i < D; i++) for (int k = 0; k < n; k++) {
-            ival jt(0.0); for (int l = 0; l < D; l++) ipfma(jt, Jc[i][l], Tc[l][k]);
-            Tcn[i][k] = mid_ru(jt);
+            ival jt(0.0); for (int l = 0; l < D; l++) ipfma(jt, Kc[i][l], Tc[l][k]);               // increment Kc Tc
+            Tcn[i][k] = add_ru(Tc[i][k], mid_ru(jt));
+            jt = (ival(Tc[i][k]) - ival(Tcn[i][k])) + jt;                                           // Jc Tc - Tc+
             acc4 e;
             for (int l = 0; l < D; l++) acc_term(e, Jcm[i][l], iv2mt(R[l][k]));                    // Jc R
             for (int l = 0; l < D; l++) acc_term(e, dJm[i][l], iv2mt(S0[l][k] + R[l][k]));         // second order
             ival xr(0.0); for (int l = 0; l < D; l++) ipfma(xr, Xi[D][i][l], Tc[l][k]);            // Xi_r Tc
-            Rn[i][k] = ((jt - ival(Tcn[i][k])) + acc_finish(e)) + xr;
+            Rn[i][k] = (jt + acc_finish(e)) + xr;
         }
         for (int j = 0; j < D; j++) for (int i = 0; i < D; i++) for (int k = 0; k < n; k++) {
             ival t(0.0);

@@ -58,15 +58,15 @@ def test_c2_and_ref_agree(config1_ref, config1_c2):
         assert 0.5 <= ratio.min() and ratio.max() <= 2.0
         assert abs(np.median(ratio) - 1.0) < 1e-2
     # point evaluations (det at the grid points): the point values (midpoints) agree to 1e-12 relative where the
-    # enclosure is that tight; widths within 2x of the reference-structured run on EVERY row (the first-order tracking of
-    # the frame's dependence on the front's box, oracle/c2.hpp; mode c1 without it is up to 173x wider)
+    # enclosure is that tight; widths at most 1.05x the reference-structured run's on EVERY row (north_star: within 2x) -- first-order
+    # tracking of the frame's dependence on the front's box + centres advanced by increments, oracle/c2.hpp; mode c1 is up to 173x wider
     for col in (2, 4):
         rm, cm = (rs[:, col] + rs[:, col + 1]) / 2, (cs[:, col] + cs[:, col + 1]) / 2
         rel = np.abs(rm - cm) / np.abs(rm)
         tight = (rs[:, col + 1] - rs[:, col]) / np.abs(rm) < 1e-13
         assert tight.sum() == 0 or rel[tight].max() < 1e-12
         ratio = (cs[:, col + 1] - cs[:, col]) / (rs[:, col + 1] - rs[:, col])
-        assert ratio.max() <= 2.0 and np.median(ratio) < 1.1, (ratio.max(), np.median(ratio))
+        assert ratio.max() <= 1.05 and np.median(ratio) < 1.01, (ratio.max(), np.median(ratio))
 
 
 def test_c1_legacy_mode_still_consistent(pkg, orc, config1_desc, config1_c2):
@@ -138,13 +138,13 @@ def test_edge_cases(pkg, orc):
 
 
 @pytest.mark.parametrize("n,params,bound", [
-    (2, [1.0, .97, .05], 2.0),
-    (3, [1.0, .98, .96, .04, -.02], 2.0),
-    (4, [1.0, .98, .96, .94, .04, .02, .03], 2.0),
-    (3, "sweep13", 2.0),            # reference sweep (Construct_ParameterList 24 x 4), front 13
-    (3, "sweep50", 2.0),
-    (3, "sweep0", 4.0),             # longest fronts of the sweep (L_- > 35.5): the rounding box of the centre trajectory is not
-                                    # tracked across steps: det at grid points up to 2.3x, last frame up to 3.7x
+    (2, [1.0, .97, .05], 1.25),
+    (3, [1.0, .98, .96, .04, -.02], 1.25),
+    (4, [1.0, .98, .96, .94, .04, .02, .03], 1.25),
+    (3, "sweep13", 1.25),           # reference sweep (Construct_ParameterList 24 x 4), front 13
+    (3, "sweep50", 1.25),
+    (3, "sweep0", 1.25),            # one of the fronts that were 2.3x / 3.7x (last frame) before the centres advanced by increments
+    (3, "sweep95", 1.25),
 ])
 def test_enclosure_widths_within_bound_of_ref(pkg, orc, n, params, bound):
     """north_star: every enclosure contains the reference's values and is at most 2x as wide.  'Reference' = oracle mode ref
