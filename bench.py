@@ -77,6 +77,27 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(self.rows)}
 
 
+def ncu_dram_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one front_kernel<3> launch of 1,024 fronts, from the newest committed
+    `ncu --set full` summary under profiles/ (bytes; None if there is none).  Mostly instruction fetch: the algorithmic traffic is
+    ~2.9 MB per launch (descriptors in, result records out)."""
+    import glob
+    import re
+    best = None
+    for f in glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_front_kernel.txt")):
+        m = re.search(r"_v(\d+)_", os.path.basename(f))
+        if m and (best is None or int(m.group(1)) > best[0]):
+            best = (int(m.group(1)), f)
+    if best is None:
+        return None
+    tot = 0.0
+    for ln in open(best[1]):
+        m = re.match(r"dram__bytes_(read|write)\.sum \[(\w+)\] = ([\d.,]+)", ln)
+        if m:
+            tot += float(m.group(3).replace(",", "")) * {"Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Gbyte": 1e9}[m.group(2)]
+    return tot or None
+
+
 def cpu_reference_sample(pkg, orc, n_fronts_total, cores, steps=1, warmup=0):
     """Times the oracle's reference-structured mode (n separate 4n-dim validated integrations + topFrame) on
     `cores` fronts taken evenly from the sweep, one front per host thread."""
@@ -236,7 +257,7 @@ def main():
     # ---- roofline of the dominant kernel: counted FP64 flop of the implemented algorithm / CUDA-event time
     flop_local = float(sum(pkg.front_flops(3, 20, 14, int(s)) for s in steps_arr[mine]))
     achieved = flop_local / (sum(ker_ms) / K * 1e-3) / 1e12
-    roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+    roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": ncu_dram_traffic(),
                 "peak_source": "measured live on this GPU: 8 independent DFMA.RM/RP chains per thread (ccp_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry (nominal 37 TF)",
                 "kernel": "ccp::front_kernel<3>", "kernel_ms": sum(ker_ms) / K, "flop_per_launch": flop_local,
                 "note": "FP64 vector-pipe bound: ~1.2 MB in / 1.7 MB out per launch vs ~2e11 flop; DFMA=2 flop, DADD/DMUL=1 (DESIGN.md 5)"}
