@@ -67,7 +67,7 @@ struct SPar { double pl, ph; int neg, straddle; };
 
 // low-order Taylor data over the hull [X] of the phi-set (oracle/c2.hpp:HullM): W[q] = coefficients of u - 1/2 (q <= 3),
 // G = u(1-u), Pw = w_0 w_1, dense tridiagonal M_0, M_1 -- all in (mid,t) form
-template <int N> struct HullM { mt W[4][N], M0[N][N], M1[N][N]; };
+template <int N> struct HullM { mt W[4][N], G[N], Pw[N], M0[N][N], M1[N][N]; };
 // parameter tables of a front (oracle/c2.hpp:ParM); missing chain neighbours are zero parameters
 template <int N> struct ParM { mt B[N], B3[N], B6[N], Cm[N], Cp[N], C2m[N], C2p[N], C2[N]; ival halfB[N]; mt PN[N][N][3]; };
 
@@ -561,46 +561,38 @@ __device__ __noinline__ void second_variation(FrontSmem<N>& S, PostTab<N>& PT, i
     constexpr int D = 2 * N;
     const int tid = threadIdx.x;
     HullM<N>& H = S.hm;
-    // H: W_0, W_1, u_2 = F(u)/2 and the diagonals of M_0, M_1 (lane i < N; G = u(1-u) and Pw = w_0 w_1 of the chain neighbours are
-    //    recomputed, same operations => same bits);  off-diagonals of M_0, M_1 (lanes 32..32+N-2)
-    if (tid < N) {
-        const int i = tid, im = i > 0 ? i - 1 : 0, ip = i < N - 1 ? i + 1 : N - 1;
-        mt w0i, gi, gm, gp, pi, pm_, pp;
-        {
-            const ival u = S.X[i]; const ival w0v = isub(u, pt(0.5));
-            const mt w0 = iv2mt(w0v), w1 = iv2mt(S.X[N + i]);
-            H.W[0][i] = w0; H.W[1][i] = w1; w0i = w0;
-            gi = iv2mt(imul(u, isub(pt(1.0), u)));
-            acc4 a = acc_zero(); acc_term(a, w0, w1); pi = iv2mt(acc_finish(a));
+    // H (warp 0 only; warp 1 waits at the barrier): lanes < N: W_0, W_1, G = u(1-u), Pw = w_0 w_1; lanes N..2N-2: off-diagonals of
+    //    M_0, M_1; then, after a __syncwarp, lanes < N: u_2 = F(u)/2 and the diagonals of M_0, M_1 from G, Pw of the chain neighbours
+    if (tid < 32) {
+        if (tid < N) {
+            const int m = tid;
+            const ival u = S.X[m];
+            const mt w0 = iv2mt(isub(u, pt(0.5))), w1 = iv2mt(S.X[N + m]);
+            H.W[0][m] = w0; H.W[1][m] = w1; H.G[m] = iv2mt(imul(u, isub(pt(1.0), u)));
+            acc4 a = acc_zero(); acc_term(a, w0, w1); H.Pw[m] = iv2mt(acc_finish(a));
+        } else if (tid < 2 * N - 1) {
+            const int e = tid - N;
+            const mt w0a = iv2mt(isub(S.X[e], pt(0.5))), w0b = iv2mt(isub(S.X[e + 1], pt(0.5))), w1a = iv2mt(S.X[N + e]), w1b = iv2mt(S.X[N + e + 1]);
+            acc4 a = acc_zero(); acc_term(a, w0a, w0b);
+            acc4 a2 = acc_zero(); acc_term(a2, S.pm.C2[e], iv2mt(acc_finish(a)));
+            const mt m0 = iv2mt(acc_finish(a2));
+            H.M0[e][e + 1] = m0; H.M0[e + 1][e] = m0;
+            acc4 u = acc_zero(); acc_term(u, w0a, w1b); acc_term(u, w1a, w0b);
+            acc4 u2 = acc_zero(); acc_term(u2, S.pm.C2[e], iv2mt(acc_finish(u)));
+            const mt m1 = iv2mt(acc_finish(u2));
+            H.M1[e][e + 1] = m1; H.M1[e + 1][e] = m1;
         }
-        {
-            const ival u = S.X[im];
-            gm = iv2mt(imul(u, isub(pt(1.0), u)));
-            acc4 a = acc_zero(); acc_term(a, iv2mt(isub(u, pt(0.5))), iv2mt(S.X[N + im])); pm_ = iv2mt(acc_finish(a));
+        __syncwarp();
+        if (tid < N) {
+            const int i = tid, im = i > 0 ? i - 1 : 0, ip = i < N - 1 ? i + 1 : N - 1;
+            const mt gi = H.G[i], gm = H.G[im], gp = H.G[ip];
+            acc4 sa = acc_zero(); acc_term(sa, S.pm.B[i], gi); acc_term(sa, S.pm.Cm[i], gm); acc_term(sa, S.pm.Cp[i], gp);
+            H.W[2][i] = iv2mt(ihalf(ineg(imul(isub(S.X[i], pt(0.5)), acc_finish(sa)))));
+            acc4 ta = acc_zero(); acc_term(ta, S.pm.B3[i], gi); acc_term(ta, S.pm.Cm[i], gm); acc_term(ta, S.pm.Cp[i], gp);
+            H.M0[i][i] = iv2mt(isub(S.pm.halfB[i], acc_finish(ta)));
+            acc4 ma = acc_zero(); acc_term(ma, S.pm.B6[i], H.Pw[i]); acc_term(ma, S.pm.C2m[i], H.Pw[im]); acc_term(ma, S.pm.C2p[i], H.Pw[ip]);
+            H.M1[i][i] = iv2mt(acc_finish(ma));
         }
-        {
-            const ival u = S.X[ip];
-            gp = iv2mt(imul(u, isub(pt(1.0), u)));
-            acc4 a = acc_zero(); acc_term(a, iv2mt(isub(u, pt(0.5))), iv2mt(S.X[N + ip])); pp = iv2mt(acc_finish(a));
-        }
-        acc4 sa = acc_zero(); acc_term(sa, S.pm.B[i], gi); acc_term(sa, S.pm.Cm[i], gm); acc_term(sa, S.pm.Cp[i], gp);
-        H.W[2][i] = iv2mt(ihalf(ineg(imul(isub(S.X[i], pt(0.5)), acc_finish(sa)))));
-        acc4 ta = acc_zero(); acc_term(ta, S.pm.B3[i], gi); acc_term(ta, S.pm.Cm[i], gm); acc_term(ta, S.pm.Cp[i], gp);
-        H.M0[i][i] = iv2mt(isub(S.pm.halfB[i], acc_finish(ta)));
-        acc4 ma = acc_zero(); acc_term(ma, S.pm.B6[i], pi); acc_term(ma, S.pm.C2m[i], pm_); acc_term(ma, S.pm.C2p[i], pp);
-        H.M1[i][i] = iv2mt(acc_finish(ma));
-        (void)w0i;
-    } else if (tid >= 32 && tid < 32 + N - 1) {
-        const int e = tid - 32;
-        const mt w0a = iv2mt(isub(S.X[e], pt(0.5))), w0b = iv2mt(isub(S.X[e + 1], pt(0.5))), w1a = iv2mt(S.X[N + e]), w1b = iv2mt(S.X[N + e + 1]);
-        acc4 a = acc_zero(); acc_term(a, w0a, w0b);
-        acc4 a2 = acc_zero(); acc_term(a2, S.pm.C2[e], iv2mt(acc_finish(a)));
-        const mt m0 = iv2mt(acc_finish(a2));
-        H.M0[e][e + 1] = m0; H.M0[e + 1][e] = m0;
-        acc4 u = acc_zero(); acc_term(u, w0a, w1b); acc_term(u, w1a, w0b);
-        acc4 u2 = acc_zero(); acc_term(u2, S.pm.C2[e], iv2mt(acc_finish(u)));
-        const mt m1 = iv2mt(acc_finish(u2));
-        H.M1[e][e + 1] = m1; H.M1[e + 1][e] = m1;
     }
     __syncthreads();
     // X1: u_3 = M_0 u_1 / 6;  d_0..d_3 of every direction
@@ -1232,16 +1224,36 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
         PROF(1);
         TRC(3);
         // ---- step image: y = Phi(x), Jc = DPhi(x) (centre tables); frame at step start W = ((Tc + sum_j Theta_j r0_j) + R) + Ps Err ----
-        for (int t = tid; t < D + D * D + D * N; t += NT) {
-            if (t < D) {
-                const int i = t % N;
-                S.y[t] = iadd(eval_inc(t < N ? T[L::U(i)] : T[L::V(i)], p, hs), sym(mj.rho_phi));         // increment Phi(x) - x
-            } else if (t < D + D * D) {
-                const int e = t - D, row = e / D, cc = e % D, i = row % N;
-                const ival kc = iadd(eval_inc(row < N ? T[L::PU(i, cc)] : T[L::PV(i, cc)], p, hs), sym(mj.rho_psi));  // DPhi(x) - I
-                S.Kc[row][cc] = kc; S.Jc[row][cc] = iadd(pt(row == cc ? 1.0 : 0.0), kc);
-            } else {
-                const int e = t - D - D * D, cc = e / N, bb = e % N;
+        //      One instruction stream per warp: the first threads evaluate TWO increment series each (interleaved Horner chains), the
+        //      last D*N threads form the frame entries.
+        {
+            constexpr int NH = D + D * D, NHT = (NH + 1) / 2;
+            for (int tt = tid; tt < NHT; tt += NT) {
+                const int hA = 2 * tt, hB = 2 * tt + 1 < NH ? 2 * tt + 1 : NH - 1;
+                auto row_of = [&](int h) -> const mt* {
+                    if (h < D) return h < N ? T[L::U(h)] : T[L::V(h - N)];
+                    const int e = h - D, row = e / D, cc = e % D, i = row % N;
+                    return row < N ? T[L::PU(i, cc)] : T[L::PV(i, cc)];
+                };
+                const mt* ra = row_of(hA); const mt* rb = row_of(hB);
+                ival a = mt2iv(ra[p]), bq = mt2iv(rb[p]);
+#pragma unroll 4
+                for (int k = p - 1; k >= 1; k--) { a = horner_pt(a, hs, mt2iv(ra[k])); bq = horner_pt(bq, hs, mt2iv(rb[k])); }
+                a = mk(__dmul_rd(a.lo, hs), __dmul_ru(a.hi, hs)); bq = mk(__dmul_rd(bq.lo, hs), __dmul_ru(bq.hi, hs));     // = eval_inc
+                auto put = [&](int h, const ival& v) {
+                    if (h < D) { S.y[h] = iadd(v, sym(mj.rho_phi)); }                                   // increment Phi(x) - x
+                    else {
+                        const int e = h - D, row = e / D, cc = e % D;
+                        const ival kc = iadd(v, sym(mj.rho_psi));                                       // DPhi(x) - I
+                        S.Kc[row][cc] = kc; S.Jc[row][cc] = iadd(pt(row == cc ? 1.0 : 0.0), kc);
+                    }
+                };
+                put(hA, a);
+                if (2 * tt + 1 < NH) put(hB, bq);
+            }
+            for (int e = tid - (NT - (D * N) % NT) % NT; e < D * N; e += NT) {
+                if (e < 0) continue;
+                const int cc = e / N, bb = e % N;
                 ival s0;
                 const ival w = frame_entry<N>(S, cc, bb, &s0);
                 S.S0[cc][bb] = s0; S.Ws[cc][bb] = w; S.Wm[cc][bb] = iv2mt(w);

@@ -207,6 +207,12 @@ def test_full_size_sweep_properties(engine, pkg):
     assert ok.mean() > 0.9
     assert np.array_equal(codes[ok], exp[ok])
     assert all(r.status == 0 for r in full)
+    # counts and certified / not certified on ALL 1,024 fronts against the reference-structured oracle (committed fixture,
+    # tests/golden/make_sweep_golden.py): north_star "counts and validation pass/fail must match exactly"
+    R = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sweep1024_ref.npz"))
+    z = np.array([r.zero_count for r in full]); f = np.array([r.failure_count for r in full]); steps = np.array([r.steps for r in full])
+    assert np.array_equal(steps, R["steps"]) and np.array_equal(z, R["zero_count"])
+    assert np.array_equal(f > 0, R["failure_count"] > 0) and np.abs(f - R["failure_count"]).max() <= 1
 
 
 def test_config4_subboxes(engine, pkg, orc):

@@ -166,3 +166,17 @@ def test_enclosure_widths_within_bound_of_ref(pkg, orc, n, params, bound):
     m = wr > 0
     assert np.all((lr[m].mean(axis=1) >= lc[m, 0]) & (lr[m].mean(axis=1) <= lc[m, 1]))
     assert (wc[m] / wr[m]).max() <= bound
+
+
+def test_sweep1024_counts_and_pass_fail_equal_ref(pkg, orc):
+    """north_star: conjugate-point counts and validation pass/fail must match exactly.  All 1,024 fronts of the bench sweep, kernel twin
+    c2 against the committed results of the reference-structured oracle (tests/golden/make_sweep_golden.py; 16 CPU-minutes)."""
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sweep1024_ref.npz"))
+    descs, _ = pkg.setup_sweep(3, pkg.parameter_list(128, 8, 0.02, 0.06))
+    res, _ = orc.run_batch(pkg.abi, descs, orc.MODE_C2, threads=0)
+    st = np.array([r.status for r in res]); z = np.array([r.zero_count for r in res]); f = np.array([r.failure_count for r in res]); steps = np.array([r.steps for r in res])
+    assert np.array_equal(st, G["status"]) and np.array_equal(steps, G["steps"])
+    assert np.array_equal(z, G["zero_count"])
+    assert np.array_equal(f > 0, G["failure_count"] > 0)                 # certified / not certified: identical on every front
+    assert np.abs(f - G["failure_count"]).max() <= 1                     # failing fronts: same failing sub-intervals up to one
+    assert int((f > 0).sum()) == 23 and sorted(np.unique(z[f == 0])) == [0, 1, 2]
