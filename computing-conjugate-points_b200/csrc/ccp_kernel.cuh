@@ -3,11 +3,11 @@
 // Replaces, for a whole batch of fronts in ONE launch, the reference's
 //   propagateManifold::frameDet -> computeTotalTrajectory x n -> getTotalTrajectory -> topFrame
 //   (propagateManifold.cpp:84-188, utils.cpp:175-263, topFrame.cpp:4-108,193-351).
-// One warp owns one front.  All Taylor tables of the current step live in that warp's shared memory
-// slice; set state is in shared memory too (small); per-lane accumulators in registers.  The sub-interval
-// determinants, Jacobi derivative and the countZeros decision tree are evaluated by the lanes that
-// produced the frame enclosures, so no trajectory (43.7 MB per front in the reference)
-// is ever materialised.  Algorithm = oracle/c1.hpp (structured C^1 Lohner method), operation for operation.
+// One CTA of 64 threads (two specialised warps) owns one front.  All Taylor tables of the current step live in that CTA's shared
+// memory; set state is in shared memory too (small); per-lane accumulators in registers.  The sub-interval determinants, Jacobi
+// derivative and the countZeros decision tree are evaluated in the same kernel, so no trajectory (43.7 MB per front in the
+// reference) is ever materialised.  Algorithm = oracle/c2.hpp (structured C^1 Lohner method with first-order tracking
+// of the frame's dependence on the front's box and centres advanced by increments), operation for operation.
 #pragma once
 #include "ccp_interval.cuh"
 #include "../../include/ccp.h"
@@ -118,7 +118,7 @@ struct FrontSmem {
     Majorant mj;
     double g15[2];
     union alignas(16) {
-        ival scratch[Lay<N>::NB + Lay<N>::NC + 2 * N];   // table loop: Cauchy sums awaiting combination; then [0,0]; then the newest hull g, q
+        ival scratch[Lay<N>::NB + Lay<N>::NC + 2 * N];   // table loop: Cauchy sums awaiting combination; then [0,0]; then the newest g, q
         mt JCr[2 * N][2 * N];                // set update: J*C - C+
         ccp_front_desc desc;                 // start of the front only
     } un;
@@ -963,12 +963,12 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
     const mt* const Tf = &T[0][0];
     // ---- per-lane operands of the three "combine" stages, fixed for the whole front.  Every stage is ONE branch-free
     //      instruction stream: out = -(P0*X0) - P1*X1 - P2*X2 (missing neighbours: zero parameter / zero slot).
-    //        phi warp, lanes < 2N      : X = Cauchy sums g*w (scratch), out/(k+1) -> v[k+1]; v[k]/(k+1) -> u[k+1], z[k+1]
-    //        Psi warp, lanes < N       : Md_i[k-1]:  X0 = 3 g_i - [k==1]/2, X1 = g_{i-1}, X2 = g_{i+1}  (hull g rows)
-    //        Psi warp, lanes N..2N-2   : Mo_e[k-1]:  X0 = 2 q_e, P0 = -c_e
-    //        Psi warp, lanes < N*D     : Pv[k] = (X0 + X1 + X2)/k from the C sums (scratch); Pu[k] = Pv[k-1]/k
+    //        phi warp, lanes MB..       : Md_i[k]:  X0 = 3 g_i - [k==0]/2, X1 = g_{i-1}, X2 = g_{i+1};  Mo_e[k]:  X0 = 2 q_e, P0 = -c_e;
+    //                                     H_i[k]:  X0 = g_i  (v' = H w)          -- g, q of the newest order come from the A lanes (scratch)
+    //        Psi warp, lanes < N*D      : Pv[k] = (X0 + X1 + X2)/k from the C sums (scratch); Pu[k] = Pv[k-1]/k
+    //      The B lanes of the phi warp turn their own Cauchy sum (H w)[k] into v[k+1], u[k+2], z[k+2] (store_vuz).
     constexpr int ZSLOT = L::NB + L::NC;
-    constexpr int GS = ZSLOT + 1;                    // scratch slots of the hull g_i (N) and q_e (N-1) of the newest order
+    constexpr int GS = ZSLOT + 1;                    // scratch slots of g_i (N) and q_e (N-1) of the newest order
     static_assert(sizeof(S.un) >= (GS + 2 * N - 1) * sizeof(ival), "scratch slots");
     bool anystr = false;
     for (int i = 0; i < 2 * N - 1; i++) anystr = anystr || S.par[i].straddle;
@@ -1042,7 +1042,7 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
             if (fl & 1) { status = CCP_ST_NONFINITE; break; }
             if (fl & 2) { status = CCP_ST_ENCLOSURE; break; }
         }
-        // ---- order 0 of all tables: set 0 = centre x, set 1 = hull X; Psi = identity ----
+        // ---- order 0 of all tables (centre x); Psi = identity ----
         if (tid < N) {
             const int i = tid;
             const ival u0 = pt(S.x[cur][i]), v0 = pt(S.x[cur][N + i]);
@@ -1062,12 +1062,12 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
         __syncthreads();
         PROF(0);
         TRC(2);
-        // ---- Taylor tables, order by order.  Warp 0 builds the front tables (centre + hull) of order k while warp 1
-        //      builds the variational tables of order k-1 from the M-series warp 0 finished one iteration earlier;
-        //      the two warps meet once per order (bar.sync 1), everything else is __syncwarp. ----
+        // ---- Taylor tables, order by order.  Warp 0 builds the front tables of order k while warp 1 builds the variational
+        //      tables of order k-1 from the M-series warp 0 finished one iteration earlier; the two warps meet once per order
+        //      (bar.sync 1), everything else is __syncwarp. ----
         // The A tasks run one order AHEAD of the B tasks: g[k+1] only needs u[<= k+1] = v[<= k]/(k+1), which is known before
-        // the products g*w of order k are -- so no lane ever waits for another lane's sum.  Lanes 2N..4N-2 of the phi warp turn
-        // the hull g, q of the newest order into the M-series with the same instruction stream that turns the g*w sums into v.
+        // the product H*w of order k is -- so no lane ever waits for another lane's sum.  The M/H lanes of the phi warp turn
+        // g, q of the newest order into the M-series and H with one branch-free instruction stream.
         // Orders are processed in blocks of two (run_block): long pass = sums of order k complete + interior of order k+1,
         // combine(k), then the two end terms of order k+1 (they need the coefficients combine(k) just produced), combine(k+1).
         // Prologue: g, q, M of order 0.
