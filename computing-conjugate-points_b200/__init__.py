@@ -123,6 +123,47 @@ def frame_det_code(res):
     return -3 if res.failure_count > 0 else res.zero_count
 
 
+# ----------------------------------------------------------------------------- boundary-value stage: C^1 flow maps
+def flow_desc(n, params, p_i, A_i, Uxy, T, stable=False, order=20, step_log2=5):
+    """Descriptor of one validated integration of the boundary-value stage: boundaryValueProblem::Gxy / DGxy
+    (boundaryValueProblem.cpp:9-115) integrate C0Rect2Set / C1Rect2Set(p_i, A_i, Uxy) for time T, forwards from the unstable
+    manifold or, `stable=True`, with the reversed field f_minus from the stable manifold.  The reversed flow is the forward
+    flow of the mirrored set (S = diag(I,-I), host/ccp_bvp.hpp), so one kernel serves both.  `p_i`, `Uxy`: (2n,2) arrays of
+    interval end points, `A_i`: (2n,2n) point matrix, `params`: b_1..b_n, c_12.. as numbers or (lo,hi) pairs."""
+    d = abi.FrontDesc()
+    D = 2 * n
+    d.n, d.order, d.step_log2, d.grid, d.L_minus = n, order, step_log2, 1, float(T)
+    pr = [(float(q), float(q)) if np.isscalar(q) else (float(q[0]), float(q[1])) for q in params]
+    for i in range(n):
+        d.b[i].lo, d.b[i].hi = pr[i]
+    for i in range(n - 1):
+        d.c[i].lo, d.c[i].hi = pr[n + i]
+    p_i = np.asarray(p_i, dtype=np.float64).reshape(D, 2); Uxy = np.asarray(Uxy, dtype=np.float64).reshape(D, 2)
+    A_i = np.asarray(A_i, dtype=np.float64).reshape(D, D)
+    for i in range(D):
+        flip = stable and i >= n
+        d.p_i[i].lo, d.p_i[i].hi = (-p_i[i, 1], -p_i[i, 0]) if flip else (p_i[i, 0], p_i[i, 1])
+        d.Uxy[i].lo, d.Uxy[i].hi = Uxy[i, 0], Uxy[i, 1]
+        for j in range(D):
+            d.A_u[i * abi.CCP_MAX_DIM + j] = -A_i[i, j] if flip else A_i[i, j]
+    return d
+
+
+def flow_result(res, n, stable=False):
+    """(image, deriv_A) of one flow-map result record: image[2n,2] encloses Phi_T(set) (Gxy), deriv_A[2n,2n,2] encloses
+    [D Phi_T] A_i over the set (DGxy before the factor DW); mirrored back for `stable=True`."""
+    D = 2 * n
+    img = np.zeros((D, 2)); P = np.zeros((D, D, 2))
+    for i in range(D):
+        flip = stable and i >= n
+        a = res.last_frame[i * (abi.CCP_MAX_N + 2) + n + 1]
+        img[i] = (-a.hi, -a.lo) if flip else (a.lo, a.hi)
+        for j in range(D):
+            q = res.flow_P[i * abi.CCP_MAX_DIM + j]
+            P[i, j] = (-q.hi, -q.lo) if flip else (q.lo, q.hi)
+    return img, P
+
+
 # ----------------------------------------------------------------------------- the engine (GPU only)
 class Engine:
     """One process, one GPU.  `frame_count_batch` is the drop-in for the reference's serial loop over

@@ -46,6 +46,7 @@ class FrontResult(C.Structure):
         ("first_frame", Interval * (CCP_MAX_DIM * (CCP_MAX_N + 1))),
         ("det_first", Interval),
         ("det_last", Interval),
+        ("flow_P", Interval * (CCP_MAX_DIM * CCP_MAX_DIM)),
     ]
 
 

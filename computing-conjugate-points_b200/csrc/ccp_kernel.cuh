@@ -1407,7 +1407,14 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
         cur = nxt;
         if (last && status == CCP_OK) {            // topFrame::getLastFrame: frame and front point at the end of the last step
             constexpr int ld = CCP_MAX_N + 2;
-            for (int t = tid; t < D * N; t += NT) { const int rr = t / N, k = t % N; ival s0; gres->last_frame[rr * ld + k] = toc(frame_entry<N>(S, rr, k, &s0)); }
+            for (int t = tid; t < D * N; t += NT) {
+                const int rr = t / N, k = t % N;
+                ival s0;
+                gres->last_frame[rr * ld + k] = toc(frame_entry<N>(S, rr, k, &s0));
+                // C^1 flow map times A_u (boundaryValueProblem::DGxy): unstable columns (Tc + sum_j Theta_j r0_j) + R, stable columns Ps
+                gres->flow_P[rr * CCP_MAX_DIM + k] = toc(iadd(iadd(pt(S.Tc[rr][k]), s0), S.R[rr][k]));
+                gres->flow_P[rr * CCP_MAX_DIM + N + k] = toc(S.Ps[rr][k]);
+            }
             if (tid < D) {
                 ival a = pt(S.x[cur][tid]);
                 for (int j = 0; j < D; j++) a = iadd(a, imul_nl(pt(S.C[cur][tid][j]), S.r0[j]));

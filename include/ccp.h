@@ -88,6 +88,13 @@ typedef struct {
     ccp_interval first_frame[CCP_MAX_DIM * (CCP_MAX_N + 1)];
     ccp_interval det_first;   /* det range enclosure on the first sub-interval                          */
     ccp_interval det_last;    /* det range enclosure on the last sub-interval                           */
+    /* C^1 time-L_minus map of the front ODE over the initial set, times the linearisation:
+       flow_P = [D Phi_T(set)] * A_u, rows/cols 0..2n-1, row-major ld = CCP_MAX_DIM.  This is `XY_deriv*A_i` of
+       boundaryValueProblem::DGxy (boundaryValueProblem.cpp:61-115, C1Rect2Set(p_i,A_i,Uxy)); the C^0 image
+       Phi_T(set) of boundaryValueProblem::Gxy (:9-59, C0Rect2Set(p_i,A_i,Uxy)) is last_frame column n+1.
+       Does not depend on Eu_err.  The backward maps (STABLE = true, field f_minus) follow from the time-reversal
+       symmetry Phi_{-T} = S Phi_T S, S = diag(I,-I) (host/ccp_bvp.hpp).                                        */
+    ccp_interval flow_P[CCP_MAX_DIM * CCP_MAX_DIM];
 } ccp_front_result;
 
 /* optional per-sub-interval series (topFrame::time_series / det_series, makePlot) */

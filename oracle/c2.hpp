@@ -448,7 +448,11 @@ static inline void run_front(const ccp_front_desc& d, ccp_front_result& res, std
             const int ld = CCP_MAX_N + 2;
             ival S1[MAXD][MAXN], Wl[MAXD][MAXN];
             frame_of_state(n, Tc, Th, R, Ps, r0, Errm, S1, Wl);
-            for (int rr = 0; rr < D; rr++) for (int k = 0; k < n; k++) res.last_frame[rr * ld + k] = toc(Wl[rr][k]);
+            for (int rr = 0; rr < D; rr++) for (int k = 0; k < n; k++) {
+                res.last_frame[rr * ld + k] = toc(Wl[rr][k]);
+                res.flow_P[rr * CCP_MAX_DIM + k] = toc((ival(Tc[rr][k]) + S1[rr][k]) + R[rr][k]);      // [D Phi_T(set)] A_u: unstable columns
+                res.flow_P[rr * CCP_MAX_DIM + n + k] = toc(Ps[rr][k]);                                  // stable columns
+            }
             for (int i = 0; i < D; i++) {
                 ival a(x[i]);
                 for (int j = 0; j < D; j++) a = a + ival(C[i][j]) * r0[j];

@@ -1,6 +1,6 @@
 // Exercises the C++ host shim the way the reference's driver would (heteroclinic.cpp:299-334):
 // build propagateManifold, call frameDet, read countZeros / getLastFrame.  Exit code 0 = ok, 77 = no GPU.
-#include "../../computing-conjugate-points_b200/host/ccp_frame_det.hpp"
+#include "../../computing-conjugate-points_b200/host/ccp_bvp.hpp"
 #include <cmath>
 #include <cstdio>
 using namespace ccp_host;
@@ -26,6 +26,24 @@ int main() {
     if (E_u.frameDet(interval(info.L_minus), 14, IVector(6)) != -4) return 4;
     E_u.below_Lminus = [] { return false; };
     if (E_u.frameDet(interval(info.L_minus), 14, IVector(6)) != -5) return 5;
+    // boundary-value stage (boundaryValueProblem::Gxy / DGxy): forward image of the front's start set, then the backward map
+    // (STABLE = true, field f_minus) of that image must contain the start point; both integrations in one launch each
+    {
+        boundaryValueProblem BVP(n, par, /*order*/ 20, /*stepsize*/ 5);
+        FlowSet fs; fs.p_i = p_i; fs.Uxy = Uxy; fs.A_i = A; fs.stable = false;
+        const double T = 4.0;
+        IVector img = BVP.Gxy(fs, T);
+        IMatrix DA = BVP.DGxyA(fs, T);
+        FlowSet bs; bs.p_i = img; bs.Uxy = IVector(6); bs.A_i = DMatrix(6, std::vector<double>(6, 0.0)); bs.stable = true;
+        for (int i = 0; i < 6; i++) bs.A_i[i][i] = 1.0;
+        IVector back = BVP.Gxy(bs, T);
+        for (int i = 0; i < 6; i++) {
+            const double mid = 0.5 * (p_i[i].lo + p_i[i].hi);
+            if (!(back[i].lo <= mid && mid <= back[i].hi) || !(back[i].hi - back[i].lo < 1e-6)) { std::printf("round trip failed in component %d\n", i); return 6; }
+            if (!(DA[i][0].lo <= DA[i][0].hi)) return 7;
+        }
+        std::printf("Gxy round trip ok, image u_1 in [%.12e, %.12e], (D Phi A)_11 in [%.12e, %.12e]\n", img[0].lo, img[0].hi, DA[0][0].lo, DA[0][0].hi);
+    }
     ccp_shutdown();
     return 0;
 }

@@ -18,7 +18,7 @@ def test_struct_sizes_match_header(pkg):
     abi = pkg.abi
     assert C.sizeof(abi.Interval) == 16
     assert C.sizeof(abi.FrontDesc) == 1168 and C.sizeof(abi.FrontDesc) % 16 == 0
-    assert C.sizeof(abi.FrontResult) == 1632
+    assert C.sizeof(abi.FrontResult) == 2656
     assert C.sizeof(abi.SeriesRec) == 80
 
 

@@ -18,7 +18,7 @@ def _worker(rank, world, port, n_total, out_dir):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    rb = 1632
+    rb = 2656
     idx = sweep.local_indices(n_total, rank, world)
     # fake "results": record f carries f in its zero_count field and f*3 in failure_count
     local = np.zeros((len(idx), rb), dtype=np.uint8)
@@ -49,6 +49,6 @@ def test_single_rank_gather_is_identity():
     import __graft_entry__ as ge
     ge.load_package()
     from ccp_b200 import sweep
-    local = torch.arange(5 * 1632, dtype=torch.int64).to(torch.uint8)
-    out = sweep.gather_records(local, 5, 0, 1, 1632)
+    local = torch.arange(5 * 2656, dtype=torch.int64).to(torch.uint8)
+    out = sweep.gather_records(local, 5, 0, 1, 2656)
     assert torch.equal(out, local)
