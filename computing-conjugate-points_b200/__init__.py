@@ -164,6 +164,30 @@ def flow_result(res, n, stable=False):
     return img, P
 
 
+def dfu_desc(n, params, A, p, U, subdivision=15, stable=False, ainv_rel_radius=1e-13):
+    """Descriptor of one call of localManifold::boundDFU.  `A`: (2n,2n) point matrix ((*pF).A), `p`: equilibrium (2n numbers),
+    `U`: (2n,2) box in local coordinates.  The reference hands over CAPD's gaussInverseMatrix(A); for tests and synthetic sweeps the
+    float inverse is inflated by `ainv_rel_radius` * max|A^-1| per entry (far above its actual error for these 2n x 2n matrices)."""
+    D = 2 * n
+    d = abi.DfuDesc()
+    d.n, d.subdivision, d.stable = n, int(subdivision), 1 if stable else 0
+    pr = [(float(q), float(q)) if np.isscalar(q) else (float(q[0]), float(q[1])) for q in params]
+    for i in range(n):
+        d.b[i].lo, d.b[i].hi = pr[i]
+    for i in range(n - 1):
+        d.c[i].lo, d.c[i].hi = pr[n + i]
+    A = np.asarray(A, dtype=np.float64).reshape(D, D)
+    Ai = np.linalg.inv(A); rad = ainv_rel_radius * np.abs(Ai).max()
+    U = np.asarray(U, dtype=np.float64).reshape(D, 2)
+    for i in range(D):
+        d.p[i].lo = d.p[i].hi = float(p[i])
+        d.U[i].lo, d.U[i].hi = U[i, 0], U[i, 1]
+        for j in range(D):
+            d.A[i * abi.CCP_MAX_DIM + j] = A[i, j]
+            d.Ainv[i * abi.CCP_MAX_DIM + j].lo, d.Ainv[i * abi.CCP_MAX_DIM + j].hi = Ai[i, j] - rad, Ai[i, j] + rad
+    return d
+
+
 # ----------------------------------------------------------------------------- the engine (GPU only)
 class Engine:
     """One process, one GPU.  `frame_count_batch` is the drop-in for the reference's serial loop over
@@ -180,6 +204,13 @@ class Engine:
         m = len(descs)
         res = (FrontResult * m)()
         _check(self.L.ccp_frame_count_batch(descs, m, res), "ccp_frame_count_batch")
+        return res
+
+    def bound_dfu_batch(self, descs):
+        """localManifold::boundDFU (localManifold.cpp:347-409) for a batch of calls: one abi.DfuDesc each."""
+        m = len(descs)
+        res = (abi.DfuResult * m)()
+        _check(self.L.ccp_bound_dfu_batch(descs, m, res), "ccp_bound_dfu_batch")
         return res
 
     def frame_count_batch_device(self, d_descs_ptr, m, d_results_ptr, stream_ptr=None):

@@ -78,6 +78,23 @@ class SetupInfo(C.Structure):
     ]
 
 
+CCP_DFU_MAX_SUBDIV = 32
+
+
+class DfuDesc(C.Structure):
+    """One call of localManifold::boundDFU (include/ccp.h: ccp_dfu_desc)."""
+    _fields_ = [
+        ("n", C.c_int32), ("subdivision", C.c_int32), ("stable", C.c_int32), ("reserved", C.c_int32),
+        ("b", Interval * CCP_MAX_N), ("c", Interval * CCP_MAX_N),
+        ("A", C.c_double * (CCP_MAX_DIM * CCP_MAX_DIM)), ("Ainv", Interval * (CCP_MAX_DIM * CCP_MAX_DIM)),
+        ("p", Interval * CCP_MAX_DIM), ("U", Interval * CCP_MAX_DIM),
+    ]
+
+
+class DfuResult(C.Structure):
+    _fields_ = [("status", C.c_int32), ("parts", C.c_int32), ("DF", Interval * (CCP_MAX_DIM * CCP_MAX_DIM))]
+
+
 # every symbol include/ccp.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "ccp_device_count": (C.c_int, []),
@@ -88,6 +105,7 @@ SYMBOLS = {
     "ccp_frame_count_batch": (C.c_int, [C.POINTER(FrontDesc), C.c_size_t, C.POINTER(FrontResult)]),
     "ccp_frame_count_batch_device": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "ccp_frame_count_series": (C.c_int, [C.POINTER(FrontDesc), C.POINTER(FrontResult), C.POINTER(SeriesRec), C.c_size_t, C.POINTER(C.c_size_t)]),
+    "ccp_bound_dfu_batch": (C.c_int, [C.POINTER(DfuDesc), C.c_size_t, C.POINTER(DfuResult)]),
     "ccp_kernel_launches": (C.c_uint64, []),
     "ccp_last_kernel_ms": (C.c_float, []),
     "ccp_debug_primitives": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_size_t]),

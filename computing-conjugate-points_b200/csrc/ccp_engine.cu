@@ -2,6 +2,7 @@
 // FP64 peak microbenchmark.  There is NO CPU fallback: without a CUDA device every compute entry
 // point returns CCP_E_NO_DEVICE.
 #include "ccp_kernel.cuh"
+#include "ccp_dfu.cuh"
 #include <cstdio>
 #include <cstring>
 #include <cmath>
@@ -311,6 +312,37 @@ int ccp_measure_fp64_peak(int iters, double* tflops) {
 }
 
 // FP64 work of one front under the implemented algorithm: DFMA = 2 flop, DADD/DMUL = 1.
+// localManifold::boundDFU for a batch of calls: host buffers in, host buffers out
+int ccp_bound_dfu_batch(const ccp_dfu_desc* descs, size_t n_descs, ccp_dfu_result* results) {
+    std::lock_guard<std::mutex> lk(E.mu);
+    if (!E.ready) { E.err = "ccp_init has not been called (no CPU fallback)"; return CCP_E_NOT_INIT; }
+    if (!descs || !results) { E.err = "null argument"; return CCP_E_ARG; }
+    if (n_descs == 0) return 0;
+    void* d_in = nullptr; void* d_out = nullptr;
+    CK(cudaMalloc(&d_in, n_descs * sizeof(ccp_dfu_desc)));
+    CK(cudaMalloc(&d_out, n_descs * sizeof(ccp_dfu_result)));
+    CK(cudaMemcpyAsync(d_in, descs, n_descs * sizeof(ccp_dfu_desc), cudaMemcpyHostToDevice, E.stream));
+    CK(cudaMemsetAsync(d_out, 0, n_descs * sizeof(ccp_dfu_result), E.stream));               // unused matrix entries (n < CCP_MAX_N) stay zero
+    const int grid = (int)(n_descs < (size_t)(8 * E.sm_count) ? n_descs : (size_t)(8 * E.sm_count));
+    CK(cudaFuncSetAttribute(ccp::dfu_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ccp::DfuSmem<2>)));
+    CK(cudaFuncSetAttribute(ccp::dfu_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ccp::DfuSmem<3>)));
+    CK(cudaFuncSetAttribute(ccp::dfu_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ccp::DfuSmem<4>)));
+    bool has[CCP_MAX_N + 1] = {false, false, false, false, false};
+    for (size_t i = 0; i < n_descs; i++) if (descs[i].n >= 2 && descs[i].n <= CCP_MAX_N) has[descs[i].n] = true;
+    CK(cudaEventRecord(E.ev0, E.stream));
+    if (has[2]) { ccp::dfu_kernel<2><<<grid, ccp::DFU_NT, sizeof(ccp::DfuSmem<2>), E.stream>>>((const ccp_dfu_desc*)d_in, (ccp_dfu_result*)d_out, (int)n_descs); E.launches++; }
+    if (has[3]) { ccp::dfu_kernel<3><<<grid, ccp::DFU_NT, sizeof(ccp::DfuSmem<3>), E.stream>>>((const ccp_dfu_desc*)d_in, (ccp_dfu_result*)d_out, (int)n_descs); E.launches++; }
+    if (has[4]) { ccp::dfu_kernel<4><<<grid, ccp::DFU_NT, sizeof(ccp::DfuSmem<4>), E.stream>>>((const ccp_dfu_desc*)d_in, (ccp_dfu_result*)d_out, (int)n_descs); E.launches++; }
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(E.ev1, E.stream));
+    CK(cudaMemcpyAsync(results, d_out, n_descs * sizeof(ccp_dfu_result), cudaMemcpyDeviceToHost, E.stream));
+    CK(cudaStreamSynchronize(E.stream));
+    CK(cudaEventElapsedTime(&E.last_ms, E.ev0, E.ev1));
+    for (size_t i = 0; i < n_descs; i++) if (descs[i].n < 2 || descs[i].n > CCP_MAX_N) { std::memset(&results[i], 0, sizeof(ccp_dfu_result)); results[i].status = CCP_ST_BAD_DESC; }
+    cudaFree(d_in); cudaFree(d_out);
+    return 0;
+}
+
 double ccp_front_flops(int n, int order, int grid, int steps) {
     // algorithmic FP64 work of one front (DFMA = 2 flop, DADD/DMUL = 1), DESIGN.md section 5
     const double p = order, g = grid, N = n, D = 2.0 * n;

@@ -135,6 +135,30 @@ int ccp_frame_count_batch_device(const void* d_fronts, size_t n_fronts, void* d_
 int ccp_frame_count_series(const ccp_front_desc* front, ccp_front_result* result,
                            ccp_series_rec* series, size_t cap, size_t* len);
 
+/* ---------------- next row: localManifold::boundDFU ----------------
+   Interval hull, over the N^n sub-boxes of the neighbourhood U, of the derivative of the local vector field
+   Ainv * Df(p + A w) * A  (localManifold.cpp:347-409, localVField.h:31-35; part(): utils.cpp:3-10).  One descriptor per call of
+   boundDFU; the reference calls it >= 4 times per front with N = 15 (3,375 sub-boxes for n = 3).                              */
+#define CCP_DFU_MAX_SUBDIV 32
+typedef struct {
+    int32_t n;            /* components; the field is 2n-dimensional                                              */
+    int32_t subdivision;  /* N = subdivisionNUM (localManifold.h:28; heteroclinic.cpp:64 manifold_subdivision = 15) */
+    int32_t stable;       /* 1: subdivide coordinates n..2n-1 (stable manifold), 0: coordinates 0..n-1            */
+    int32_t reserved;
+    ccp_interval b[CCP_MAX_N];
+    ccp_interval c[CCP_MAX_N];                  /* c[0..n-2]                                                        */
+    double       A[CCP_MAX_DIM * CCP_MAX_DIM];  /* (*pF).A, point matrix, row-major ld CCP_MAX_DIM                  */
+    ccp_interval Ainv[CCP_MAX_DIM * CCP_MAX_DIM]; /* (*pF).Ainv = gaussInverseMatrix(A) (host, stays CAPD)          */
+    ccp_interval p[CCP_MAX_DIM];                /* (*pF).p, the equilibrium                                         */
+    ccp_interval U[CCP_MAX_DIM];                /* the neighbourhood in local coordinates (constructU)              */
+} ccp_dfu_desc;
+typedef struct {
+    int32_t status;       /* CCP_OK or CCP_ST_BAD_DESC                                                             */
+    int32_t parts;        /* N^n                                                                                   */
+    ccp_interval DF[CCP_MAX_DIM * CCP_MAX_DIM]; /* the hull, row-major ld CCP_MAX_DIM                              */
+} ccp_dfu_result;
+int ccp_bound_dfu_batch(const ccp_dfu_desc* descs, size_t n_descs, ccp_dfu_result* results);
+
 /* kernel launch accounting + last kernel time for bench.py */
 uint64_t ccp_kernel_launches(void);
 float    ccp_last_kernel_ms(void);

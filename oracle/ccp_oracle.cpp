@@ -16,6 +16,7 @@
 #include "ref.hpp"
 #include "c1.hpp"
 #include "c2.hpp"
+#include "dfu.hpp"
 #include <thread>
 #include <atomic>
 #include <chrono>
@@ -58,6 +59,12 @@ int orc_run_batch(const ccp_front_desc* d, size_t n_fronts, int mode, ccp_front_
     work();
     for (auto& t : th) t.join();
     if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return 0;
+}
+
+int orc_bound_dfu(const ccp_dfu_desc* d, size_t n, ccp_dfu_result* res) {
+    RoundUpGuard guard;
+    for (size_t i = 0; i < n; i++) dfu::run(d[i], res[i]);
     return 0;
 }
 

@@ -67,6 +67,16 @@ def run_batch(abi, descs, mode, threads=0):
     return res, sec.value
 
 
+def bound_dfu(abi, descs):
+    """oracle/dfu.hpp: serial restatement of localManifold::boundDFU for an array of abi.DfuDesc."""
+    L = lib(abi)
+    L.orc_bound_dfu.argtypes = [C.POINTER(abi.DfuDesc), C.c_size_t, C.POINTER(abi.DfuResult)]
+    m = len(descs)
+    res = (abi.DfuResult * m)()
+    L.orc_bound_dfu(descs, m, res)
+    return res
+
+
 def ival_op(abi, op, a, b):
     out = (C.c_double * 2)()
     lib(abi).orc_ival_op(op, a[0], a[1], b[0], b[1], out)

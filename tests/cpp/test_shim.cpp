@@ -1,6 +1,7 @@
 // Exercises the C++ host shim the way the reference's driver would (heteroclinic.cpp:299-334):
 // build propagateManifold, call frameDet, read countZeros / getLastFrame.  Exit code 0 = ok, 77 = no GPU.
 #include "../../computing-conjugate-points_b200/host/ccp_bvp.hpp"
+#include "../../computing-conjugate-points_b200/host/ccp_local_manifold.hpp"
 #include <cmath>
 #include <cstdio>
 using namespace ccp_host;
@@ -43,6 +44,29 @@ int main() {
             if (!(DA[i][0].lo <= DA[i][0].hi)) return 7;
         }
         std::printf("Gxy round trip ok, image u_1 in [%.12e, %.12e], (D Phi A)_11 in [%.12e, %.12e]\n", img[0].lo, img[0].hi, DA[0][0].lo, DA[0][0].hi);
+    }
+    // localManifold::boundDFU: the undivided box must contain the N = 15 hull, and Df at the equilibrium (diagonal in eigen-coordinates) lies inside
+    {
+        LocalField F; F.A = A; F.p = IVector(6, interval(0.0)); F.Ainv = IMatrix(6, IVector(6));
+        // inverse of the symplectically normalised eigenbasis by Gauss-Jordan in doubles, inflated (the reference hands over CAPD's gaussInverseMatrix)
+        double M[6][12];
+        for (int i = 0; i < 6; i++) for (int j = 0; j < 12; j++) M[i][j] = j < 6 ? A[i][j] : (j - 6 == i ? 1.0 : 0.0);
+        for (int c = 0; c < 6; c++) {
+            int piv = c; for (int r = c + 1; r < 6; r++) if (std::fabs(M[r][c]) > std::fabs(M[piv][c])) piv = r;
+            for (int j = 0; j < 12; j++) std::swap(M[c][j], M[piv][j]);
+            const double dv = M[c][c]; for (int j = 0; j < 12; j++) M[c][j] /= dv;
+            for (int r = 0; r < 6; r++) if (r != c) { const double f = M[r][c]; for (int j = 0; j < 12; j++) M[r][j] -= f * M[c][j]; }
+        }
+        for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) F.Ainv[i][j] = interval(M[i][6 + j] - 1e-12, M[i][6 + j] + 1e-12);
+        IVector U(6); for (int i = 0; i < 6; i++) U[i] = i < 3 ? interval(-1e-2, 1e-2) : interval(-1e-3, 1e-3);
+        IMatrix H1 = boundDFU(n, par, F, U, false, 1), H15 = boundDFU(n, par, F, U, false, 15);
+        double w1 = 0, w15 = 0;
+        for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) {
+            if (!(H15[i][j].lo >= H1[i][j].lo - 1e-12 && H15[i][j].hi <= H1[i][j].hi + 1e-12)) { std::printf("boundDFU: subdivision is not a subset at (%d,%d)\n", i, j); return 8; }
+            w1 += H1[i][j].hi - H1[i][j].lo; w15 += H15[i][j].hi - H15[i][j].lo;
+        }
+        if (!(w15 < w1)) return 9;
+        std::printf("boundDFU ok: total width %.3e (N = 1) -> %.3e (N = 15), DF[0][0] in [%.9f, %.9f]\n", w1, w15, H15[0][0].lo, H15[0][0].hi);
     }
     ccp_shutdown();
     return 0;
