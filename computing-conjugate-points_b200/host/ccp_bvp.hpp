@@ -17,8 +17,30 @@
 // Integration parameters are the engine's (fixed step 2^-step_size, order); T is a point (the reference passes a thin interval).
 #pragma once
 #include "ccp_frame_det.hpp"
+#include <algorithm>
+#include <cmath>
 
 namespace ccp_host {
+
+// Rigorous host interval operations for the small amount of interval algebra of NewtonStep: every IEEE result is moved outward by
+// one ulp (nextafter), which encloses the exact result of a correctly rounded +, -, *, sqrt whatever the rounding mode.
+namespace ia {
+inline double dn(double x) { return std::nextafter(x, -INFINITY); }
+inline double up(double x) { return std::nextafter(x, INFINITY); }
+inline interval add(const interval& a, const interval& b) { return interval(dn(a.lo + b.lo), up(a.hi + b.hi)); }
+inline interval sub(const interval& a, const interval& b) { return interval(dn(a.lo - b.hi), up(a.hi - b.lo)); }
+inline interval neg(const interval& a) { return interval(-a.hi, -a.lo); }
+inline interval mul(const interval& a, const interval& b) {
+    const double c[4] = {a.lo * b.lo, a.lo * b.hi, a.hi * b.lo, a.hi * b.hi};
+    return interval(dn(std::min(std::min(c[0], c[1]), std::min(c[2], c[3]))), up(std::max(std::max(c[0], c[1]), std::max(c[2], c[3]))));
+}
+inline interval sqr(const interval& a) {
+    if (a.lo >= 0) return interval(dn(a.lo * a.lo), up(a.hi * a.hi));
+    if (a.hi <= 0) return interval(dn(a.hi * a.hi), up(a.lo * a.lo));
+    return interval(0.0, up(std::max(a.lo * a.lo, a.hi * a.hi)));
+}
+inline interval sqrt(const interval& a) { return interval(a.lo > 0 ? std::max(0.0, dn(std::sqrt(a.lo))) : 0.0, up(std::sqrt(std::max(a.hi, 0.0)))); }
+}
 
 struct FlowSet {                 // what getPointNbd / (*pF).A hand to C0Rect2Set / C1Rect2Set
     IVector p_i, Uxy;            // 2n each
@@ -71,6 +93,98 @@ class boundaryValueProblem {
         }
         return out;
     }
+
+    // ---------------- the Krawczyk / Newton step of the boundary-value stage ----------------
+    // What boundaryValueProblem reads from its two localManifold objects (localManifold.h:24-36, localVField.h:17-19).
+    struct Manifold { DMatrix A; IVector p; interval L; bool stable; };
+
+    // localManifold::getPointNbd (localManifold.cpp:73-102) with constructU (:4-41) and getPoint (:43-71)
+    static FlowSet getPointNbd(const Manifold& m, const IVector& pt, const IVector& nbd) {
+        const int n = (int)pt.size(), D = 2 * n;
+        interval norm(0.0);
+        for (int i = 0; i < n; i++) norm = ia::add(norm, ia::sqr(ia::add(pt[i], nbd[i])));
+        norm = ia::sqrt(norm);
+        const interval error = ia::mul(ia::mul(m.L, interval(-1.0, 1.0)), norm);        // +- L ||U_flat||
+        FlowSet s; s.A_i = m.A; s.stable = m.stable; s.p_i.assign(D, interval(0.0)); s.Uxy.assign(D, interval(0.0));
+        IVector local(D, interval(0.0));
+        for (int i = 0; i < n; i++) local[m.stable ? n + i : i] = pt[i];
+        for (int i = 0; i < D; i++) {
+            const bool on = m.stable ? i >= n : i < n;
+            const interval U = on ? ia::add(pt[m.stable ? i - n : i], nbd[m.stable ? i - n : i]) : error;   // constructU(XY_pt + XY_nbd)
+            s.Uxy[i] = ia::sub(U, local[i]);                                                                  // translated back to enclose zero
+            interval a = m.p[i];
+            for (int j = 0; j < D; j++) a = ia::add(a, ia::mul(interval(m.A[i][j]), local[j]));              // p + A * local_pt
+            s.p_i[i] = a;
+        }
+        return s;
+    }
+    // localManifold::constructDW (localManifold.cpp:134-175): chart derivative, identity on the manifold coordinates, +-L elsewhere
+    static IMatrix DW(const Manifold& m, int n) {
+        IMatrix W(2 * n, IVector(n));
+        const interval error = ia::mul(m.L, interval(-1.0, 1.0));
+        for (int i = 0; i < 2 * n; i++) for (int j = 0; j < n; j++) {
+            const bool on = m.stable ? i >= n : i < n;
+            W[i][j] = on ? interval((m.stable ? i - n : i) == j ? 1.0 : 0.0) : error;
+        }
+        return W;
+    }
+
+    bool SUCCESS = false;
+    // boundaryValueProblem::NewtonStep (boundaryValueProblem.cpp:237-317): the image of XY_pt + XY_nbd under the interval Krawczyk
+    // operator of G(x,y) = Phi_T(x) - Phi_{-T}(y) (last row: |x|^2 - r_u^2).  The four validated integrations are ONE launch.
+    IVector NewtonStep(const Manifold& unstable, const Manifold& stable, const IVector& XY_pt, const IVector& XY_nbd, double T, interval r_u_sqr) {
+        const int n = n_, D = 2 * n;
+        IVector X_pt(XY_pt.begin(), XY_pt.begin() + n), Y_pt(XY_pt.begin() + n, XY_pt.end());
+        IVector X_nbd(XY_nbd.begin(), XY_nbd.begin() + n), Y_nbd(XY_nbd.begin() + n, XY_nbd.end());
+        const IVector zero(n, interval(0.0));
+        std::vector<Out> o = run({getPointNbd(unstable, X_pt, zero), getPointNbd(stable, Y_pt, zero),
+                                  getPointNbd(unstable, X_pt, X_nbd), getPointNbd(stable, Y_pt, Y_nbd)}, {T, T, T, T});
+        for (const Out& q : o) if (q.status != CCP_OK) throw std::runtime_error("ccp: flow map status " + std::to_string(q.status));
+        const IVector& G_x = o[0].image; const IVector& G_y = o[1].image;
+        IVector G(D);
+        for (int i = 0; i < D; i++) G[i] = ia::sub(G_x[i], G_y[i]);
+        interval x_radius_sqr(0.0);
+        for (int i = 0; i < n; i++) x_radius_sqr = ia::add(x_radius_sqr, ia::sqr(X_pt[i]));
+        G[D - 1] = ia::sub(x_radius_sqr, r_u_sqr);
+        // DG = [ DPhi_T A_u DW_u | -DPhi_{-T} A_s DW_s ;  2 (X_pt + X_nbd) | 0 ]      (DGxy :108-111, DG_combine :320-353)
+        const IMatrix Wu = DW(unstable, n), Ws = DW(stable, n);
+        IMatrix DG(D, IVector(D, interval(0.0)));
+        for (int i = 0; i < D; i++) for (int j = 0; j < n; j++) {
+            interval a(0.0), b(0.0);
+            for (int k = 0; k < D; k++) { a = ia::add(a, ia::mul(o[2].deriv_A[i][k], Wu[k][j])); b = ia::add(b, ia::mul(o[3].deriv_A[i][k], Ws[k][j])); }
+            DG[i][j] = a; DG[i][n + j] = ia::neg(b);
+        }
+        for (int j = 0; j < D; j++) DG[D - 1][j] = j < n ? ia::mul(interval(2.0), ia::add(X_pt[j], X_nbd[j])) : interval(0.0);
+        // fixed approximate inverse of mid(DG) (the reference: midMatrix(krawczykInverse(midMatrix(DG))) -- any approximation is valid)
+        std::vector<std::vector<double>> M(D, std::vector<double>(2 * D, 0.0));
+        for (int i = 0; i < D; i++) { for (int j = 0; j < D; j++) M[i][j] = 0.5 * (DG[i][j].lo + DG[i][j].hi); M[i][D + i] = 1.0; }
+        for (int c = 0; c < D; c++) {
+            int piv = c; for (int r = c + 1; r < D; r++) if (std::fabs(M[r][c]) > std::fabs(M[piv][c])) piv = r;
+            std::swap(M[c], M[piv]);
+            const double dv = M[c][c]; if (dv == 0.0) throw std::runtime_error("ccp: singular DG midpoint");
+            for (int j = 0; j < 2 * D; j++) M[c][j] /= dv;
+            for (int r = 0; r < D; r++) if (r != c) { const double f = M[r][c]; for (int j = 0; j < 2 * D; j++) M[r][j] -= f * M[c][j]; }
+        }
+        // new_Nbd = -C G + (I - C DG) XY_nbd
+        IVector new_Nbd(D), kraw(D);
+        for (int i = 0; i < D; i++) {
+            interval a(0.0);
+            for (int k = 0; k < D; k++) a = ia::sub(a, ia::mul(interval(M[i][D + k]), G[k]));
+            for (int j = 0; j < D; j++) {
+                interval e(i == j ? 1.0 : 0.0);
+                for (int k = 0; k < D; k++) e = ia::sub(e, ia::mul(interval(M[i][D + k]), DG[k][j]));
+                a = ia::add(a, ia::mul(e, XY_nbd[j]));
+            }
+            new_Nbd[i] = a; kraw[i] = ia::add(XY_pt[i], a);
+        }
+        // same energy level: the discarded velocity component must have a definite sign (:303-313); then proper containment
+        const interval gy = G_y[D - 1];
+        bool ok = gy.lo > 0 || gy.hi < 0;
+        for (int i = 0; i < D && ok; i++) ok = XY_nbd[i].lo < new_Nbd[i].lo && new_Nbd[i].hi < XY_nbd[i].hi;     // subsetInterior
+        SUCCESS = ok;
+        return kraw;
+    }
+    bool checkProof() const { return SUCCESS; }          // boundaryValueProblem::checkProof
 
   private:
     int n_; IVector params_; int order_, step_;

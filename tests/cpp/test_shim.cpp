@@ -45,6 +45,32 @@ int main() {
         }
         std::printf("Gxy round trip ok, image u_1 in [%.12e, %.12e], (D Phi A)_11 in [%.12e, %.12e]\n", img[0].lo, img[0].hi, DA[0][0].lo, DA[0][0].hi);
     }
+    // boundary-value stage end to end (heteroclinic.cpp:165-281): zero-width Newton steps, Krawczyk iterations on a neighbourhood,
+    // inflation by 1.5, final step with proper containment = existence + local uniqueness of the connecting orbit (given the validated
+    // manifolds: cone constant L = 1.5e-5 of heteroclinic.cpp:85-86).  Every NewtonStep = 4 validated integrations in one launch.
+    {
+        boundaryValueProblem BVP(n, par, /*order*/ 20, /*stepsize*/ 5);
+        boundaryValueProblem::Manifold Mu{A, IVector(6, interval(0.0)), interval(1.5e-5), false}, Ms{A, IVector(6, interval(0.0)), interval(1.5e-5), true};
+        for (int i = 0; i < 3; i++) Ms.p[i] = interval(1.0);                       // equilibrium (1,1,1 | 0,0,0); same eigenbasis (the Hessian agrees)
+        IVector XY_pt(6), XY_nbd(6, interval(0.0));
+        for (int i = 0; i < 3; i++) { XY_pt[i] = interval(info.x_local[i]); XY_pt[3 + i] = interval(info.y_local[i]); }
+        interval r_u_sqr(0.0);
+        for (int i = 0; i < 3; i++) r_u_sqr = ia::add(r_u_sqr, ia::sqr(XY_pt[i]));
+        r_u_sqr = interval(r_u_sqr.lo);
+        const double T = info.T;
+        auto midv = [](const IVector& v) { IVector m(v.size()); for (size_t i = 0; i < v.size(); i++) m[i] = interval(0.5 * (v[i].lo + v[i].hi)); return m; };
+        for (int it = 0; it < 6; it++) XY_pt = midv(BVP.NewtonStep(Mu, Ms, XY_pt, XY_nbd, T, r_u_sqr));
+        for (int i = 0; i < 6; i++) XY_nbd[i] = interval(-1e-12, 1e-12);            // scale * initial_box
+        for (int it = 0; it < 8; it++) {
+            IVector out = BVP.NewtonStep(Mu, Ms, XY_pt, XY_nbd, T, r_u_sqr);
+            XY_pt = midv(out);
+            for (int i = 0; i < 6; i++) XY_nbd[i] = ia::sub(out[i], XY_pt[i]);
+        }
+        for (int i = 0; i < 6; i++) XY_nbd[i] = ia::mul(XY_nbd[i], interval(1.5));
+        BVP.NewtonStep(Mu, Ms, XY_pt, XY_nbd, T, r_u_sqr);
+        std::printf("BVP: T = %.6f, x = (%.6e, %.6e, %.6e), nbd radius %.3e, checkProof = %d\n", T, XY_pt[0].lo, XY_pt[1].lo, XY_pt[2].lo, XY_nbd[0].hi, (int)BVP.checkProof());
+        if (!BVP.checkProof()) return 10;
+    }
     // localManifold::boundDFU: the undivided box must contain the N = 15 hull, and Df at the equilibrium (diagonal in eigen-coordinates) lies inside
     {
         LocalField F; F.A = A; F.p = IVector(6, interval(0.0)); F.Ainv = IMatrix(6, IVector(6));
