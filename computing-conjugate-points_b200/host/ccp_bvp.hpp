@@ -46,6 +46,7 @@ struct FlowSet {                 // what getPointNbd / (*pF).A hand to C0Rect2Se
     IVector p_i, Uxy;            // 2n each
     DMatrix A_i;                 // 2n x 2n point matrix
     bool stable = false;         // true: backward flow from the stable manifold (f_minus)
+    IVector params;              // optional: parameters of this set (sweeps over parameter values); empty = the solver's
 };
 
 class boundaryValueProblem {
@@ -69,8 +70,9 @@ class boundaryValueProblem {
             ccp_front_desc& e = d[q];
             e = ccp_front_desc{};
             e.n = n_; e.order = order_; e.step_log2 = step_; e.grid = 1; e.L_minus = T[q];
-            for (int i = 0; i < n_; i++) e.b[i] = to_c(params_[i]);
-            for (int i = 0; i < n_ - 1; i++) e.c[i] = to_c(params_[n_ + i]);
+            const IVector& par = s.params.empty() ? params_ : s.params;
+            for (int i = 0; i < n_; i++) e.b[i] = to_c(par[i]);
+            for (int i = 0; i < n_ - 1; i++) e.c[i] = to_c(par[n_ + i]);
             for (int i = 0; i < D; i++) {
                 const double sg = (s.stable && i >= n_) ? -1.0 : 1.0;                       // S = diag(I, -I)
                 e.p_i[i] = sg > 0 ? to_c(s.p_i[i]) : to_c(interval(-s.p_i[i].hi, -s.p_i[i].lo));
@@ -130,59 +132,84 @@ class boundaryValueProblem {
     }
 
     bool SUCCESS = false;
-    // boundaryValueProblem::NewtonStep (boundaryValueProblem.cpp:237-317): the image of XY_pt + XY_nbd under the interval Krawczyk
-    // operator of G(x,y) = Phi_T(x) - Phi_{-T}(y) (last row: |x|^2 - r_u^2).  The four validated integrations are ONE launch.
-    IVector NewtonStep(const Manifold& unstable, const Manifold& stable, const IVector& XY_pt, const IVector& XY_nbd, double T, interval r_u_sqr) {
+    // One Krawczyk step of one front: everything NewtonStep reads (the two manifolds, the point and its neighbourhood, T, r_u^2).
+    struct StepIn { Manifold unstable, stable; IVector XY_pt, XY_nbd; double T; interval r_u_sqr; IVector params; };
+    struct StepOut { IVector kraw_image; bool success; };
+
+    // boundaryValueProblem::NewtonStep (boundaryValueProblem.cpp:237-317) for many fronts (a parameter sweep): the image of
+    // XY_pt + XY_nbd under the interval Krawczyk operator of G(x,y) = Phi_T(x) - Phi_{-T}(y) (last row: |x|^2 - r_u^2).
+    // The 4 validated integrations of every front -- 4 * in.size() -- are ONE launch.
+    std::vector<StepOut> NewtonStepBatch(const std::vector<StepIn>& in) {
         const int n = n_, D = 2 * n;
-        IVector X_pt(XY_pt.begin(), XY_pt.begin() + n), Y_pt(XY_pt.begin() + n, XY_pt.end());
-        IVector X_nbd(XY_nbd.begin(), XY_nbd.begin() + n), Y_nbd(XY_nbd.begin() + n, XY_nbd.end());
         const IVector zero(n, interval(0.0));
-        std::vector<Out> o = run({getPointNbd(unstable, X_pt, zero), getPointNbd(stable, Y_pt, zero),
-                                  getPointNbd(unstable, X_pt, X_nbd), getPointNbd(stable, Y_pt, Y_nbd)}, {T, T, T, T});
-        for (const Out& q : o) if (q.status != CCP_OK) throw std::runtime_error("ccp: flow map status " + std::to_string(q.status));
-        const IVector& G_x = o[0].image; const IVector& G_y = o[1].image;
-        IVector G(D);
-        for (int i = 0; i < D; i++) G[i] = ia::sub(G_x[i], G_y[i]);
-        interval x_radius_sqr(0.0);
-        for (int i = 0; i < n; i++) x_radius_sqr = ia::add(x_radius_sqr, ia::sqr(X_pt[i]));
-        G[D - 1] = ia::sub(x_radius_sqr, r_u_sqr);
-        // DG = [ DPhi_T A_u DW_u | -DPhi_{-T} A_s DW_s ;  2 (X_pt + X_nbd) | 0 ]      (DGxy :108-111, DG_combine :320-353)
-        const IMatrix Wu = DW(unstable, n), Ws = DW(stable, n);
-        IMatrix DG(D, IVector(D, interval(0.0)));
-        for (int i = 0; i < D; i++) for (int j = 0; j < n; j++) {
-            interval a(0.0), b(0.0);
-            for (int k = 0; k < D; k++) { a = ia::add(a, ia::mul(o[2].deriv_A[i][k], Wu[k][j])); b = ia::add(b, ia::mul(o[3].deriv_A[i][k], Ws[k][j])); }
-            DG[i][j] = a; DG[i][n + j] = ia::neg(b);
+        std::vector<FlowSet> sets; std::vector<double> times;
+        for (const StepIn& q : in) {
+            IVector X_pt(q.XY_pt.begin(), q.XY_pt.begin() + n), Y_pt(q.XY_pt.begin() + n, q.XY_pt.end());
+            IVector X_nbd(q.XY_nbd.begin(), q.XY_nbd.begin() + n), Y_nbd(q.XY_nbd.begin() + n, q.XY_nbd.end());
+            FlowSet f[4] = {getPointNbd(q.unstable, X_pt, zero), getPointNbd(q.stable, Y_pt, zero), getPointNbd(q.unstable, X_pt, X_nbd), getPointNbd(q.stable, Y_pt, Y_nbd)};
+            for (FlowSet& g : f) { g.params = q.params; sets.push_back(g); times.push_back(q.T); }
         }
-        for (int j = 0; j < D; j++) DG[D - 1][j] = j < n ? ia::mul(interval(2.0), ia::add(X_pt[j], X_nbd[j])) : interval(0.0);
-        // fixed approximate inverse of mid(DG) (the reference: midMatrix(krawczykInverse(midMatrix(DG))) -- any approximation is valid)
-        std::vector<std::vector<double>> M(D, std::vector<double>(2 * D, 0.0));
-        for (int i = 0; i < D; i++) { for (int j = 0; j < D; j++) M[i][j] = 0.5 * (DG[i][j].lo + DG[i][j].hi); M[i][D + i] = 1.0; }
-        for (int c = 0; c < D; c++) {
-            int piv = c; for (int r = c + 1; r < D; r++) if (std::fabs(M[r][c]) > std::fabs(M[piv][c])) piv = r;
-            std::swap(M[c], M[piv]);
-            const double dv = M[c][c]; if (dv == 0.0) throw std::runtime_error("ccp: singular DG midpoint");
-            for (int j = 0; j < 2 * D; j++) M[c][j] /= dv;
-            for (int r = 0; r < D; r++) if (r != c) { const double f = M[r][c]; for (int j = 0; j < 2 * D; j++) M[r][j] -= f * M[c][j]; }
-        }
-        // new_Nbd = -C G + (I - C DG) XY_nbd
-        IVector new_Nbd(D), kraw(D);
-        for (int i = 0; i < D; i++) {
-            interval a(0.0);
-            for (int k = 0; k < D; k++) a = ia::sub(a, ia::mul(interval(M[i][D + k]), G[k]));
-            for (int j = 0; j < D; j++) {
-                interval e(i == j ? 1.0 : 0.0);
-                for (int k = 0; k < D; k++) e = ia::sub(e, ia::mul(interval(M[i][D + k]), DG[k][j]));
-                a = ia::add(a, ia::mul(e, XY_nbd[j]));
+        const std::vector<Out> all = run(sets, times);
+        std::vector<StepOut> res(in.size());
+        for (size_t f = 0; f < in.size(); f++) {
+            const StepIn& q = in[f];
+            const Out* o = &all[4 * f];
+            res[f].success = false; res[f].kraw_image.assign(D, interval(0.0));
+            bool okflow = true; for (int k = 0; k < 4; k++) okflow = okflow && o[k].status == CCP_OK;
+            if (!okflow) continue;                                   // like a CAPD exception inside one parameter value: this front fails, the sweep goes on
+            IVector X_pt(q.XY_pt.begin(), q.XY_pt.begin() + n), X_nbd(q.XY_nbd.begin(), q.XY_nbd.begin() + n);
+            const IVector& G_x = o[0].image; const IVector& G_y = o[1].image;
+            IVector G(D);
+            for (int i = 0; i < D; i++) G[i] = ia::sub(G_x[i], G_y[i]);
+            interval x_radius_sqr(0.0);
+            for (int i = 0; i < n; i++) x_radius_sqr = ia::add(x_radius_sqr, ia::sqr(X_pt[i]));
+            G[D - 1] = ia::sub(x_radius_sqr, q.r_u_sqr);
+            // DG = [ DPhi_T A_u DW_u | -DPhi_{-T} A_s DW_s ;  2 (X_pt + X_nbd) | 0 ]      (DGxy :108-111, DG_combine :320-353)
+            const IMatrix Wu = DW(q.unstable, n), Ws = DW(q.stable, n);
+            IMatrix DG(D, IVector(D, interval(0.0)));
+            for (int i = 0; i < D; i++) for (int j = 0; j < n; j++) {
+                interval a(0.0), b(0.0);
+                for (int k = 0; k < D; k++) { a = ia::add(a, ia::mul(o[2].deriv_A[i][k], Wu[k][j])); b = ia::add(b, ia::mul(o[3].deriv_A[i][k], Ws[k][j])); }
+                DG[i][j] = a; DG[i][n + j] = ia::neg(b);
             }
-            new_Nbd[i] = a; kraw[i] = ia::add(XY_pt[i], a);
+            for (int j = 0; j < D; j++) DG[D - 1][j] = j < n ? ia::mul(interval(2.0), ia::add(X_pt[j], X_nbd[j])) : interval(0.0);
+            // fixed approximate inverse of mid(DG) (the reference: midMatrix(krawczykInverse(midMatrix(DG))) -- any approximation is valid)
+            std::vector<std::vector<double>> M(D, std::vector<double>(2 * D, 0.0));
+            for (int i = 0; i < D; i++) { for (int j = 0; j < D; j++) M[i][j] = 0.5 * (DG[i][j].lo + DG[i][j].hi); M[i][D + i] = 1.0; }
+            bool singular = false;
+            for (int c = 0; c < D && !singular; c++) {
+                int piv = c; for (int r = c + 1; r < D; r++) if (std::fabs(M[r][c]) > std::fabs(M[piv][c])) piv = r;
+                std::swap(M[c], M[piv]);
+                const double dv = M[c][c]; if (dv == 0.0 || !std::isfinite(dv)) { singular = true; break; }
+                for (int j = 0; j < 2 * D; j++) M[c][j] /= dv;
+                for (int r = 0; r < D; r++) if (r != c) { const double fct = M[r][c]; for (int j = 0; j < 2 * D; j++) M[r][j] -= fct * M[c][j]; }
+            }
+            if (singular) continue;
+            // new_Nbd = -C G + (I - C DG) XY_nbd
+            IVector new_Nbd(D);
+            for (int i = 0; i < D; i++) {
+                interval a(0.0);
+                for (int k = 0; k < D; k++) a = ia::sub(a, ia::mul(interval(M[i][D + k]), G[k]));
+                for (int j = 0; j < D; j++) {
+                    interval e(i == j ? 1.0 : 0.0);
+                    for (int k = 0; k < D; k++) e = ia::sub(e, ia::mul(interval(M[i][D + k]), DG[k][j]));
+                    a = ia::add(a, ia::mul(e, q.XY_nbd[j]));
+                }
+                new_Nbd[i] = a; res[f].kraw_image[i] = ia::add(q.XY_pt[i], a);
+            }
+            // same energy level: the discarded velocity component must have a definite sign (:303-313); then proper containment
+            const interval gy = G_y[D - 1];
+            bool ok = gy.lo > 0 || gy.hi < 0;
+            for (int i = 0; i < D && ok; i++) ok = q.XY_nbd[i].lo < new_Nbd[i].lo && new_Nbd[i].hi < q.XY_nbd[i].hi;     // subsetInterior
+            res[f].success = ok;
         }
-        // same energy level: the discarded velocity component must have a definite sign (:303-313); then proper containment
-        const interval gy = G_y[D - 1];
-        bool ok = gy.lo > 0 || gy.hi < 0;
-        for (int i = 0; i < D && ok; i++) ok = XY_nbd[i].lo < new_Nbd[i].lo && new_Nbd[i].hi < XY_nbd[i].hi;     // subsetInterior
-        SUCCESS = ok;
-        return kraw;
+        return res;
+    }
+    // the reference's single-front signature
+    IVector NewtonStep(const Manifold& unstable, const Manifold& stable, const IVector& XY_pt, const IVector& XY_nbd, double T, interval r_u_sqr) {
+        std::vector<StepOut> r = NewtonStepBatch({StepIn{unstable, stable, XY_pt, XY_nbd, T, r_u_sqr, IVector()}});
+        SUCCESS = r[0].success;
+        return r[0].kraw_image;
     }
     bool checkProof() const { return SUCCESS; }          // boundaryValueProblem::checkProof
 

@@ -28,3 +28,19 @@ def test_shim_runs_frameDet_on_gpu(pkg):
     r = subprocess.run([EXE], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "frameDet = 2" in r.stdout and "Gxy round trip ok" in r.stdout and "boundDFU ok" in r.stdout and "checkProof = 1" in r.stdout
+
+
+SWEEP = os.path.join(ROOT, "tests", "cpp", "bvp_sweep")
+
+
+@pytest.mark.gpu
+def test_bvp_sweep_validates_reference_sweep_on_gpu(pkg):
+    """Boundary-value stage for the reference's own 96-point sweep: every batched Krawczyk step is one launch
+    of 4 x 96 validated integrations; all 96 connecting orbits must be verified (heteroclinic.cpp:186-281 loop)."""
+    cmd = ["g++", "-std=c++17", "-O1", "-o", SWEEP, os.path.join(ROOT, "tests", "cpp", "bvp_sweep.cpp"),
+           "-L", pkg.PKG_DIR, "-lccp_b200", "-Wl,-rpath," + pkg.PKG_DIR]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([SWEEP, "24", "4"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "96 connecting orbits verified" in r.stdout
