@@ -213,6 +213,51 @@ class boundaryValueProblem {
     }
     bool checkProof() const { return SUCCESS; }          // boundaryValueProblem::checkProof
 
+    // boundaryValueProblem::FindTime (boundaryValueProblem.cpp:118-214): for fixed points x, y on the two manifolds, 10 Newton steps
+    // on T for F(T) = <Gx - Gy, f(Gx) + f(Gy)> = d/dT |Phi_T(x) - Phi_{-T}(y)|^2 / 2; like the reference only midpoints enter the
+    // update, so f and Df are evaluated in doubles at the midpoints of the validated images (two integrations per step, one launch).
+    double FindTime(const Manifold& unstable, const Manifold& stable, const IVector& XY_pt, double T) {
+        const int n = n_, D = 2 * n;
+        const double T_original = T;
+        IVector X_pt(XY_pt.begin(), XY_pt.begin() + n), Y_pt(XY_pt.begin() + n, XY_pt.end());
+        const IVector zero(n, interval(0.0));
+        auto mid = [](const interval& a) { return 0.5 * (a.lo + a.hi); };
+        std::vector<double> b(n), c(n, 0.0);
+        for (int i = 0; i < n; i++) b[i] = mid(params_[i]);
+        for (int i = 0; i < n - 1; i++) c[i] = mid(params_[n + i]);
+        auto field = [&](const std::vector<double>& z, std::vector<double>& f, std::vector<std::vector<double>>& Df) {
+            f.assign(D, 0.0); Df.assign(D, std::vector<double>(D, 0.0));
+            std::vector<double> g(n), w(n);
+            for (int i = 0; i < n; i++) { g[i] = z[i] * (1.0 - z[i]); w[i] = z[i] - 0.5; f[i] = z[n + i]; Df[i][n + i] = 1.0; }
+            for (int i = 0; i < n; i++) {
+                double F = -b[i] * g[i] * w[i], Mii = -b[i] * (3.0 * g[i] - 0.5);
+                if (i > 0)     { F -= c[i - 1] * g[i - 1] * w[i]; Mii -= c[i - 1] * g[i - 1]; Df[n + i][i - 1] = 2.0 * c[i - 1] * w[i] * w[i - 1]; }
+                if (i < n - 1) { F -= c[i] * g[i + 1] * w[i];     Mii -= c[i] * g[i + 1];     Df[n + i][i + 1] = 2.0 * c[i] * w[i] * w[i + 1]; }
+                f[n + i] = F; Df[n + i][i] = Mii;
+            }
+        };
+        double original_dist = 0, dist0 = 0;
+        for (int it = 0; it < 10; it++) {
+            std::vector<Out> o = run({getPointNbd(unstable, X_pt, zero), getPointNbd(stable, Y_pt, zero)}, {T, T});
+            if (o[0].status != CCP_OK || o[1].status != CCP_OK) return T_original;
+            std::vector<double> gx(D), gy(D), fx, fy; std::vector<std::vector<double>> Dx, Dy;
+            for (int i = 0; i < D; i++) { gx[i] = mid(o[0].image[i]); gy[i] = mid(o[1].image[i]); }
+            field(gx, fx, Dx); field(gy, fy, Dy);
+            dist0 = 0; double d1 = 0, d2 = 0;
+            for (int i = 0; i < D; i++) {
+                // the y-trajectory runs backwards: d/dT Phi_{-T}(y) = -f, d^2/dT^2 = +Df f
+                const double dv = gx[i] - gy[i], dd1 = fx[i] + fy[i];
+                double ax = 0, ay = 0; for (int k = 0; k < D; k++) { ax += Dx[i][k] * fx[k]; ay += Dy[i][k] * fy[k]; }
+                const double dd2 = ax - ay;
+                dist0 += dv * dv; d1 += dv * dd1; d2 += dd1 * dd1 + dv * dd2;
+            }
+            if (it == 0) original_dist = dist0;
+            if (d2 == 0.0 || !std::isfinite(d1 / d2)) break;
+            T = T - d1 / d2;
+        }
+        return original_dist < dist0 ? T_original : T;
+    }
+
   private:
     int n_; IVector params_; int order_, step_;
 };

@@ -59,6 +59,12 @@ int main() {
         r_u_sqr = interval(r_u_sqr.lo);
         const double T = info.T;
         auto midv = [](const IVector& v) { IVector m(v.size()); for (size_t i = 0; i < v.size(); i++) m[i] = interval(0.5 * (v[i].lo + v[i].hi)); return m; };
+        // FindTime (boundaryValueProblem.cpp:118-214): from a perturbed time back to the minimiser of |Phi_T(x) - Phi_{-T}(y)|
+        {
+            const double Tf = BVP.FindTime(Mu, Ms, XY_pt, T + 0.02);
+            std::printf("FindTime: %.6f -> %.6f (shooting time %.6f)\n", T + 0.02, Tf, T);
+            if (!(std::fabs(Tf - T) < 1e-4)) return 11;
+        }
         for (int it = 0; it < 6; it++) XY_pt = midv(BVP.NewtonStep(Mu, Ms, XY_pt, XY_nbd, T, r_u_sqr));
         for (int i = 0; i < 6; i++) XY_nbd[i] = interval(-1e-12, 1e-12);            // scale * initial_box
         for (int it = 0; it < 8; it++) {

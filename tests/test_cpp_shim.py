@@ -27,7 +27,7 @@ def test_shim_runs_frameDet_on_gpu(pkg):
     _build(pkg)
     r = subprocess.run([EXE], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "frameDet = 2" in r.stdout and "Gxy round trip ok" in r.stdout and "boundDFU ok" in r.stdout and "checkProof = 1" in r.stdout
+    assert "frameDet = 2" in r.stdout and "Gxy round trip ok" in r.stdout and "boundDFU ok" in r.stdout and "checkProof = 1" in r.stdout and "FindTime:" in r.stdout
 
 
 SWEEP = os.path.join(ROOT, "tests", "cpp", "bvp_sweep")
