@@ -132,7 +132,7 @@ def flow_desc(n, params, p_i, A_i, Uxy, T, stable=False, order=20, step_log2=5):
     interval end points, `A_i`: (2n,2n) point matrix, `params`: b_1..b_n, c_12.. as numbers or (lo,hi) pairs."""
     d = abi.FrontDesc()
     D = 2 * n
-    d.n, d.order, d.step_log2, d.grid, d.L_minus = n, order, step_log2, 1, float(T)
+    d.n, d.order, d.step_log2, d.grid, d.L_minus = n, order, step_log2, 0, float(T)      # grid 0 = flow map only
     pr = [(float(q), float(q)) if np.isscalar(q) else (float(q[0]), float(q[1])) for q in params]
     for i in range(n):
         d.b[i].lo, d.b[i].hi = pr[i]

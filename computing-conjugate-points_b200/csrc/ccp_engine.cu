@@ -318,9 +318,10 @@ int ccp_bound_dfu_batch(const ccp_dfu_desc* descs, size_t n_descs, ccp_dfu_resul
     if (!E.ready) { E.err = "ccp_init has not been called (no CPU fallback)"; return CCP_E_NOT_INIT; }
     if (!descs || !results) { E.err = "null argument"; return CCP_E_ARG; }
     if (n_descs == 0) return 0;
-    void* d_in = nullptr; void* d_out = nullptr;
-    CK(cudaMalloc(&d_in, n_descs * sizeof(ccp_dfu_desc)));
-    CK(cudaMalloc(&d_out, n_descs * sizeof(ccp_dfu_result)));
+    int rc;                                                                                   // the engine's staging buffers are reused
+    if ((rc = ensure(&E.d_desc, &E.desc_cap, n_descs * sizeof(ccp_dfu_desc)))) return rc;
+    if ((rc = ensure(&E.d_res, &E.res_cap, n_descs * sizeof(ccp_dfu_result)))) return rc;
+    void* d_in = E.d_desc; void* d_out = E.d_res;
     CK(cudaMemcpyAsync(d_in, descs, n_descs * sizeof(ccp_dfu_desc), cudaMemcpyHostToDevice, E.stream));
     CK(cudaMemsetAsync(d_out, 0, n_descs * sizeof(ccp_dfu_result), E.stream));               // unused matrix entries (n < CCP_MAX_N) stay zero
     const int grid = (int)(n_descs < (size_t)(8 * E.sm_count) ? n_descs : (size_t)(8 * E.sm_count));
@@ -339,7 +340,6 @@ int ccp_bound_dfu_batch(const ccp_dfu_desc* descs, size_t n_descs, ccp_dfu_resul
     CK(cudaStreamSynchronize(E.stream));
     CK(cudaEventElapsedTime(&E.last_ms, E.ev0, E.ev1));
     for (size_t i = 0; i < n_descs; i++) if (descs[i].n < 2 || descs[i].n > CCP_MAX_N) { std::memset(&results[i], 0, sizeof(ccp_dfu_result)); results[i].status = CCP_ST_BAD_DESC; }
-    cudaFree(d_in); cudaFree(d_out);
     return 0;
 }
 

@@ -557,7 +557,7 @@ __device__ __forceinline__ ival frame_entry(const FrontSmem<N>& S, int cc, int b
 //      All sums are dense fixed-length dot products in (mid,t) form (missing chain neighbours = zero parameters), so every stage is
 //      one branch-free instruction stream over (direction, entry) items.  Called by all threads of the CTA. ----
 template <int N>
-__device__ __noinline__ void second_variation(FrontSmem<N>& S, PostTab<N>& PT, int cur, double hs, double g5) {
+__device__ __noinline__ void second_variation(FrontSmem<N>& S, PostTab<N>& PT, int cur, double hs, double g5, bool frames) {
     constexpr int D = 2 * N;
     const int tid = threadIdx.x;
     HullM<N>& H = S.hm;
@@ -719,7 +719,7 @@ __device__ __noinline__ void second_variation(FrontSmem<N>& S, PostTab<N>& PT, i
     }
     __syncthreads();
     // truncation box of the centre tables + box for (Psi(tau;phi) - Psi(tau;x)) W on [0,hs]; same for the derivative
-    if (tid < N * N) {
+    if (frames && tid < N * N) {
         const int a = tid / N, bb = tid % N;
         double sm = 0;
 #pragma unroll
@@ -890,7 +890,7 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
     const int p = S.un.desc.order, g = S.un.desc.grid, step_log2 = S.un.desc.step_log2;
     const double L_minus = S.un.desc.L_minus;
     int status = CCP_OK;
-    if (S.un.desc.n != N || p < 2 || p > CCP_MAX_ORDER || g < 1 || g > GMAX || step_log2 < 1 || step_log2 > 20 || !(L_minus > 0) || !isfinite(L_minus))
+    if (S.un.desc.n != N || p < 2 || p > CCP_MAX_ORDER || g < 0 || g > GMAX || step_log2 < 1 || step_log2 > 20 || !(L_minus > 0) || !isfinite(L_minus))
         status = CCP_ST_BAD_DESC;
     if (status != CCP_OK) {
         __syncthreads();
@@ -1265,7 +1265,8 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
         PROF(2);
         TRC(4);
         // ---- frame tables F_k = Psi^u_k * Ws (the box for truncation and for Psi(phi) - Psi(x) is added to F_0 below) ----
-        for (int t = tid; t < (p + 1) * N * N; t += NT) {
+        //      grid == 0: flow map only (boundaryValueProblem::Gxy / DGxy; include/ccp.h flow_P): no frame tables, no grid loop
+        if (g > 0) for (int t = tid; t < (p + 1) * N * N; t += NT) {
             const int k = t / (N * N), a = (t / N) % N, bb = t % N;
             acc4 ac = acc_zero();
 #pragma unroll
@@ -1275,14 +1276,14 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
         // ---- first / last frame data (topFrame::getFirstFrame / getLastFrame): rare ----
         if (s == 0) {
             for (int t = tid; t < D * N; t += NT) { const int rr = t / N, k = t % N; gres->first_frame[rr * (CCP_MAX_N + 1) + k] = toc(S.Ws[rr][k]); }
-            if (tid < N) {
+            if (tid < N && g > 0) {
                 const double t1 = (1 < g) ? __ddiv_rd(__dmul_rd(1.0, hs), (double)g) : hs;
                 ival du, dv; phi_prime<N>(S, Tf, tid, p, cur, hs, 0.0, t1, mj, du, dv);
                 gres->first_frame[tid * (CCP_MAX_N + 1) + N] = toc(du);
                 gres->first_frame[(N + tid) * (CCP_MAX_N + 1) + N] = toc(dv);
             }
         }
-        if (last && tid < N) {
+        if (last && tid < N && g > 0) {
             constexpr int ld = CCP_MAX_N + 2;
             const double tl = __ddiv_rd(__dmul_rd((double)(g - 1), hs), (double)g);
             ival du, dv; phi_prime<N>(S, Tf, tid, p, cur, hs, tl, hs, mj, du, dv);
@@ -1292,9 +1293,10 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
         __syncthreads();                            // Fk complete; all Taylor tables and un.scratch are dead from here (PT overlays them)
         PROF(3);
         TRC(5);
-        second_variation<N>(S, PT, cur, hs, mj.g5);          // Xi_j, dJ, J = Jc + [0,1] dJ, boxes added to F_0 / boxFd
+        second_variation<N>(S, PT, cur, hs, mj.g5, g > 0);          // Xi_j, dJ, J = Jc + [0,1] dJ, boxes added to F_0 / boxFd
         PROF(11);
         TRC(9);
+        if (g > 0) {                                // grid == 0: flow map only, no grid loop / determinants / decisions
         // ---- grid loop (utils.cpp:219-252).  A lane owns ONE frame entry c and every (32/N^2)-th grid point: each coefficient
         //      Fk[k][c] is loaded once and feeds PPL independent Horner chains (shared-memory loads, not DFMAs, bound this loop).
         //      warp 0: point enclosures F(tau_i), i = 1..g   (F(0) = Fk[0] exactly)       -> EV[i]
@@ -1397,6 +1399,7 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
                 if (s == 0) det_first = DT[g + 1];
                 if (last) det_last = DT[2 * g];
             }
+        }
         }
         PROF(5);
         TRC(7);

@@ -69,7 +69,7 @@ class boundaryValueProblem {
             const FlowSet& s = sets[q];
             ccp_front_desc& e = d[q];
             e = ccp_front_desc{};
-            e.n = n_; e.order = order_; e.step_log2 = step_; e.grid = 1; e.L_minus = T[q];
+            e.n = n_; e.order = order_; e.step_log2 = step_; e.grid = 0; e.L_minus = T[q];     // grid 0 = flow map only
             const IVector& par = s.params.empty() ? params_ : s.params;
             for (int i = 0; i < n_; i++) e.b[i] = to_c(par[i]);
             for (int i = 0; i < n_ - 1; i++) e.c[i] = to_c(par[n_ + i]);

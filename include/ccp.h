@@ -43,7 +43,8 @@ typedef struct {
     int32_t n;            /* number of components; dimension = 2n, coupled system d = 4n                 */
     int32_t order;        /* Taylor order p          (propagateManifold.h:63 `order`)                   */
     int32_t step_log2;    /* fixed step h = 2^-step_log2 (propagateManifold.cpp:92 `step_size`)         */
-    int32_t grid;         /* sub-intervals per step  (frameDet argument `grid`)                          */
+    int32_t grid;         /* sub-intervals per step  (frameDet argument `grid`); 0 = flow map only
+                             (Gxy / DGxy: no frame tables, grid loop, determinants; flow_P and last_frame only) */
     double  L_minus;      /* integration time L_- as an exact double (heteroclinic.cpp:324)             */
     double  reserved;     /* keeps sizeof(ccp_front_desc) a multiple of 16 (coalesced 16-byte staging)  */
     ccp_interval b[CCP_MAX_N];        /* b_1..b_n  (n=2: a,b)  ODE_functions.cpp:257-273                */

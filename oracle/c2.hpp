@@ -164,7 +164,7 @@ static inline void run_front(const ccp_front_desc& d, ccp_front_result& res, std
     std::memset(&res, 0, sizeof(res));
     res.first_failure = -1;
     const int n = d.n, D = 2 * n, p = d.order, g = d.grid;
-    if (n < 2 || n > MAXN || p < 2 || p > MAXP || g < 1 || g > MAXG || d.step_log2 < 1 || d.step_log2 > 20 || !(d.L_minus > 0) || !std::isfinite(d.L_minus)) {
+    if (n < 2 || n > MAXN || p < 2 || p > MAXP || g < 0 || g > MAXG || d.step_log2 < 1 || d.step_log2 > 20 || !(d.L_minus > 0) || !std::isfinite(d.L_minus)) {
         res.status = CCP_ST_BAD_DESC; return;
     }
     const double h = std::ldexp(1.0, -d.step_log2);
@@ -307,14 +307,15 @@ static inline void run_front(const ccp_front_desc& d, ccp_front_result& res, std
                 boxF[a][bb] = s0; boxFd[a][bb] = s1;
             }
         }
-        for (int k = 0; k <= p; k++) for (int a = 0; a < n; a++) for (int bb = 0; bb < n; bb++) {
+        // grid == 0: flow map only (boundaryValueProblem::Gxy / DGxy, include/ccp.h flow_P) -- no frame tables, no grid loop
+        if (g > 0) for (int k = 0; k <= p; k++) for (int a = 0; a < n; a++) for (int bb = 0; bb < n; bb++) {
             acc4 ac; for (int cc = 0; cc < D; cc++) acc_term(ac, ps.Pu[a][cc][k], Wm[cc][bb]);
             ival f = acc_finish(ac);
             if (k == 0) f = f + sym(boxF[a][bb]);
             Fk[k][a][bb] = f;
         }
         // ---- grid loop + topFrame (as c1) ----
-        double gp[MAXG + 1]; grid_points(hs, g, gp);
+        double gp[MAXG + 1]; grid_points(hs, g, gp); if (g == 0) gp[1] = hs;
         Frame FL, FR, FV, FD;
         for (int i = 0; i < g; i++) {
             const double tl = gp[i], th = gp[i + 1];
@@ -385,13 +386,13 @@ static inline void run_front(const ccp_front_desc& d, ccp_front_result& res, std
         };
         if (s == 0) {     // topFrame::getFirstFrame (topFrame.cpp:301-331)
             for (int rr = 0; rr < D; rr++) for (int k = 0; k < n; k++) res.first_frame[rr * (CCP_MAX_N + 1) + k] = toc(Ws[rr][k]);
-            ival du[MAXN], dv[MAXN]; phi_prime(gp[0], gp[1], du, dv);
-            for (int i = 0; i < n; i++) {
+            ival du[MAXN], dv[MAXN]; if (g > 0) phi_prime(gp[0], gp[1], du, dv);
+            if (g > 0) for (int i = 0; i < n; i++) {
                 res.first_frame[i * (CCP_MAX_N + 1) + n] = toc(du[i]);
                 res.first_frame[(n + i) * (CCP_MAX_N + 1) + n] = toc(dv[i]);
             }
         }
-        if (last) {
+        if (last && g > 0) {
             const int ld = CCP_MAX_N + 2;
             ival du[MAXN], dv[MAXN]; phi_prime(gp[g - 1], gp[g], du, dv);
             for (int i = 0; i < n; i++) {
