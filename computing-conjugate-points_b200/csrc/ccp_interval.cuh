@@ -46,9 +46,12 @@ __device__ __forceinline__ ival imulk(const ival& a, int k) { return mk(__dmul_r
 __device__ __forceinline__ double mid_ru(const ival& a) { return __dadd_ru(0.5 * a.lo, 0.5 * a.hi); }
 
 __device__ __forceinline__ ival mt2iv(const mt& a) { double r = __dadd_ru(a.t, -fabs(a.m)); return mk(__dadd_rd(a.m, -r), __dadd_ru(a.m, r)); }
+// m = RU(lo/2 + hi/2) is never below the exact midpoint (the halvings are exact, or rounded up for subnormals), hence
+// m - lo >= hi - m and r = RU(m - lo) alone bounds both distances: no comparison on the critical chains.  (For normal numbers this is
+// bit-identical to max(RU(hi - m), RU(m - lo)): rounding is monotone.)
 __device__ __forceinline__ mt iv2mt(const ival& a) {
-    mt o; o.m = mid_ru(a);
-    double r = dmax(__dadd_ru(a.hi, -o.m), __dadd_ru(o.m, -a.lo));
+    mt o; o.m = __dadd_ru(__dmul_ru(0.5, a.lo), __dmul_ru(0.5, a.hi));
+    const double r = __dadd_ru(o.m, -a.lo);
     o.t = __dadd_ru(fabs(o.m), r);
     return o;
 }
@@ -67,9 +70,10 @@ __device__ __forceinline__ void acc_term_neg(acc4& a, const mt& x, const mt& y) 
     a.T   = __fma_ru(x.t, y.t, a.T);
     a.Q   = __fma_rd(fabs(x.m), fabs(y.m), a.Q);
 }
+// R = RU(T - Q) >= 0 always: every term of T (round-up chain of t_x t_y) dominates the matching term of Q (round-down chain of
+// |m_x||m_y| <= t_x t_y), so no sign guard is needed; a NaN propagates into both bounds and is caught by the finiteness checks.
 __device__ __forceinline__ ival acc_finish(const acc4& a) {
-    double R = __dadd_ru(a.T, -a.Q);
-    if (!(R >= 0)) R = (R != R) ? R : 0.0;
+    const double R = __dadd_ru(a.T, -a.Q);
     return mk(__dadd_rd(a.slo, -R), __dadd_ru(a.shi, R));
 }
 

@@ -32,9 +32,11 @@ struct mt { double m, t; };
 
 static inline ival mt2iv(const mt& a) { double r = sub_ru(a.t, std::fabs(a.m)); return ival(sub_rd(a.m, r), add_ru(a.m, r)); }
 static inline double mid_ru(const ival& a) { return add_ru(0.5 * a.lo, 0.5 * a.hi); }
+// m = RU(lo/2 + hi/2) is never below the exact midpoint, hence m - lo >= hi - m and r = RU(m - lo) bounds both distances
+// (bit-identical to max(RU(hi - m), RU(m - lo)) for normal numbers; see csrc/ccp_interval.cuh)
 static inline mt iv2mt(const ival& a) {
-    mt o; o.m = mid_ru(a);
-    double r = std::max(sub_ru(a.hi, o.m), sub_ru(o.m, a.lo));
+    mt o; o.m = add_ru(mul_ru(0.5, a.lo), mul_ru(0.5, a.hi));
+    const double r = sub_ru(o.m, a.lo);
     o.t = add_ru(std::fabs(o.m), r);
     return o;
 }
@@ -45,9 +47,9 @@ static inline void acc_term(acc4& a, const mt& x, const mt& y) {
     a.T   = fma_ru(x.t, y.t, a.T);
     a.Q   = fma_rd(std::fabs(x.m), std::fabs(y.m), a.Q);
 }
+// R = RU(T - Q) >= 0 always (termwise t_x t_y >= |m_x||m_y|, T rounded up, Q rounded down): no sign guard needed
 static inline ival acc_finish(const acc4& a) {
-    double R = sub_ru(a.T, a.Q);
-    if (!(R >= 0)) R = (R != R) ? R : 0.0;
+    const double R = sub_ru(a.T, a.Q);
     return ival(sub_rd(a.slo, R), add_ru(a.shi, R));
 }
 // Summation order of every Cauchy product sum_j x[j] y[k-j]:  interior terms j = 1..k-1 ascending, then the two end
