@@ -112,7 +112,6 @@ struct FrontSmem {
     double invlo[KMAX + 2], invhi[KMAX + 2]; // [rd(1/k), ru(1/k)]
     double gp[GMAX + 1];                     // grid points of the current step (utils.cpp:219-223)
     ival dtime[GMAX];
-    SPar par[3 * N];                         // unified: b_i | c_e | zero | -c_e   (indices N+e, 2N-1, 2N+e) for the branch-free combines
     int dec[GMAX];
     int flag;
     Majorant mj;
@@ -938,13 +937,6 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
             S.pm.PN[i][l][sl] = v;
         }
     }
-    if (tid < 3 * N - 1) {
-        SPar q; q.pl = 0; q.ph = 0; q.neg = 0; q.straddle = 0;                       // index 2N-1: zero parameter
-        if (tid < N) q = make_spar(S.bpar[tid]);
-        else if (tid < 2 * N - 1) q = make_spar(S.cpar[tid - N]);
-        else if (tid >= 2 * N) { q = make_spar(S.cpar[tid - 2 * N]); q.neg = q.neg ? 0 : 1; }   // -c_e
-        S.par[tid] = q;
-    }
     __syncthreads();
     Majorant mj = S.mj; mj.g1 = S.g15[0]; mj.g5 = S.g15[1];
     if (!mj.ok) status = CCP_ST_ENCLOSURE;
@@ -962,17 +954,15 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
     const TaskR tC = make_taskr(decode_task<N>(2, pi2)), tD = make_taskr(decode_task<N>(2, pi3));
     const mt* const Tf = &T[0][0];
     // ---- per-lane operands of the three "combine" stages, fixed for the whole front.  Every stage is ONE branch-free
-    //      instruction stream: out = -(P0*X0) - P1*X1 - P2*X2 (missing neighbours: zero parameter / zero slot).
-    //        phi warp, lanes MB..       : Md_i[k]:  X0 = 3 g_i - [k==0]/2, X1 = g_{i-1}, X2 = g_{i+1};  Mo_e[k]:  X0 = 2 q_e, P0 = -c_e;
-    //                                     H_i[k]:  X0 = g_i  (v' = H w)          -- g, q of the newest order come from the A lanes (scratch)
+    //      instruction stream (missing neighbours: zero parameter, clamped slot).
+    //        phi warp, lanes MB..       : one (mid,t) dot product of three parameter * series slots (parameter tables S.pm, g / q of the
+    //                                     newest order from the A lanes through scratch):  Md_i[k] = [k==0] b_i/2 - (3 b_i g_i + c g_{i-1} + c g_{i+1}),
+    //                                     Mo_e[k] = 2 c_e q_e,  H_i[k] = -(b_i g_i + c g_{i-1} + c g_{i+1})   (v' = H w)
     //        Psi warp, lanes < N*D      : Pv[k] = (X0 + X1 + X2)/k from the C sums (scratch); Pu[k] = Pv[k-1]/k
     //      The B lanes of the phi warp turn their own Cauchy sum (H w)[k] into v[k+1], u[k+2], z[k+2] (store_vuz).
     constexpr int ZSLOT = L::NB + L::NC;
     constexpr int GS = ZSLOT + 1;                    // scratch slots of g_i (N) and q_e (N-1) of the newest order
     static_assert(sizeof(S.un) >= (GS + 2 * N - 1) * sizeof(ival), "scratch slots");
-    bool anystr = false;
-    for (int i = 0; i < 2 * N - 1; i++) anystr = anystr || S.par[i].straddle;
-    // parameters by index into S.par (2N-1 = zero)
     constexpr int PZ = 2 * N - 1;
     int cs0 = ZSLOT, cs1 = ZSLOT, cs2 = ZSLOT, rowV = 0, rowU = 0, rowZ = 0;
     int ap0 = PZ, ap1 = PZ, ap2 = PZ, mscale = 1, gslot = -1;
@@ -985,15 +975,16 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
         if (lane >= L::NA && lane < MB) {                    // B lane: v, u, z rows of component i
             const int i = lane - L::NA;
             rowV = L::V(i) * KMAX; rowU = L::U(i) * KMAX; rowZ = L::Z(i) * KMAX;
-        } else if (mrole >= 0 && (mrole < N || mrole >= 2 * N - 1)) {   // Md_i (3 g_i - [k = 0]/2) and H_i (g_i): -(b_i X0) - c_{i-1} g_{i-1} - c_i g_{i+1}
+        } else if (mrole >= 0 && (mrole < N || mrole >= 2 * N - 1)) {   // Md_i = [k = 0] b_i/2 - (3 b_i g_i + c_{i-1} g_{i-1} + c_i g_{i+1}),  H_i = -(b_i g_i + c_{i-1} g_{i-1} + c_i g_{i+1})
             const bool isH = mrole >= 2 * N - 1;
             const int i = isH ? mrole - (2 * N - 1) : mrole;
-            cs0 = GS + i; ap0 = i; mscale = isH ? 1 : 3; mcst = isH ? 0.0 : 0.5; rowV = (isH ? L::G(i) : L::MD(i)) * KMAX;
-            if (i > 0)     { cs1 = GS + i - 1; ap1 = N + i - 1; }
-            if (i < N - 1) { cs2 = GS + i + 1; ap2 = N + i; }
-        } else if (mrole >= N) {                             // Mo_e = c_e * 2 q_e  (P0 = -c_e)
+            cs0 = GS + i; cs1 = GS + (i > 0 ? i - 1 : 0); cs2 = GS + (i < N - 1 ? i + 1 : N - 1);       // clamped: missing neighbours carry zero parameters
+            ap0 = (isH ? 0 : N) + i; ap1 = 3 * N + i; ap2 = 4 * N + i;                                    // B or B3 | Cm | Cp in S.pm
+            mscale = 1; mcst = isH ? 0.0 : 1.0; rowV = (isH ? L::G(i) : L::MD(i)) * KMAX;                // mscale: negate;  mcst: add b_i/2 at order 0
+        } else if (mrole >= N) {                             // Mo_e = 2 c_e q_e
             const int e = mrole - N;
-            cs0 = GS + N + e; ap0 = 2 * N + e; mscale = 2; rowV = L::MO(e) * KMAX;
+            cs0 = cs1 = cs2 = GS + N + e; ap0 = 7 * N + e; ap1 = ap2 = 3 * N;                             // C2 | zero (Cm[0]) | zero
+            mscale = 0; rowV = L::MO(e) * KMAX;
         }
         if (lane < L::NA) gslot = GS + lane;                 // A lanes: g (task i) and q (task N+e)
     } else if (lane < N * D) {
@@ -1074,27 +1065,17 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
         if (wq == 0) {
             if (tA.kind() == 0) {
                 acc4 s0, s1; run_block(Tf, tA, 0, s0, s1);
-                S.un.scratch[gslot] = mt2iv(iv2mt(acc_finish(s0)));
+                reinterpret_cast<mt*>(S.un.scratch)[gslot] = iv2mt(acc_finish(s0));
             }
             __syncwarp();
             if (mrole >= 0) {
-                ival x0 = imulk(S.un.scratch[cs0], mscale);
-                x0 = isub(x0, pt(mcst));
-                const ival x1 = S.un.scratch[cs1], x2 = S.un.scratch[cs2];
-                ival dd;
-                if (!anystr) {
-                    const SPar q0 = S.par[ap0], q1 = S.par[ap1], q2 = S.par[ap2];
-                    dd = ineg(imul_pos3(x0, q0.pl, q0.ph, q0.neg));
-                    dd = isub(dd, imul_pos3(x1, q1.pl, q1.ph, q1.neg));
-                    dd = isub(dd, imul_pos3(x2, q2.pl, q2.ph, q2.neg));
-                } else if (mrole < N || mrole >= 2 * N - 1) {
-                    const int i = mrole < N ? mrole : mrole - (2 * N - 1);
-                    dd = ineg(imul_nl(x0, S.bpar[i]));
-                    if (i > 0)     dd = isub(dd, imul_nl(x1, S.cpar[i - 1]));
-                    if (i < N - 1) dd = isub(dd, imul_nl(x2, S.cpar[i]));
-                } else {
-                    dd = imul_nl(x0, S.cpar[mrole - N]);
-                }
+                const mt* const gq = reinterpret_cast<const mt*>(S.un.scratch);
+                const mt* const pmt = &S.pm.B[0];                       // B | B3 | B6 | Cm | Cp | C2m | C2p | C2, N entries each
+                acc4 ac = acc_zero();
+                acc_term(ac, pmt[ap0], gq[cs0]); acc_term(ac, pmt[ap1], gq[cs1]); acc_term(ac, pmt[ap2], gq[cs2]);
+                ival dd = acc_finish(ac);
+                if (mscale) dd = ineg(dd);
+                if (mcst != 0.0) dd = iadd(S.pm.halfB[mrole], dd);      // Md_i[0] = b_i/2 - (...)
                 T[0][rowV] = iv2mt(dd);
             }
         }
@@ -1102,22 +1083,12 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
         // phi warp, M/H lanes: g, q of order kc+1 (scratch) -> Md, Mo, H of order kc+1
         auto combine_phi = [&](int kc) {
             if (mrole >= 0 && kc + 1 <= p - 1) {
-                const ival s0 = imulk(S.un.scratch[cs0], mscale), s1 = S.un.scratch[cs1], s2 = S.un.scratch[cs2];
-                ival f;
-                if (!anystr) {
-                    const SPar q0 = S.par[ap0], q1 = S.par[ap1], q2 = S.par[ap2];
-                    f = ineg(imul_pos3(s0, q0.pl, q0.ph, q0.neg));
-                    f = isub(f, imul_pos3(s1, q1.pl, q1.ph, q1.neg));
-                    f = isub(f, imul_pos3(s2, q2.pl, q2.ph, q2.neg));
-                } else if (mrole < N || mrole >= 2 * N - 1) {     // a parameter interval straddles zero: general products
-                    const int i = mrole < N ? mrole : mrole - (2 * N - 1);
-                    f = ineg(imul_nl(s0, S.bpar[i]));
-                    if (i > 0)     f = isub(f, imul_nl(s1, S.cpar[i - 1]));
-                    if (i < N - 1) f = isub(f, imul_nl(s2, S.cpar[i]));
-                } else {
-                    f = imul_nl(s0, S.cpar[mrole - N]);
-                }
-                T[0][rowV + kc + 1] = iv2mt(f);
+                const mt* const gq = reinterpret_cast<const mt*>(S.un.scratch);
+                const mt* const pmt = &S.pm.B[0];
+                acc4 ac = acc_zero();                                   // one (mid,t) dot product: parameter * g (or q), three slots
+                acc_term(ac, pmt[ap0], gq[cs0]); acc_term(ac, pmt[ap1], gq[cs1]); acc_term(ac, pmt[ap2], gq[cs2]);
+                const ival f = acc_finish(ac);
+                T[0][rowV + kc + 1] = iv2mt(mscale ? ineg(f) : f);
             }
         };
         // phi warp, B lanes: the Cauchy sum (H w)[kc] is v'[kc]:  v[kc+1] = sum/(kc+1), u[kc+2] = v[kc+1]/(kc+2), z = -u  (no scratch round trip)
@@ -1164,7 +1135,7 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
                 if (act0) {
                     run_block(Tf, tA, kk, s0, s1);
                     const ival sum = acc_finish(s0);
-                    if (isA) S.un.scratch[gslot] = mt2iv(iv2mt(sum));      // g, q only travel to the M/H lanes
+                    if (isA) reinterpret_cast<mt*>(S.un.scratch)[gslot] = iv2mt(sum);      // g, q only travel to the M/H lanes
                     else store_vuz(kk, sum);
                 }
                 __syncwarp();
@@ -1177,7 +1148,7 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
                     if (act1) {
                         run_ends(Tf, tA, kk + 1, s1);
                         const ival sum = acc_finish(s1);
-                        if (isA) S.un.scratch[gslot] = mt2iv(iv2mt(sum));
+                        if (isA) reinterpret_cast<mt*>(S.un.scratch)[gslot] = iv2mt(sum);
                         else store_vuz(kk + 1, sum);
                     }
                     __syncwarp();

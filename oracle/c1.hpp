@@ -151,10 +151,11 @@ static inline void phi_tables(PhiTables& t, int n, int p, const ival* b, const i
             t.q[e][k] = iv2mt(acc_finish(a));
         }
         for (int i = 0; i < n; i++) {                 // H_i[k] = -(b_i g_i + c_{i-1} g_{i-1} + c_i g_{i+1})[k]:  v' = F(u) = H w  (one product per component)
-            ival hh = -(mt2iv(t.g[i][k]) * b[i]);
-            if (i > 0)     hh = hh - mt2iv(t.g[i - 1][k]) * c[i - 1];
-            if (i < n - 1) hh = hh - mt2iv(t.g[i + 1][k]) * c[i];
-            t.h[i][k] = iv2mt(hh);
+            const int im = i > 0 ? i - 1 : 0, ip = i < n - 1 ? i + 1 : n - 1;      // missing neighbours: zero parameter, clamped index
+            const mt z = {0.0, 0.0};
+            acc4 a;                                   // one (mid,t) dot product of parameters and g (the GPU's M/H lanes)
+            acc_term(a, iv2mt(b[i]), t.g[i][k]); acc_term(a, i > 0 ? iv2mt(c[i - 1]) : z, t.g[im][k]); acc_term(a, i < n - 1 ? iv2mt(c[i]) : z, t.g[ip][k]);
+            t.h[i][k] = iv2mt(-acc_finish(a));
         }
         for (int i = 0; i < n; i++) {
             acc4 a;
@@ -177,14 +178,19 @@ static inline void psi_tables(PsiTables& s, const PhiTables& hu, int n, int p, c
         s.Pv[i][cc][0] = iv2mt(ival(cc == n + i ? 1.0 : 0.0));
     }
     for (int k = 0; k < p; k++) {
-        for (int i = 0; i < n; i++) {
-            ival t3 = mulk(mt2iv(hu.g[i][k]), 3);
-            if (k == 0) t3 = t3 - ival(0.5);
-            ival d = -(b[i] * t3);
-            if (i > 0)     d = d - c[i - 1] * mt2iv(hu.g[i - 1][k]);
-            if (i < n - 1) d = d - c[i] * mt2iv(hu.g[i + 1][k]);
+        for (int i = 0; i < n; i++) {                 // Md_i[k] = [k = 0] b_i/2 - (3 b_i g_i + c_{i-1} g_{i-1} + c_i g_{i+1})[k],  Mo_e[k] = 2 c_e q_e[k]
+            const int im = i > 0 ? i - 1 : 0, ip = i < n - 1 ? i + 1 : n - 1;
+            const mt z = {0.0, 0.0};
+            acc4 a;
+            acc_term(a, iv2mt(mulk(b[i], 3)), hu.g[i][k]); acc_term(a, i > 0 ? iv2mt(c[i - 1]) : z, hu.g[im][k]); acc_term(a, i < n - 1 ? iv2mt(c[i]) : z, hu.g[ip][k]);
+            ival d = -acc_finish(a);
+            if (k == 0) d = ival(0.5 * b[i].lo, 0.5 * b[i].hi) + d;
             s.Md[i][k] = iv2mt(d);
-            if (i < n - 1) { ival qe = mt2iv(hu.q[i][k]); s.Mo[i][k] = iv2mt(ival(2.0 * qe.lo, 2.0 * qe.hi) * c[i]); }
+            if (i < n - 1) {
+                acc4 e;
+                acc_term(e, iv2mt(mulk(c[i], 2)), hu.q[i][k]); acc_term(e, z, hu.q[i][k]); acc_term(e, z, hu.q[i][k]);
+                s.Mo[i][k] = iv2mt(acc_finish(e));
+            }
         }
         for (int i = 0; i < n; i++) for (int cc = 0; cc < D; cc++) {
             acc4 a0; cauchy(a0, s.Md[i], s.Pu[i][cc], k);
