@@ -110,6 +110,7 @@ struct FrontSmem {
     mt r0m[D + 1], Errm[N][N];               // (mid,t) forms; r0m[D] = 1 weights the direction "box r"
     double boxFd[N][N];
     double invlo[KMAX + 2], invhi[KMAX + 2]; // [rd(1/k), ru(1/k)]
+    double invs[KMAX + 2];                   // ru(ru(1/k) (1 + 2^-50)): radius factor of the (mid,t) scaling by 1/k (mt_scale)
     double gp[GMAX + 1];                     // grid points of the current step (utils.cpp:219-223)
     ival dtime[GMAX];
     int dec[GMAX];
@@ -275,6 +276,12 @@ __device__ __forceinline__ ival fromc(const ccp_interval& a) { return mk(a.lo, a
 // ---- helpers of the second-variation / set-update phases (oracle/c2.hpp, same expression order) ----
 __device__ __forceinline__ ival ihalf(const ival& a) { return mk(0.5 * a.lo, 0.5 * a.hi); }
 __device__ __forceinline__ ival idivk_tab(const ival& a, const double* ilo, const double* ihi, int k);
+// a / k directly in (mid,t) form (oracle/c1.hpp:scalek): no interval conversion, no sign selects on the critical chain of an order.
+//   m' = RN(m ih),  t' = RU(t ihs + 2^-1000)  >=  |m'| + (t - |m|) ih + |m| (ih - 1/k) + rounding of m'     (ih = RU(1/k), ihs = RU(ih (1 + 2^-50)))
+__device__ __forceinline__ mt mt_scale(const mt& a, double ih, double ihs) {
+    mt o; o.m = a.m * ih; o.t = __fma_ru(a.t, ihs, 0x1p-1000);
+    return o;
+}
 __device__ __forceinline__ mt ptm(double v) { mt o; o.m = v; o.t = fabs(v); return o; }      // iv2mt of a point
 // a += x * p for a point p: one directed FMA per bound (tighter than a rounded product plus a rounded sum)
 __device__ __forceinline__ void ipfma(ival& a, const ival& x, double p) {
@@ -915,7 +922,7 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
         if (tid >= 32 && tid < 32 + D + 1) { const int j = tid - 32; S.r0m[j] = j < D ? iv2mt(fromc(d.Uxy[j])) : ptm(1.0); }
         for (int t = tid; t < N * N; t += NT) { const int j = t / N, k = t % N; S.Errm[j][k] = iv2mt(fromc(d.Eu_err[j * CCP_MAX_N + k])); }
         for (int t = tid; t < N * N; t += NT) { int j = t / N, k = t % N; S.Err[j][k] = fromc(d.Eu_err[j * CCP_MAX_N + k]); }
-        if (tid >= 32 && tid < 32 + KMAX + 2) { const int k = tid - 32; if (k >= 1) { S.invlo[k] = __ddiv_rd(1.0, (double)k); S.invhi[k] = __ddiv_ru(1.0, (double)k); } else { S.invlo[0] = S.invhi[0] = 0.0; } }
+        if (tid >= 32 && tid < 32 + KMAX + 2) { const int k = tid - 32; if (k >= 1) { S.invlo[k] = __ddiv_rd(1.0, (double)k); S.invhi[k] = __ddiv_ru(1.0, (double)k); S.invs[k] = __dmul_ru(__ddiv_ru(1.0, (double)k), 1.0000000000000009); } else { S.invlo[0] = S.invhi[0] = S.invs[0] = 0.0; } }
     }
     for (int t = tid; t < (int)(sizeof(ccp_front_result) / 8); t += NT) reinterpret_cast<double*>(gres)[t] = 0.0;
     __syncthreads();                                // the descriptor (un.desc) is dead from here on
@@ -1040,7 +1047,7 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
             T[L::U(i)][0] = iv2mt(u0); T[L::V(i)][0] = iv2mt(v0);
             T[L::G(i)][KMAX - 1] = iv2mt(isub(u0, pt(0.5)));               // w0
             T[L::Z(i)][0] = iv2mt(isub(pt(1.0), u0));                      // z0
-            const mt u1 = iv2mt(idivk_tab(mt2iv(iv2mt(v0)), S.invlo, S.invhi, 1));   // u[1] = v[0]/1
+            const mt u1 = iv2mt(v0);                                                    // u[1] = v[0]/1
             T[L::U(i)][1] = u1;
             mt z1; z1.m = -u1.m; z1.t = u1.t;
             T[L::Z(i)][1] = z1;
@@ -1093,15 +1100,10 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
         };
         // phi warp, B lanes: the Cauchy sum (H w)[kc] is v'[kc]:  v[kc+1] = sum/(kc+1), u[kc+2] = v[kc+1]/(kc+2), z = -u  (no scratch round trip)
         auto store_vuz = [&](int kc, const ival& f) {
-            const double il = S.invlo[kc + 1], ih = S.invhi[kc + 1];
-            const ival fv = mk(__dmul_rd(f.lo, f.lo >= 0 ? il : ih), __dmul_ru(f.hi, f.hi >= 0 ? ih : il));
-            const mt vn = iv2mt(fv);
+            const mt vn = mt_scale(iv2mt(f), S.invhi[kc + 1], S.invs[kc + 1]);
             T[0][rowV + kc + 1] = vn;
             if (kc + 2 <= p) {
-                const double jl = S.invlo[kc + 2], jh = S.invhi[kc + 2];
-                const ival vi = mt2iv(vn);
-                const ival fu = mk(__dmul_rd(vi.lo, vi.lo >= 0 ? jl : jh), __dmul_ru(vi.hi, vi.hi >= 0 ? jh : jl));
-                const mt un = iv2mt(fu);
+                const mt un = mt_scale(vn, S.invhi[kc + 2], S.invs[kc + 2]);
                 T[0][rowU + kc + 2] = un;
                 mt zn; zn.m = -un.m; zn.t = un.t;
                 T[0][rowZ + kc + 2] = zn;
@@ -1112,13 +1114,9 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
             if (lane < N * D) {
                 const ival s0 = S.un.scratch[cs0], s1 = S.un.scratch[cs1], s2 = S.un.scratch[cs2];
                 const mt pvk = Tf[rowV + kc];
-                const double il = S.invlo[kc + 1], ih = S.invhi[kc + 1];
-                const ival sm = iadd(iadd(s0, s1), s2);
-                const ival fv = mk(__dmul_rd(sm.lo, sm.lo >= 0 ? il : ih), __dmul_ru(sm.hi, sm.hi >= 0 ? ih : il));
-                const ival vi = mt2iv(pvk);
-                const ival fu = mk(__dmul_rd(vi.lo, vi.lo >= 0 ? il : ih), __dmul_ru(vi.hi, vi.hi >= 0 ? ih : il));
-                T[0][rowV + kc + 1] = iv2mt(fv);
-                T[0][rowU + kc + 1] = iv2mt(fu);
+                const double ih = S.invhi[kc + 1], ihs = S.invs[kc + 1];
+                T[0][rowV + kc + 1] = mt_scale(iv2mt(iadd(iadd(s0, s1), s2)), ih, ihs);
+                T[0][rowU + kc + 1] = kc == 0 ? pvk : mt_scale(pvk, ih, ihs);
             }
         };
         for (int k = 0; k < p; k += 2) {

@@ -69,6 +69,16 @@ static inline ival divk(const ival& a, int k) {
     if (!inv) inv = new InvK();       // built under FE_UPWARD by the calling oracle thread
     return ival(mul_rd(a.lo, a.lo >= 0 ? inv->lo[k] : inv->hi[k]), mul_ru(a.hi, a.hi >= 0 ? inv->hi[k] : inv->lo[k]));
 }
+// a / k directly in (mid,t) form, k >= 1: no interval conversion, no sign selects.  With ih = RU(1/k) and ihs = RU(ih (1 + 2^-50)):
+//   m' = RN(m ih),  t' = RU(t ihs + 2^-1000)  >=  |m'| + (t - |m|) ih + |m| (ih - 1/k) + rounding of m'   (2^-1000 covers subnormal products)
+static inline mt scalek(const mt& a, int k) {
+    static thread_local InvK* inv = nullptr;
+    if (!inv) inv = new InvK();
+    mt o;
+    { RoundNearestGuard rn; o.m = a.m * inv->hi[k]; }
+    o.t = fma_ru(a.t, mul_ru(inv->hi[k], 1.0000000000000009), 0x1p-1000);
+    return o;
+}
 static inline ival mulk(const ival& a, int k) { return ival(mul_rd((double)k, a.lo), mul_ru((double)k, a.hi)); }
 
 // Horner steps for tau >= 0
@@ -160,8 +170,8 @@ static inline void phi_tables(PhiTables& t, int n, int p, const ival* b, const i
         for (int i = 0; i < n; i++) {
             acc4 a;
             cauchy_order(k, [&](int j) { acc_term(a, t.h[i][j], k - j == 0 ? t.w0[i] : t.u[i][k - j]); });
-            t.v[i][k + 1] = iv2mt(divk(acc_finish(a), k + 1));
-            t.u[i][k + 1] = iv2mt(divk(mt2iv(t.v[i][k]), k + 1));
+            t.v[i][k + 1] = scalek(iv2mt(acc_finish(a)), k + 1);
+            t.u[i][k + 1] = k == 0 ? t.v[i][0] : scalek(t.v[i][k], k + 1);              // u[1] = v[0] exactly
         }
     }
 }
@@ -197,8 +207,8 @@ static inline void psi_tables(PsiTables& s, const PhiTables& hu, int n, int p, c
             ival sm = acc_finish(a0);                     // each product is enclosed on its own (one GPU lane each), then summed
             if (i > 0)     { acc4 a1; cauchy(a1, s.Mo[i - 1], s.Pu[i - 1][cc], k); sm = sm + acc_finish(a1); }
             if (i < n - 1) { acc4 a2; cauchy(a2, s.Mo[i], s.Pu[i + 1][cc], k); sm = sm + acc_finish(a2); }
-            s.Pv[i][cc][k + 1] = iv2mt(divk(sm, k + 1));
-            s.Pu[i][cc][k + 1] = iv2mt(divk(mt2iv(s.Pv[i][cc][k]), k + 1));
+            s.Pv[i][cc][k + 1] = scalek(iv2mt(sm), k + 1);
+            s.Pu[i][cc][k + 1] = k == 0 ? s.Pv[i][cc][0] : scalek(s.Pv[i][cc][k], k + 1);
         }
     }
 }

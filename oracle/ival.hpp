@@ -25,6 +25,12 @@ struct RoundUpGuard {
     ~RoundUpGuard() { fesetround(old); }
 };
 
+struct RoundNearestGuard {          // for the few round-to-nearest operations of the (mid,t) scalings
+    int old;
+    RoundNearestGuard() : old(fegetround()) { fesetround(FE_TONEAREST); }
+    ~RoundNearestGuard() { fesetround(old); }
+};
+
 // ---- directed primitives (FE_UPWARD assumed) ----
 // `volatile`-free: -frounding-math forbids the re-association that would break these.
 static inline double add_ru(double a, double b) { return a + b; }
