@@ -137,6 +137,9 @@ __global__ void debug_prim_kernel(int op, const double* in, double* out, int n) 
         case 19: { ival r = horner_pt(mk(x[0], x[1]), x[2], mk(x[4], x[5])); o[0] = r.lo; o[1] = r.hi; break; }
         case 20: { ival m[3][3]; for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) { int q = (a * 3 + b) % 7; m[a][b] = mk(dmin(x[q], x[q + 1]), dmax(x[q], x[q + 1])); }
                    ival r = Det<3>::det(m); o[0] = r.lo; o[1] = r.hi; break; }
+        case 21: { const int k = (int)x[2]; const double ih = __ddiv_ru(1.0, (double)k);
+                   mt a; a.m = x[0]; a.t = x[1]; mt r = mt_scale(a, ih, __dmul_ru(ih, 1.0000000000000009)); o[0] = r.m; o[1] = r.t; break; }
+        case 22: { ival a = mk(x[0], x[1]); ipfma(a, mk(x[2], x[3]), x[4]); o[0] = a.lo; o[1] = a.hi; break; }
         default: break;
     }
 }

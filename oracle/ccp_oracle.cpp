@@ -122,6 +122,8 @@ int orc_debug_primitives(int op, const double* in, double* out, size_t n) {
             case 19: { ival r = horner_pt(ival(x[0], x[1]), x[2], ival(x[4], x[5])); o[0] = r.lo; o[1] = r.hi; break; }
             case 20: { Frame m; for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) { int q = (a * 3 + b) % 7; m[a][b] = ival(std::min(x[q], x[q + 1]), std::max(x[q], x[q + 1])); }
                        ival r = detN(m, 3); o[0] = r.lo; o[1] = r.hi; break; }
+            case 21: { mt r = scalek(mt{x[0], x[1]}, (int)x[2]); o[0] = r.m; o[1] = r.t; break; }
+            case 22: { ival a(x[0], x[1]); c2::ipfma(a, ival(x[2], x[3]), x[4]); o[0] = a.lo; o[1] = a.hi; break; }
             default: return -1;
         }
     }

@@ -25,7 +25,7 @@ def _same_bits(a, b):
 
 
 PRIM_KINDS = {0: 'r', 1: 'r', 2: 'r', 3: 'r', 4: 'r', 5: 'r', 6: 'r', 7: 'r', 10: 'ival', 11: 'ival', 12: 'mt', 13: 'mt',
-              14: 'k', 15: 'horner', 16: 'ival', 17: 'ival', 18: 'k', 19: 'horner', 20: 'r'}
+              14: 'k', 15: 'horner', 16: 'ival', 17: 'ival', 18: 'k', 19: 'horner', 20: 'r', 21: 'mtk', 22: 'ival'}
 
 
 def _gen(rng, kind, n):
@@ -34,6 +34,9 @@ def _gen(rng, kind, n):
     for a in pairs:
         lo, hi = np.minimum(x[:, a], x[:, a + 1]), np.maximum(x[:, a], x[:, a + 1])
         x[:, a], x[:, a + 1] = lo, hi
+    if kind == 'mtk':
+        x[:, 1] = np.abs(x[:, 0]) * (1 + np.abs(rng.standard_normal(n)) * 1e-8)
+        x[:, 2] = rng.integers(1, 22, n)
     if kind == 'mt':
         for a in (0, 2, 4, 6):
             x[:, a + 1] = np.abs(x[:, a]) * (1 + np.abs(rng.standard_normal(n)) * 1e-10)

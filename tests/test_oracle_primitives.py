@@ -87,3 +87,40 @@ def test_det_encloses_float_det(pkg, orc):
             d = float(np.linalg.det(M))
             assert out[0] <= d + 1e-9 * abs(d) and d - 1e-9 * abs(d) <= out[1]
             assert out[1] - out[0] < 1e-8 * max(1.0, np.abs(M).max() ** n * n ** n)
+
+
+def test_mt_scale_and_ipfma_enclose_exact_results(pkg, orc):
+    """The two primitives introduced with the first-order tracking: a / k directly in (mid,t) form (scalek / mt_scale) and the fused
+    interval * point accumulation (ipfma), against exact rational arithmetic."""
+    import ctypes as C
+    from fractions import Fraction
+    L = orc.lib(pkg.abi)
+    L.orc_debug_primitives.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_size_t]
+    dp = C.POINTER(C.c_double)
+    rng = np.random.default_rng(11)
+    n = 400
+    x = rng.standard_normal((n, 8)) * np.exp(rng.uniform(-30, 30, (n, 8)))
+    x[:, 1] = np.abs(x[:, 0]) * (1 + np.abs(rng.standard_normal(n)) * np.exp(rng.uniform(-40, 2, n)))     # t >= |m|, radius from tiny to large
+    x[::7, 1] = np.abs(x[::7, 0])                                                                          # points
+    x[:, 2] = rng.integers(1, 22, n)
+    out = np.zeros((n, 4))
+    assert L.orc_debug_primitives(21, x.ctypes.data_as(dp), out.ctypes.data_as(dp), n) == 0
+    for i in range(n):
+        m, t, k = Fraction(float(x[i, 0])), Fraction(float(x[i, 1])), int(x[i, 2])
+        r = t - abs(m)
+        m2, t2 = Fraction(float(out[i, 0])), Fraction(float(out[i, 1]))
+        r2 = t2 - abs(m2)
+        assert r2 >= 0
+        assert m2 - r2 <= (m - r) / k and (m + r) / k <= m2 + r2                  # encloses [m - r, m + r] / k
+        assert r2 <= r / k + t / k * Fraction(1, 2 ** 48) + Fraction(1, 2 ** 990)        # and is tight (inflation 2^-50 of t)
+    # ipfma: a + x * p
+    y = rng.standard_normal((n, 8)) * np.exp(rng.uniform(-10, 10, (n, 8)))
+    for a in (0, 2):
+        lo, hi = np.minimum(y[:, a], y[:, a + 1]), np.maximum(y[:, a], y[:, a + 1]); y[:, a], y[:, a + 1] = lo, hi
+    assert L.orc_debug_primitives(22, y.ctypes.data_as(dp), out.ctypes.data_as(dp), n) == 0
+    for i in range(n):
+        alo, ahi, xlo, xhi, p = (Fraction(float(v)) for v in y[i, :5])
+        cands = [xlo * p, xhi * p]
+        lo, hi = alo + min(cands), ahi + max(cands)
+        assert Fraction(float(out[i, 0])) <= lo and hi <= Fraction(float(out[i, 1]))
+        assert Fraction(float(np.nextafter(out[i, 0], np.inf))) > lo and Fraction(float(np.nextafter(out[i, 1], -np.inf))) < hi   # one rounding per bound
