@@ -1028,7 +1028,7 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
         // ---- hull of the phi-set ----
         if (tid < D) {
             ival a = pt(S.x[cur][tid]);
-            for (int j = 0; j < D; j++) a = iadd(a, imul_nl(pt(S.C[cur][tid][j]), S.r0[j]));
+            for (int j = 0; j < D; j++) ipfma(a, S.r0[j], S.C[cur][tid][j]);          // fused: one rounding per bound and term
             a = iadd(a, S.r[cur][tid]);
             S.X[tid] = a;
             if (!ifinite(a)) atomicOr(&S.flag, 1);
@@ -1389,7 +1389,7 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
             }
             if (tid < D) {
                 ival a = pt(S.x[cur][tid]);
-                for (int j = 0; j < D; j++) a = iadd(a, imul_nl(pt(S.C[cur][tid][j]), S.r0[j]));
+                for (int j = 0; j < D; j++) ipfma(a, S.r0[j], S.C[cur][tid][j]);          // fused: one rounding per bound and term
                 gres->last_frame[tid * ld + N + 1] = toc(iadd(a, S.r[cur][tid]));
             }
         }

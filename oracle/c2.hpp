@@ -209,7 +209,7 @@ static inline void run_front(const ccp_front_desc& d, ccp_front_result& res, std
         ival X[MAXD];
         for (int i = 0; i < D; i++) {
             ival a(x[i]);
-            for (int j = 0; j < D; j++) a = a + ival(C[i][j]) * r0[j];
+            for (int j = 0; j < D; j++) ipfma(a, r0[j], C[i][j]);
             X[i] = a + r[i];
         }
         bool inside = true, fin = true;
@@ -456,7 +456,7 @@ static inline void run_front(const ccp_front_desc& d, ccp_front_result& res, std
             }
             for (int i = 0; i < D; i++) {
                 ival a(x[i]);
-                for (int j = 0; j < D; j++) a = a + ival(C[i][j]) * r0[j];
+                for (int j = 0; j < D; j++) ipfma(a, r0[j], C[i][j]);
                 res.last_frame[i * ld + n + 1] = toc(a + r[i]);
             }
         }
