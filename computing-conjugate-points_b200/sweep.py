@@ -6,6 +6,7 @@ result records at the end (NCCL over NVLink on GPUs, gloo in the CPU tests of th
 torch is used for device buffers, streams and torch.distributed only.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -70,3 +71,70 @@ def write_plot_parameters(path, params, counts):
     with open(path, "w") as f:
         for p, c in zip(params, counts):
             f.write("%.8g %.8g %d\n" % (p[3], p[4], c if c >= 0 else -1))
+
+
+# ----------------------------------------------------------------------------- SampleParameters (heteroclinic.cpp:429-491)
+
+def _read_journal(path):
+    """Journal lines are `index code`; a torn last line (crash while writing) is dropped."""
+    done = {}
+    try:
+        with open(path) as f:
+            text = f.read()
+    except FileNotFoundError:
+        return done
+    lines = text.split("\n")
+    if text and not text.endswith("\n"):
+        lines = lines[:-1]
+    for ln in lines:
+        parts = ln.split()
+        if len(parts) == 2:
+            done[int(parts[0])] = int(parts[1])
+    return done
+
+
+def SampleParameters(frame_count_batch, descs, params, path="plot_parameters.txt", chunk=1024, resume=True, code_of=None):
+    """The sweep loop of SampleParameters (heteroclinic.cpp:447-471) over prepared descriptors, in chunks of `chunk`
+    fronts per launch: Unstable_EigenValues[i] = frameDet's return value (`frame_det_code`), every negative code
+    collapsed to -1 (heteroclinic.cpp:469-470), then `plot_parameters.txt` in the reference's format (:474-486).
+
+    The reference keeps all counts in memory until the very end and loses the sweep on a crash; here every finished
+    chunk is appended to `<path>.journal` (fsync'ed), a rerun with resume=True skips what the journal holds, and the
+    journal is removed once the final file is written.  `frame_count_batch` is `Engine.frame_count_batch` (the GPU
+    call; there is no CPU fallback -- a failing call propagates).  Returns the list of counts.
+    """
+    from . import frame_det_code
+    code_of = code_of or frame_det_code
+    m = len(descs)
+    if len(params) != m:
+        raise ValueError("SampleParameters: %d descriptors for %d parameter vectors" % (m, len(params)))
+    if chunk <= 0:
+        raise ValueError("SampleParameters: chunk must be positive")
+    jpath = path + ".journal"
+    done = _read_journal(jpath) if resume else {}
+    done = {i: c for i, c in done.items() if 0 <= i < m}
+    todo = [i for i in range(m) if i not in done]
+    with open(jpath + ".tmp", "w") as jf:              # rewrite what was parsed: a torn last line must not be appended to
+        jf.write("".join("%d %d\n" % (i, done[i]) for i in sorted(done)))
+    os.replace(jpath + ".tmp", jpath)
+    with open(jpath, "a") as jf:
+        for at in range(0, len(todo), chunk):
+            idx = todo[at:at + chunk]
+            batch = (abi.FrontDesc * len(idx))()
+            for k, i in enumerate(idx):
+                C.memmove(C.byref(batch[k]), C.byref(descs[i]), C.sizeof(abi.FrontDesc))
+            res = frame_count_batch(batch)
+            if len(res) != len(idx):
+                raise RuntimeError("SampleParameters: engine returned %d records for %d fronts" % (len(res), len(idx)))
+            out = []
+            for k, i in enumerate(idx):
+                c = code_of(res[k])
+                done[i] = c if c >= 0 else -1
+                out.append("%d %d\n" % (i, done[i]))
+            jf.write("".join(out))
+            jf.flush()
+            os.fsync(jf.fileno())
+    counts = [done[i] for i in range(m)]
+    write_plot_parameters(path, params, counts)
+    os.remove(jpath)
+    return counts
