@@ -18,3 +18,20 @@ def test_eigenvalue_mirror_host_only(pkg):
     assert r.returncode == 0, r.stdout + r.stderr
     for tag in ("boundEigenvectors ok: 6 columns validated", "krawczykEigenvector ok", "failure codes ok", "boundEigenvalues ok"):
         assert tag in r.stdout
+
+
+def test_manifold_conditions_mirror_host_only(pkg):
+    """host/ccp_manifold_conditions.hpp: localManifold::constructU / checkIsolatingBlock / checkRateCondition / checkConditions
+    (localManifold.cpp:4-41, 180-325) around the GPU call boundDFU.  tests/cpp/test_conditions.cpp checks the certified norm bounds
+    (spectral norm, logarithmic norm, ml) against long double on 200 random matrices, and the two conditions on the n = 3 defaults
+    at the equilibrium 0 with DF enclosed over the whole neighbourhood on the host (accepted at radius 1e-3 for both manifolds,
+    rejected at radius 0.6 and for a cone that is too thin)."""
+    exe = os.path.join(ROOT, "tests", "cpp", "test_conditions")
+    cmd = ["g++", "-std=c++17", "-O1", "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_conditions.cpp"),
+           "-L", pkg.PKG_DIR, "-lccp_b200", "-Wl,-rpath," + pkg.PKG_DIR]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    for tag in ("norm bounds ok", "checkConditions ok", "failing neighbourhoods rejected", "helpers ok"):
+        assert tag in r.stdout
