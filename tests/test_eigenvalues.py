@@ -35,3 +35,19 @@ def test_manifold_conditions_mirror_host_only(pkg):
     assert r.returncode == 0, r.stdout + r.stderr
     for tag in ("norm bounds ok", "checkConditions ok", "failing neighbourhoods rejected", "helpers ok"):
         assert tag in r.stdout
+
+
+def test_local_manifold_eig_mirror_host_only(pkg):
+    """host/ccp_local_manifold_eig.hpp: localManifold_Eig (localManifold.cpp:426-681) -- computeK, ErrorEigenfunction,
+    computeEigenError_minus/plus_infty, checkConjugatePointsBelowLminus: the producer of the descriptor field Eu_err.
+    tests/cpp/test_eig_error.cpp: K against the condition number in long double (1e-6), eps against the formula of Section 3
+    evaluated independently (2 %), eps ~ r_u, Eu_m_Error_Final symmetric boxes of the size of eps copied into the descriptor,
+    (2.12) accepted at radius 1e-3 and rejected where eps > 1."""
+    exe = os.path.join(ROOT, "tests", "cpp", "test_eig_error")
+    cmd = ["g++", "-std=c++17", "-O1", "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_eig_error.cpp"),
+           "-L", pkg.PKG_DIR, "-lccp_b200", "-Wl,-rpath," + pkg.PKG_DIR]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "localManifold_Eig ok" in r.stdout and "below-L_- test 0" in r.stdout
