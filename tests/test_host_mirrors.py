@@ -51,3 +51,20 @@ def test_local_manifold_eig_mirror_host_only(pkg):
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "localManifold_Eig ok" in r.stdout and "below-L_- test 0" in r.stdout
+
+
+def test_l_plus_stage_mirror_host_only(pkg):
+    """host/ccp_l_plus.hpp: the L_+ stage that consumes the hot path's getLastFrame / getFirstFrame output
+    (propagateManifold.cpp:192-558, topFrame.cpp:336-351).  tests/cpp/test_l_plus.cpp: Proposition 2.9's arithmetic against the
+    same formulas in plain doubles over a scan of eps_beta (one acceptance threshold), compute_epsilon_beta on frames with known
+    answers (orthonormal, thick, rank-deficient), projectionGammaBeta round trip, checkFirstFrame / checkL_plus on synthetic
+    result records.  The GPU-backed parts (construct_Manifold_at_LPlus, lastEuFrame) are compiled but not run here."""
+    exe = os.path.join(ROOT, "tests", "cpp", "test_l_plus")
+    cmd = ["g++", "-std=c++17", "-O1", "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_l_plus.cpp"),
+           "-L", pkg.PKG_DIR, "-lccp_b200", "-Wl,-rpath," + pkg.PKG_DIR]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    for tag in ("Proposition 2.9 arithmetic ok", "projectionGammaBeta ok", "checkFirstFrame / checkL_plus ok"):
+        assert tag in r.stdout
