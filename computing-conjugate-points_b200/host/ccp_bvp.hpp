@@ -217,15 +217,19 @@ class boundaryValueProblem {
     // on T for F(T) = <Gx - Gy, f(Gx) + f(Gy)> = d/dT |Phi_T(x) - Phi_{-T}(y)|^2 / 2; like the reference only midpoints enter the
     // update, so f and Df are evaluated in doubles at the midpoints of the validated images (two integrations per step, one launch).
     double FindTime(const Manifold& unstable, const Manifold& stable, const IVector& XY_pt, double T) {
+        return FindTimeBatch({TimeIn{unstable, stable, XY_pt, T, IVector()}})[0];
+    }
+    // the same for many fronts (a parameter sweep): every Newton step on T is ONE launch of two integrations per front still iterating
+    struct TimeIn { Manifold unstable, stable; IVector XY_pt; double T; IVector params; };
+    std::vector<double> FindTimeBatch(const std::vector<TimeIn>& in) {
         const int n = n_, D = 2 * n;
-        const double T_original = T;
-        IVector X_pt(XY_pt.begin(), XY_pt.begin() + n), Y_pt(XY_pt.begin() + n, XY_pt.end());
+        const size_t m = in.size();
         const IVector zero(n, interval(0.0));
         auto mid = [](const interval& a) { return 0.5 * (a.lo + a.hi); };
-        std::vector<double> b(n), c(n, 0.0);
-        for (int i = 0; i < n; i++) b[i] = mid(params_[i]);
-        for (int i = 0; i < n - 1; i++) c[i] = mid(params_[n + i]);
-        auto field = [&](const std::vector<double>& z, std::vector<double>& f, std::vector<std::vector<double>>& Df) {
+        auto field = [&](const IVector& par, const std::vector<double>& z, std::vector<double>& f, std::vector<std::vector<double>>& Df) {
+            std::vector<double> b(n), c(n, 0.0);
+            for (int i = 0; i < n; i++) b[i] = mid(par[i]);
+            for (int i = 0; i < n - 1; i++) c[i] = mid(par[n + i]);
             f.assign(D, 0.0); Df.assign(D, std::vector<double>(D, 0.0));
             std::vector<double> g(n), w(n);
             for (int i = 0; i < n; i++) { g[i] = z[i] * (1.0 - z[i]); w[i] = z[i] - 0.5; f[i] = z[n + i]; Df[i][n + i] = 1.0; }
@@ -236,26 +240,44 @@ class boundaryValueProblem {
                 f[n + i] = F; Df[n + i][i] = Mii;
             }
         };
-        double original_dist = 0, dist0 = 0;
+        std::vector<double> T(m), original_dist(m, 0.0), dist0(m, 0.0);
+        std::vector<char> active(m, 1), failed(m, 0);
+        for (size_t q = 0; q < m; q++) T[q] = in[q].T;
         for (int it = 0; it < 10; it++) {
-            std::vector<Out> o = run({getPointNbd(unstable, X_pt, zero), getPointNbd(stable, Y_pt, zero)}, {T, T});
-            if (o[0].status != CCP_OK || o[1].status != CCP_OK) return T_original;
-            std::vector<double> gx(D), gy(D), fx, fy; std::vector<std::vector<double>> Dx, Dy;
-            for (int i = 0; i < D; i++) { gx[i] = mid(o[0].image[i]); gy[i] = mid(o[1].image[i]); }
-            field(gx, fx, Dx); field(gy, fy, Dy);
-            dist0 = 0; double d1 = 0, d2 = 0;
-            for (int i = 0; i < D; i++) {
-                // the y-trajectory runs backwards: d/dT Phi_{-T}(y) = -f, d^2/dT^2 = +Df f
-                const double dv = gx[i] - gy[i], dd1 = fx[i] + fy[i];
-                double ax = 0, ay = 0; for (int k = 0; k < D; k++) { ax += Dx[i][k] * fx[k]; ay += Dy[i][k] * fy[k]; }
-                const double dd2 = ax - ay;
-                dist0 += dv * dv; d1 += dv * dd1; d2 += dd1 * dd1 + dv * dd2;
+            std::vector<FlowSet> sets; std::vector<double> times; std::vector<size_t> who;
+            for (size_t q = 0; q < m; q++) {
+                if (!active[q]) continue;
+                const IVector X_pt(in[q].XY_pt.begin(), in[q].XY_pt.begin() + n), Y_pt(in[q].XY_pt.begin() + n, in[q].XY_pt.end());
+                FlowSet fx = getPointNbd(in[q].unstable, X_pt, zero), fy = getPointNbd(in[q].stable, Y_pt, zero);
+                fx.params = in[q].params; fy.params = in[q].params;
+                sets.push_back(fx); sets.push_back(fy); times.push_back(T[q]); times.push_back(T[q]); who.push_back(q);
             }
-            if (it == 0) original_dist = dist0;
-            if (d2 == 0.0 || !std::isfinite(d1 / d2)) break;
-            T = T - d1 / d2;
+            if (who.empty()) break;
+            const std::vector<Out> o = run(sets, times);
+            for (size_t k = 0; k < who.size(); k++) {
+                const size_t q = who[k];
+                const Out &ox = o[2 * k], &oy = o[2 * k + 1];
+                if (ox.status != CCP_OK || oy.status != CCP_OK) { active[q] = 0; failed[q] = 1; continue; }
+                const IVector& par = in[q].params.empty() ? params_ : in[q].params;
+                std::vector<double> gx(D), gy(D), fx, fy; std::vector<std::vector<double>> Dx, Dy;
+                for (int i = 0; i < D; i++) { gx[i] = mid(ox.image[i]); gy[i] = mid(oy.image[i]); }
+                field(par, gx, fx, Dx); field(par, gy, fy, Dy);
+                double d0 = 0, d1 = 0, d2 = 0;
+                for (int i = 0; i < D; i++) {
+                    // the y-trajectory runs backwards: d/dT Phi_{-T}(y) = -f, d^2/dT^2 = +Df f
+                    const double dv = gx[i] - gy[i], dd1 = fx[i] + fy[i];
+                    double ax = 0, ay = 0; for (int kk = 0; kk < D; kk++) { ax += Dx[i][kk] * fx[kk]; ay += Dy[i][kk] * fy[kk]; }
+                    const double dd2 = ax - ay;
+                    d0 += dv * dv; d1 += dv * dd1; d2 += dd1 * dd1 + dv * dd2;
+                }
+                dist0[q] = d0;
+                if (it == 0) original_dist[q] = d0;
+                if (d2 == 0.0 || !std::isfinite(d1 / d2)) { active[q] = 0; continue; }
+                T[q] = T[q] - d1 / d2;
+            }
         }
-        return original_dist < dist0 ? T_original : T;
+        for (size_t q = 0; q < m; q++) if (failed[q] || original_dist[q] < dist0[q]) T[q] = in[q].T;
+        return T;
     }
 
   private:

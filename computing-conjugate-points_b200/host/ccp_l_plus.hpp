@@ -92,7 +92,8 @@ struct LPlusStage {
     localManifold stable;                 // *pStable: its F (A_s, Ainv, p) and the parameters
 
     // propagateManifold.cpp:244-304
-    localManifold_Eig construct_Manifold_at_LPlus(IVector endPoint_LPlus) const {
+    // the manifold object before the adjust_L loop (:244-289)
+    localManifold_Eig start_Manifold_at_LPlus(IVector endPoint_LPlus) const {
         const int n = dimension / 2;
         endPoint_LPlus = matVec(stable.F.Ainv, endPoint_LPlus);                                     // gauss(A_s, .): into eigen-coordinates
         IVector vec_Lplus_u(endPoint_LPlus.begin(), endPoint_LPlus.begin() + n), vec_Lplus_s(endPoint_LPlus.begin() + n, endPoint_LPlus.end());
@@ -103,6 +104,10 @@ struct LPlusStage {
         const interval L_new(ia::div(euclNorm(vec_Lplus_u), interval(ia::sqrt(ss).lo)).hi);           // right end of |u| / |s|  (vartheta of the paper)
         localManifold_Eig big(stable);
         big.stable = true; big.U_flat_global = U_flat_new; big.L = L_new; big.subdivisionNUM = manifold_subdivision;
+        return big;
+    }
+    localManifold_Eig construct_Manifold_at_LPlus(const IVector& endPoint_LPlus) const {
+        localManifold_Eig big = start_Manifold_at_LPlus(endPoint_LPlus);
         for (int i = 0; i < 10; i++) {                                                              // adjust_L
             if (big.checkConditions()) break;
             big.L = ia::mul(big.L, interval(2.0));
@@ -149,9 +154,13 @@ struct LPlusStage {
 
     // propagateManifold.cpp:192-240
     bool lastEuFrame(const topFrame& A_frame, const IVector& endPoint_LPlus) const {
-        const IMatrix last_Frame = A_frame.getLastFrame();
         localManifold_Eig big = construct_Manifold_at_LPlus(endPoint_LPlus);
-        if (!big.checkConditions()) return false;
+        return lastEuFrameWith(A_frame, big, big.checkConditions());
+    }
+    // the part after the manifold at L_+ has been built and checked (:206-239)
+    bool lastEuFrameWith(const topFrame& A_frame, localManifold_Eig& big, bool conditions_S) const {
+        const IMatrix last_Frame = A_frame.getLastFrame();
+        if (!conditions_S) return false;
         big.computeEigenError_plus_infty();
         const IMatrix& EFunction_Error = big.Eigenfunction_Error_plus_infty;
         interval eps_0(0.0);
@@ -160,5 +169,25 @@ struct LPlusStage {
         return checkL_plus(A_frame, U_coord, eps_0, big.eigenvalues);
     }
 };
+
+// construct_Manifold_at_LPlus for many fronts: every round of the adjust_L loop is ONE boundDFU launch over the manifolds not yet verified.
+// Returns the manifolds and whether each was verified (what the final checkConditions of lastEuFrame would return).
+inline std::vector<localManifold_Eig> constructManifoldsAtLPlusBatch(const std::vector<LPlusStage>& st, const std::vector<IVector>& endPoints,
+                                                                      std::vector<char>& verified) {
+    std::vector<localManifold_Eig> big;
+    for (size_t q = 0; q < st.size(); q++) big.push_back(st[q].start_Manifold_at_LPlus(endPoints[q]));
+    verified.assign(st.size(), 0);
+    for (int i = 0; i < 11; i++) {                                                                  // 10 adjust_L rounds + the final check
+        std::vector<localManifold*> todo; std::vector<size_t> who;
+        for (size_t q = 0; q < big.size(); q++) if (!verified[q]) { todo.push_back(&big[q]); who.push_back(q); }
+        if (todo.empty()) break;
+        const std::vector<char> ok = checkConditionsBatch(todo);
+        for (size_t k = 0; k < who.size(); k++) {
+            if (ok[k]) verified[who[k]] = 1;
+            else if (i < 10) big[who[k]].L = ia::mul(big[who[k]].L, interval(2.0));                 // round 10 is lastEuFrame's own check: no doubling
+        }
+    }
+    return big;
+}
 
 }  // namespace ccp_host

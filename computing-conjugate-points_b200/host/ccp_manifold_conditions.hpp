@@ -224,14 +224,20 @@ struct localManifold {
 };
 
 // many manifolds (both ends of every front of a sweep) in ONE boundDFU launch
-inline std::vector<char> checkConditionsBatch(std::vector<localManifold>& Ms) {
+inline std::vector<char> checkConditionsBatch(const std::vector<localManifold*>& Ms) {
     std::vector<ccp_dfu_desc> d;
     std::vector<IVector> Us;
-    for (auto& m : Ms) { Us.push_back(m.constructU(m.U_flat_global)); d.push_back(make_dfu_desc(m.dimension / 2, m.params, m.F, Us.back(), m.stable, m.subdivisionNUM)); }
-    const std::vector<IMatrix> DF = boundDFUBatch(d);
+    for (localManifold* m : Ms) { Us.push_back(m->constructU(m->U_flat_global)); d.push_back(make_dfu_desc(m->dimension / 2, m->params, m->F, Us.back(), m->stable, m->subdivisionNUM)); }
     std::vector<char> ok(Ms.size());
-    for (size_t q = 0; q < Ms.size(); q++) ok[q] = Ms[q].checkConditionsOn(DF[q], Us[q]) ? 1 : 0;
+    if (Ms.empty()) return ok;
+    const std::vector<IMatrix> DF = boundDFUBatch(d);
+    for (size_t q = 0; q < Ms.size(); q++) ok[q] = Ms[q]->checkConditionsOn(DF[q], Us[q]) ? 1 : 0;
     return ok;
+}
+inline std::vector<char> checkConditionsBatch(std::vector<localManifold>& Ms) {
+    std::vector<localManifold*> p;
+    for (auto& m : Ms) p.push_back(&m);
+    return checkConditionsBatch(p);
 }
 
 }  // namespace ccp_host
