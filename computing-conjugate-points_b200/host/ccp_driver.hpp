@@ -19,6 +19,7 @@ namespace ccp_host {
 struct DriverReport {
     int result = -10;
     double T = 0, radius = 0, eps_minus = 0;
+    int zero_count = -1, failure_count = -1, first_failure = -1, series_length = 0;      // countZeros of the frame stage
     interval L_minus;
     bool conditions_first = false, conditions_resized = false, inside_box = false, proof = false, below_Lminus = false;
 };
@@ -126,7 +127,10 @@ inline int computeFrontAndConjugatePoints(int dimension, const std::vector<doubl
     st.dimension = dimension; st.manifold_subdivision = manifold_subdivision; st.stable = localStable;
     E_u.below_Lminus = [&] { return rep.below_Lminus; };
     E_u.L_plus = [&](const topFrame& f, const IVector& e) { return st.lastEuFrame(f, e); };
-    return rep.result = E_u.frameDet(L_minus, grid, endPoint_LPlus);
+    rep.result = E_u.frameDet(L_minus, grid, endPoint_LPlus);
+    const ccp_front_result& fr = E_u.frame().result();
+    rep.zero_count = fr.zero_count; rep.failure_count = fr.failure_count; rep.first_failure = fr.first_failure; rep.series_length = fr.series_length;
+    return rep.result;
 }
 
 // ---- the same for a whole parameter sweep (SampleParameters, heteroclinic.cpp:429-491): all fronts advance through the stages in

@@ -25,6 +25,7 @@ int main(int argc, char** argv) {
     catch (int code) { std::printf("thrown code %d\n", code); r = code; }
     std::printf("manifolds %d/%d, T = %.6f, inside %d, proof %d (radius %.3e), eps_- = %.3e, below L_- %d, L_- = %.6f\n", (int)rep.conditions_first,
                 (int)rep.conditions_resized, rep.T, (int)rep.inside_box, (int)rep.proof, rep.radius, rep.eps_minus, (int)rep.below_Lminus, rep.L_minus.hi);
+    std::printf("countZeros: %d zeros, %d failures (first at sub-interval %d of %d)\n", rep.zero_count, rep.failure_count, rep.first_failure, rep.series_length);
     std::printf("computeFrontAndConjugatePoints = %d\n", r);
     return r == expected ? 0 : 1;
 }
