@@ -12,7 +12,7 @@
 // Small, serial per front, host only.  CAPD pieces and their replacements, all rigorous on their own:
 //   (*f)(x, Df, Hf) with setDegree(2)   -> closed-form second derivatives of the front field (frontHessian), stored like CAPD's IHessian
 //                                          as Taylor coefficients D^a f / a!  [CAPD-recollection: Hf(i,j,j) = f_jj / 2, Hf(i,j,k) = f_jk]
-//   gaussInverseMatrix / krawczykInverse -> inverseEnclosure (approximate inverse C, E = I - C Q, |E|_inf < 1  =>  Q^-1 = (I-E)^-1 C)
+//   gaussInverseMatrix / krawczykInverse -> inverseEnclosure (approximate inverse C, E = I - C Q, |E|_inf < 1  =>  Q^-1 = C + E C + E^2 (I-E)^-1 C)
 //   gauss(A, b)                          -> Ainv * b with the enclosure of A^-1 the caller already holds (LocalField::Ainv)
 //   EuclNorm                             -> the certified bounds of ccp_manifold_conditions.hpp
 #pragma once
@@ -37,22 +37,30 @@ inline IMatrix toInterval(const DMatrix& A) {                                // 
     return M;
 }
 
-// enclosure of the inverse of every matrix in Q (throws when the approximate inverse does not contract)
+// enclosure of the inverse of every matrix in Q (throws when the approximate inverse does not contract):
+//   C ~ mid(Q)^-1,  E = I - C Q,  |E|_inf < 1  =>  Q^-1 = (I - E)^-1 C = C + E C + E^2 (I - E)^-1 C;
+// the first-order term is an interval matrix product (entrywise tight for a thick Q), the rest is bounded in the infinity norm.
 inline IMatrix inverseEnclosure(const IMatrix& Q) {
     const int n = (int)Q.size();
     DMatrix mid(n, std::vector<double>(n));
     for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) mid[i][j] = ia::mid(Q[i][j]);
     const DMatrix C = approxInverse(mid);
-    const IMatrix E = matMul(toInterval(C), Q);                              // I - E' with E' = C Q
+    const IMatrix Ci = toInterval(C);
+    IMatrix E = matMul(Ci, Q);
     double nE = 0;
-    for (int i = 0; i < n; i++) { double s = 0; for (int j = 0; j < n; j++) s = ia::up(s + ia::mag(ia::sub(interval(i == j ? 1.0 : 0.0), E[i][j]))); nE = std::max(nE, s); }
+    for (int i = 0; i < n; i++) {
+        double s = 0;
+        for (int j = 0; j < n; j++) { E[i][j] = ia::sub(interval(i == j ? 1.0 : 0.0), E[i][j]); s = ia::up(s + ia::mag(E[i][j])); }
+        nE = std::max(nE, s);
+    }
     if (!(nE < 1)) throw std::runtime_error("inverseEnclosure: approximate inverse does not contract");
-    const double x = ia::up(nE / ia::dn(1 - nE));                            // |(I - (I - C Q))^-1 - I|_inf <= nE / (1 - nE)
+    const IMatrix EC = matMul(E, Ci);
+    const double x = ia::up(ia::up(nE * nE) / ia::dn(1 - nE));               // |E^2 (I - E)^-1|_inf <= nE^2 / (1 - nE)
     IMatrix out(n, IVector(n));
     for (int j = 0; j < n; j++) {
         double cmax = 0; for (int k = 0; k < n; k++) cmax = std::max(cmax, std::fabs(C[k][j]));
         const double r = ia::up(x * cmax);
-        for (int i = 0; i < n; i++) out[i][j] = interval(ia::dn(C[i][j] - r), ia::up(C[i][j] + r));
+        for (int i = 0; i < n; i++) out[i][j] = ia::add(ia::add(Ci[i][j], EC[i][j]), interval(-r, r));
     }
     return out;
 }
