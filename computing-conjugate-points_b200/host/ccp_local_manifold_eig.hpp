@@ -152,7 +152,9 @@ struct localManifold_Eig : localManifold {
         const interval r_u = euclNorm(absU);
         interval lambda = ia::div(ia::mul(ia::mul(ia::mul(ia::mul(K, C_G), r_u), norm_A0), ia::sqrt(ia::add(interval(1.0), ia::sqr(L)))), eta);
         lambda = interval(lambda.hi);
-        eps_unscaled = ia::div(lambda, ia::sub(interval(1.0), lambda));
+        // lambda/(1 - lambda) is the sum of the Neumann series only for lambda < 1; the reference evaluates the quotient regardless
+        // (a negative eps would then pass the L_- test) -- here lambda >= 1 gives eps = +infinity and every later test fails.
+        eps_unscaled = (lambda.hi < 1) ? ia::div(lambda, ia::sub(interval(1.0), lambda)) : interval(INFINITY);
     }
 
     // localManifold.cpp:540-571
