@@ -68,14 +68,15 @@ inline bool checkL_plus_local(const IMatrix& Gamma, const IMatrix& Beta, interva
     eps_0 = interval(eps_0.hi);
     const interval one(1.0), two(2.0), n((double)(dimension / 2)), d_min(1.0), d_max(1.0);
     const interval s2n1 = ia::sqrt(ia::mul(ia::mul(ia::mul(two, n), nu_1), d_max));                 // sqrt(2 n nu_1 d_max)
-    interval C_P = ia::div(ia::mul(two, s2n1), ia::sub(one, ia::mul(eps_0, s2n1)));
+    const interval sum_for_neumann_test = ia::mul(eps_0, s2n1);
+    if (!(sum_for_neumann_test.hi < 1)) return false;                                                // the reference tests this after C_P; here first: 1 - eps_0 s must not reach 0
+    interval C_P = ia::div(ia::mul(two, s2n1), ia::sub(one, sum_for_neumann_test));
     interval C_Q = ia::add(ia::add(ia::sqrt(ia::div(ia::mul(two, n), ia::mul(nu_n, d_min))), s2n1), ia::mul(ia::mul(two, eps_0), n));
     C_P = interval(C_P.hi); C_Q = interval(C_Q.hi);
     const interval eQ = ia::mul(eps_0, C_Q), eP = ia::mul(eps_0, C_P);
     const interval C_M1 = ia::mul(eQ, ia::add(two, eQ));
     const interval C_M2 = ia::add(ia::add(ia::mul(eP, ia::add(two, eP)), ia::mul(ia::mul(two, epsilon_beta), ia::add(one, eP))), ia::sqr(epsilon_beta));
-    const interval sum_for_neumann_test = ia::mul(eps_0, s2n1);
-    const bool NEUMANN_SERIES_TEST = C_M1.hi < 1 && C_M2.hi < 1 && sum_for_neumann_test.hi < 1;
+    const bool NEUMANN_SERIES_TEST = C_M1.hi < 1 && C_M2.hi < 1;
     if (!NEUMANN_SERIES_TEST) return false;                                                          // (also keeps 1 - C_M away from zero below)
     const interval sum_1 = ia::mul(ia::mul(two, eps_0), ia::add(C_Q, C_P));
     const interval sum_2 = ia::mul(ia::sqr(eps_0), ia::add(ia::sqr(C_Q), ia::sqr(C_P)));
