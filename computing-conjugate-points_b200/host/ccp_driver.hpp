@@ -300,7 +300,12 @@ inline std::vector<int> computeFrontAndConjugatePointsBatch(int dimension, const
     }
     if (!who.empty()) {
         const std::vector<int> out = propagateManifold::frameDetBatch(fronts, Lm, grid, ends);
-        for (size_t k = 0; k < who.size(); k++) code[who[k]] = thrown[k] != 0 ? thrown[k] : out[k];
+        for (size_t k = 0; k < who.size(); k++) {
+            code[who[k]] = thrown[k] != 0 ? thrown[k] : out[k];
+            const ccp_front_result& fr = fronts[k].frame().result();
+            DriverReport& r = rep[who[k]];
+            r.zero_count = fr.zero_count; r.failure_count = fr.failure_count; r.first_failure = fr.first_failure; r.series_length = fr.series_length;
+        }
     }
     for (size_t q = 0; q < m; q++) rep[q].result = code[q];
     if (reports) *reports = rep;

@@ -5,10 +5,26 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 using namespace ccp_host;
 int main(int argc, char** argv) {
     if (ccp_device_count() <= 0) { std::printf("no GPU: compiled and linked only\n"); return 77; }
     if (ccp_init(0) != 0) { std::printf("init failed: %s\n", ccp_last_error()); return 2; }
+    if (argc == 2 && std::string(argv[1]) == "n2") {                             // three fronts of the two-component system (dimension 4)
+        const std::vector<std::vector<double>> P = {{1, .97, .05}, {1, .97, -.05}, {1, .95, .03}};
+        std::vector<IVector> PI(P.size());
+        for (size_t q = 0; q < P.size(); q++) for (double v : P[q]) PI[q].push_back(interval(v));
+        std::vector<DriverReport> rep;
+        const std::vector<int> code = computeFrontAndConjugatePointsBatch(4, P, PI, &rep);
+        std::printf("n = 2 codes:");
+        for (size_t q = 0; q < code.size(); q++) std::printf(" %d", code[q]);
+        std::printf("\n");
+        for (size_t q = 0; q < code.size(); q++) {
+            if (!rep[q].proof || rep[q].failure_count != 0 || rep[q].zero_count != code[q]) return 5;
+            if (computeFrontAndConjugatePoints(4, P[q], PI[q]) != code[q]) return 6;
+        }
+        return (code[0] == 1 && code[1] == 0 && code[2] == 1) ? 0 : 7;
+    }
     const int N_c = argc > 2 ? std::atoi(argv[1]) : 8, N_r = argc > 2 ? std::atoi(argv[2]) : 2, m = N_c * N_r;
     const double b[3] = {1.0, 0.975, 0.95};
     std::vector<double> flat(5 * m);

@@ -156,6 +156,10 @@ def test_batch_driver_against_oracle_backend(pkg, orc):
     assert r.returncode == 0, r.stdout + r.stderr
     assert "batch == single-front driver on the probed fronts" in r.stdout
     assert "codes: 2 -2 1 -3 -2 1" in r.stdout
+    # the two-component system: a front with one conjugate point, a stable front (0, proven end to end), another with one
+    r = subprocess.run([exe, "n2"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "n = 2 codes: 1 0 1" in r.stdout
 
 
 @pytest.mark.gpu
