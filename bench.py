@@ -98,21 +98,34 @@ def ncu_dram_traffic():
     return tot or None
 
 
-def cpu_reference_sample(pkg, orc, n_fronts_total, cores, steps=1, warmup=0):
-    """Times the oracle's reference-structured mode (n separate 4n-dim validated integrations + topFrame) on
-    `cores` fronts taken evenly from the sweep, one front per host thread."""
+XY_NBD = 1e-12          # +- radius of the neighbourhood of the connecting orbit in x (the Krawczyk stage delivers 1e-13 .. 3e-13)
+EIG_ERR = 2e-5          # +- entries of Eu_m_Error_Final
+CONE_L = 1.5e-5         # cone constant of the unstable manifold (heteroclinic.cpp:80-87)
+
+
+def bench_opts(pkg):
+    return pkg.abi.SetupOpts.default(xy_nbd=XY_NBD, eig_err=EIG_ERR, cone_L=CONE_L)
+
+
+def cpu_reference_sample(pkg, orc, n_fronts_total, cores, steps=1, warmup=0, mode=None, n_sample=None):
+    """Times an oracle mode on fronts taken evenly from the sweep, one front per host thread at a time.  Default: the
+    reference-structured mode (n separate 4n-dim validated integrations + topFrame) on `cores` fronts.  The metric's numerator for the
+    CPU arm is FRONTS PROCESSED per second: with the rigorous box of the bench the reference-structured algorithm (no renormalisation
+    of the frame basis) certifies none of them (`certified` is reported beside it)."""
     import numpy as np
+    mode = orc.MODE_REF if mode is None else mode
+    n_sample = cores if n_sample is None else n_sample
     params = sweep_params(pkg, n_fronts_total)
-    take = np.linspace(0, len(params) - 1, cores).round().astype(int)
-    descs, _ = pkg.setup_sweep(3, params[take])
+    take = np.linspace(0, len(params) - 1, n_sample).round().astype(int)
+    descs, _ = pkg.setup_sweep(3, params[take], bench_opts(pkg))
     times, certified = [], 0
     for it in range(warmup + steps):
-        res, sec = orc.run_batch(pkg.abi, descs, orc.MODE_REF, threads=cores)
+        res, sec = orc.run_batch(pkg.abi, descs, mode, threads=cores)
         if it >= warmup:
             times.append(sec)
             certified = sum(1 for r in res if pkg.frame_det_code(r) >= 0)
     sec = sum(times) / len(times)
-    return {"fronts": int(cores), "certified": int(certified), "seconds": sec, "value": certified / sec, "all_times": times}
+    return {"fronts": int(n_sample), "certified": int(certified), "seconds": sec, "value": n_sample / sec, "all_times": times}
 
 
 def main():
@@ -135,7 +148,8 @@ def main():
     import __graft_entry__ as ge
     pkg = ge.load_package()
     config = {"workload": "bifurcation-diagram sweep, Construct_ParameterList %dx8 = %d parameter values (BASELINE configs[1] x n_gpus), n=3, b=(1,.975,.95), order 20, step 2^-5, grid 14"
-              % (n_total // 8, n_total), "fronts_per_gpu": args.fronts_per_gpu, "parallelism": "front_id mod %d shards, 1 NCCL all-gather of result records per step" % world if world > 1 else "single GPU",
+              % (n_total // 8, n_total), "xy_nbd": XY_NBD, "eig_err": EIG_ERR, "cone_L": CONE_L,
+              "fronts_per_gpu": args.fronts_per_gpu, "parallelism": "front_id mod %d shards, 1 NCCL all-gather of result records per step" % world if world > 1 else "single GPU",
               "l2": "256 MiB written between timed steps (untimed); inputs are ~1.2 MB and the kernel is FP64-compute bound"}
 
     # ------------------------------------------------------------------ reference arm (CPU, rank 0 only)
@@ -147,8 +161,8 @@ def main():
         line = {"metric": METRIC, "value": s["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": min(W, 1),
                 "ms_per_step": s["seconds"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64 interval (directed rounding)", "data": "synthetic", "impl": "reference", "config": config,
-                "cpu_baseline": {"value": s["value"], "unit": UNIT, "cores": cores, "kind": "port",
-                                 "sample": "%d fronts of the sweep (evenly strided), one per host thread, oracle mode ref; reference binary needs CAPD 5.0.59 (unbuildable here)" % s["fronts"]},
+                "cpu_baseline": {"value": s["value"], "unit": UNIT, "cores": cores, "kind": "port", "certified_of_sample": s["certified"],
+                                 "sample": "%d fronts of the sweep (evenly strided), one per host thread, oracle mode ref; value = fronts PROCESSED per second (with the rigorous box xy_nbd = %g the reference-structured algorithm certifies %d of them); reference binary needs CAPD 5.0.59 (unbuildable here)" % (s["fronts"], XY_NBD, s["certified"])},
                 "e2e": {"value": s["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line))
@@ -168,7 +182,7 @@ def main():
 
     params = sweep_params(pkg, n_total)
     mine = sweep.local_indices(n_total, rank, world)
-    descs, infos = pkg.setup_sweep(3, params[mine])
+    descs, infos = pkg.setup_sweep(3, params[mine], bench_opts(pkg))
     m = len(descs)
     rb, db = C.sizeof(abi.FrontResult), C.sizeof(abi.FrontDesc)
     d_in = sweep.desc_array_to_tensor(descs, device=dev)
@@ -257,7 +271,10 @@ def main():
     # ---- roofline of the dominant kernel: counted FP64 flop of the implemented algorithm / CUDA-event time
     flop_local = float(sum(pkg.front_flops(3, 20, 14, int(s)) for s in steps_arr[mine]))
     achieved = flop_local / (sum(ker_ms) / K * 1e-3) / 1e12
+    clk = clocks.summary()
+    nominal = 148 * 64 * 2 * (clk.get("sm_max_mhz") or 1965.0) * 1e6 / 1e12          # 64 DFMA lanes per SM
     roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": ncu_dram_traffic(),
+                "peak_nominal": nominal, "frac_of_nominal": achieved / nominal,
                 "peak_source": "measured live on this GPU: 8 independent DFMA.RM/RP chains per thread (ccp_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry (nominal 37 TF)",
                 "kernel": "ccp::front_kernel<3>", "kernel_ms": sum(ker_ms) / K, "flop_per_launch": flop_local,
                 "note": "FP64 vector-pipe bound: ~1.2 MB in / 1.7 MB out per launch vs ~2e11 flop; DFMA=2 flop, DADD/DMUL=1 (DESIGN.md 5)"}
@@ -265,15 +282,19 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64 interval (directed rounding)", "data": "synthetic", "config": config,
-            "fronts_total": n_total, "certified": certified, "uncertified": uncertified,
+            "fronts_total": n_total, "certified": certified, "uncertified": uncertified, "certified_frac": certified / n_total,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": m * db * world, "d2h_bytes_per_step": m * rb * world},
-            "gpu_launches": int(launches), "clocks": clocks.summary(), "roofline": roofline}
+            "gpu_launches": int(launches), "clocks": clk, "roofline": roofline}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         orc = ge.load_oracle()
         s = cpu_reference_sample(pkg, orc, n_total, cores)
-        line["cpu_baseline"] = {"value": s["value"], "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": "%d fronts of the same sweep (evenly strided), one per host thread, %.1f s wall; oracle mode ref = reference-structured restatement (CAPD absent)" % (s["fronts"], s["seconds"])}
+        line["cpu_baseline"] = {"value": s["value"], "unit": UNIT, "cores": cores, "kind": "port", "certified_of_sample": s["certified"],
+                                "sample": "%d fronts of the same sweep (evenly strided), one per host thread, %.1f s wall; oracle mode ref = reference-structured restatement (CAPD absent); value = fronts PROCESSED per second: with the rigorous box it certifies %d of them" % (s["fronts"], s["seconds"], s["certified"])}
+        # the SAME algorithm as the kernel (oracle c2, its serial twin) on all host cores: separates the algorithmic factor from the hardware one
+        s2 = cpu_reference_sample(pkg, orc, n_total, cores, mode=orc.MODE_C2, n_sample=min(n_total, 32 * cores))
+        line["cpu_baseline_same_algorithm"] = {"value": s2["value"], "unit": UNIT, "cores": cores, "kind": "port", "certified_of_sample": s2["certified"],
+                                               "sample": "%d fronts of the same sweep, oracle mode c2 (serial twin of the kernel), %.1f s wall" % (s2["fronts"], s2["seconds"])}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

@@ -115,11 +115,14 @@ struct FrontSmem {
     ival dtime[GMAX];
     int dec[GMAX];
     int flag;
+    int renorms;                             // basis renormalisations applied so far (renormalise)
+    ival G[N][N], sc;                        // true frame = normalised frame * G ;  sc encloses det G > 0
     Majorant mj;
     double g15[2];
     union alignas(16) {
         ival scratch[Lay<N>::NB + Lay<N>::NC + 2 * N];   // table loop: Cauchy sums awaiting combination; then [0,0]; then the newest g, q
         mt JCr[2 * N][2 * N];                // set update: J*C - C+
+        struct { double Hm[N][N]; ival Hi[N][N]; int ok; } rn;   // renormalise: H and the enclosure of its inverse
         ccp_front_desc desc;                 // start of the front only
     } un;
 };
@@ -828,6 +831,109 @@ __device__ __noinline__ int set_update(FrontSmem<N>& S, PostTab<N>& PT, int cur,
     return nonfinite;
 }
 
+// ---- basis renormalisation of the frame, once per unit of time (oracle/c2.hpp:renorm_matrix and the block after the set update,
+//      same operations in the same order).  The columns of T = Dphi_t A_u align with the fastest unstable direction (condition number
+//      ~1e5 at L_-): the interval determinant of the hull of T then loses every digit once the relative width of the entries exceeds
+//      1/cond, which with a validated neighbourhood of the connecting orbit (1e-13 .. 1e-12) is the last third of the front.  T is only
+//      a BASIS of E^u: det(top(T)) = det(top(T H)) / det(H) for any invertible point matrix H.  H = inverse R factor of a floating-point
+//      Gram-Schmidt of Tc (round to nearest: any H is valid, only determinism matters), applied rigorously:
+//        Tc <- mid([Tc H]),  Theta_j <- mid([Theta_j H]),  R <- R H + residuals,  Err <- Err H,  G <- [H^-1] G,  sc <- sc det[H^-1].
+//      Called by all threads of the CTA. ----
+template <int N>
+__device__ __noinline__ void renormalise(FrontSmem<N>& S) {
+    constexpr int D = 2 * N;
+    const int tid = threadIdx.x;
+    static_assert(D * N <= 32 && N * N + 1 <= 32, "renormalise: one item per thread");
+    if (tid == 0) {
+        double Q[D][N], Rt[N][N], H[N][N];
+        bool ok = true;
+        for (int k = 0; k < N; k++) {
+            double v[D];
+            for (int i = 0; i < D; i++) v[i] = S.Tc[i][k];
+            for (int m = 0; m < k; m++) {
+                double dp = 0.0;
+                for (int i = 0; i < D; i++) dp = __dadd_rn(dp, __dmul_rn(Q[i][m], v[i]));
+                Rt[m][k] = dp;
+                for (int i = 0; i < D; i++) v[i] = __dadd_rn(v[i], -__dmul_rn(dp, Q[i][m]));
+            }
+            double nn = 0.0;
+            for (int i = 0; i < D; i++) nn = __dadd_rn(nn, __dmul_rn(v[i], v[i]));
+            nn = __dsqrt_rn(nn);
+            if (!(nn > 0.0) || !isfinite(nn)) { ok = false; nn = 1.0; }
+            Rt[k][k] = nn;
+            for (int i = 0; i < D; i++) Q[i][k] = __ddiv_rn(v[i], nn);
+        }
+        for (int k = 0; k < N; k++) {
+            for (int i = 0; i < N; i++) H[i][k] = 0.0;
+            H[k][k] = __ddiv_rn(1.0, Rt[k][k]);
+            for (int i = k - 1; i >= 0; i--) {
+                double a = 0.0;
+                for (int m = i + 1; m <= k; m++) a = __dadd_rn(a, __dmul_rn(Rt[i][m], H[m][k]));
+                H[i][k] = __ddiv_rn(-a, Rt[i][i]);
+            }
+        }
+        for (int k = 0; k < N; k++) for (int i = 0; i <= k; i++) if (!isfinite(H[i][k])) ok = false;
+        for (int k = 0; k < N; k++) if (!(H[k][k] > 0.0)) ok = false;
+        if (ok) {
+            for (int k = 0; k < N; k++) {               // interval inverse of the upper triangular point matrix H
+                for (int i = 0; i < N; i++) { S.un.rn.Hm[i][k] = H[i][k]; S.un.rn.Hi[i][k] = pt(0.0); }
+                S.un.rn.Hi[k][k] = mk(__ddiv_rd(1.0, H[k][k]), __ddiv_ru(1.0, H[k][k]));
+                for (int i = k - 1; i >= 0; i--) {
+                    ival a = pt(0.0);
+                    for (int m = i + 1; m <= k; m++) ipfma(a, S.un.rn.Hi[m][k], H[i][m]);
+                    const ival na = ineg(a);
+                    const double hd = H[i][i];          // > 0
+                    S.un.rn.Hi[i][k] = mk(dmin(__ddiv_rd(na.lo, hd), __ddiv_rd(na.hi, hd)), dmax(__ddiv_ru(na.lo, hd), __ddiv_ru(na.hi, hd)));
+                }
+            }
+        }
+        S.un.rn.ok = ok ? 1 : 0;
+    }
+    __syncthreads();
+    if (!S.un.rn.ok) { __syncthreads(); return; }
+    // one item per thread, new values in registers until every thread has read the old state
+    double tc2 = 0.0, th2[D]; ival r2 = pt(0.0), e2 = pt(0.0), g2 = pt(0.0);
+    const int i = tid / N, k = tid % N;
+    if (tid < D * N) {
+        ival t = pt(0.0);
+        for (int l = 0; l <= k; l++) ipfma(t, pt(S.Tc[i][l]), S.un.rn.Hm[l][k]);
+        tc2 = mid_ru(t);
+        ival rr = isub(t, pt(tc2));
+        for (int l = 0; l <= k; l++) ipfma(rr, S.R[i][l], S.un.rn.Hm[l][k]);
+#pragma unroll
+        for (int j = 0; j < D; j++) {
+            ival u = pt(0.0);
+            for (int l = 0; l <= k; l++) ipfma(u, pt(S.Th[j][i][l]), S.un.rn.Hm[l][k]);
+            th2[j] = mid_ru(u);
+            rr = iadd(rr, imul_nl(isub(u, pt(th2[j])), S.r0[j]));
+        }
+        r2 = rr;
+    } else if (tid >= 32 && tid < 32 + N * N) {
+        const int jj = (tid - 32) / N, kk = (tid - 32) % N;
+        ival t = pt(0.0);
+        for (int l = 0; l <= kk; l++) ipfma(t, S.Err[jj][l], S.un.rn.Hm[l][kk]);
+        e2 = t;
+        ival a = pt(0.0);
+        for (int l = jj; l < N; l++) a = iadd(a, imul_nl(S.un.rn.Hi[jj][l], S.G[l][kk]));
+        g2 = a;
+    } else if (tid == 32 + N * N) {
+        ival c = S.sc;
+        for (int q = 0; q < N; q++) c = imul_nl(c, S.un.rn.Hi[q][q]);
+        S.sc = c;
+        S.renorms = S.renorms + 1;
+    }
+    __syncthreads();
+    if (tid < D * N) {
+        S.Tc[i][k] = tc2; S.R[i][k] = r2;
+#pragma unroll
+        for (int j = 0; j < D; j++) S.Th[j][i][k] = th2[j];
+    } else if (tid >= 32 && tid < 32 + N * N) {
+        const int jj = (tid - 32) / N, kk = (tid - 32) % N;
+        S.Err[jj][kk] = e2; S.Errm[jj][kk] = iv2mt(e2); S.G[jj][kk] = g2;
+    }
+    __syncthreads();
+}
+
 // phi' = (v, F(u)) over the sub-interval [tl,th] of the step and over the whole set (last column of the first / last frame,
 // topFrame.cpp:265-331), row i:  phi(tau) in phi_c(tau) + Psi(tau;xi)(phi0 - x),  |Psi(tau;xi) - Psi_c(tau)| <= g1 tau |phi0 - x|_1
 template <int N>
@@ -926,7 +1032,8 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
     }
     for (int t = tid; t < (int)(sizeof(ccp_front_result) / 8); t += NT) reinterpret_cast<double*>(gres)[t] = 0.0;
     __syncthreads();                                // the descriptor (un.desc) is dead from here on
-    if (tid == 0) { S.mj = majorant<N>(S.bpar, S.cpar, p, h); S.flag = 0; }
+    if (tid == 0) { S.mj = majorant<N>(S.bpar, S.cpar, p, h); S.flag = 0; S.renorms = 0; S.sc = pt(1.0); }
+    if (tid >= 32 && tid < 32 + N * N) { const int t = tid - 32; S.G[t / N][t % N] = pt(t / N == t % N ? 1.0 : 0.0); }
     if (tid == 32) majorant2<N>(S.bpar, S.cpar, h, S.g15);
     if (tid < N) {                                  // oracle/c2.hpp:make_par
         const int i = tid;
@@ -1006,6 +1113,7 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
     cs0 = opaque(cs0); cs1 = opaque(cs1); cs2 = opaque(cs2); rowV = opaque(rowV); rowU = opaque(rowU); rowZ = opaque(rowZ);
 
     const int Stot = step_count(L_minus, h);
+    const int renorm_mask = (1 << step_log2) - 1;            // basis renormalisation once per unit of time
     int zero_count = 0, failure_count = 0, first_failure = -1, n_conj = 0;      // maintained by thread 0
     ival tprev = pt(0.0);
     int cur = 0;
@@ -1317,7 +1425,8 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
             for (int a = 0; a < N; a++)
 #pragma unroll
                 for (int bb = 0; bb < N; bb++) Fm[a][bb] = (t == 0) ? S.Fk[0][a][bb] : EV[(t * N + a) * N + bb];
-            DT[t] = Det<N>::det(Fm);
+            const ival dt = Det<N>::det(Fm);
+            DT[t] = S.renorms ? imul_nl(dt, S.sc) : dt;          // determinant of the TRUE frame (renormalise)
         }
         __syncthreads();
         // ---- topFrame::countZeros decision per sub-interval (threads 0..g-1), tally by thread 0.  As in the reference the
@@ -1341,6 +1450,7 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
                         for (int bb = 0; bb < N; bb++) Fm[a][bb] = EV[((g + 1 + gi) * N + a) * N + bb];
                     deriv_entries<N>(&S.Fk[0][0][0], &S.boxFd[0][0], p, tl, th, Dm);
                     dD = jacobi_derivative<N>(Fm, Dm);
+                    if (S.renorms) dD = imul_nl(dD, S.sc);
                 }
                 decision = count_decide(timeI, dL, dR, dV, dD);
                 if (!(ifinite(dL) && ifinite(dR) && ifinite(dV) && ifinite(dD))) decision |= 4;
@@ -1377,14 +1487,33 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
         TRC(8);
         tprev = mk(__dadd_rd(tprev.lo, hs), __dadd_ru(tprev.hi, hs));
         cur = nxt;
+        if (g > 0 && !last && status == CCP_OK && ((s + 1) & renorm_mask) == 0) renormalise<N>(S);
         if (last && status == CCP_OK) {            // topFrame::getLastFrame: frame and front point at the end of the last step
             constexpr int ld = CCP_MAX_N + 2;
             for (int t = tid; t < D * N; t += NT) {
                 const int rr = t / N, k = t % N;
                 ival s0;
-                gres->last_frame[rr * ld + k] = toc(frame_entry<N>(S, rr, k, &s0));
+                ival wl = frame_entry<N>(S, rr, k, &s0);
                 // C^1 flow map times A_u (boundaryValueProblem::DGxy): unstable columns (Tc + sum_j Theta_j r0_j) + R, stable columns Ps
-                gres->flow_P[rr * CCP_MAX_DIM + k] = toc(iadd(iadd(pt(S.Tc[rr][k]), s0), S.R[rr][k]));
+                ival tu = iadd(iadd(pt(S.Tc[rr][k]), s0), S.R[rr][k]);
+                if (S.renorms) {
+                    // back to the basis A_u of the descriptor, piece by piece so that the affine dependence on r0 survives:
+                    //   T = (Tc G) + sum_j (Theta_j G) r0_j + R G ;   W = T + Ps Err_0   (Err_0 = the descriptor's Eu_err; Err = Err_0 G^-1)
+                    ival tc = pt(0.0), rg = pt(0.0), sj = pt(0.0);
+                    for (int l = 0; l <= k; l++) ipfma(tc, S.G[l][k], S.Tc[rr][l]);
+                    for (int j = 0; j < D; j++) {
+                        ival th = pt(0.0);
+                        for (int l = 0; l <= k; l++) ipfma(th, S.G[l][k], S.Th[j][rr][l]);
+                        sj = iadd(sj, imul_nl(th, S.r0[j]));
+                    }
+                    for (int l = 0; l <= k; l++) rg = iadd(rg, imul_nl(S.R[rr][l], S.G[l][k]));
+                    tu = iadd(iadd(tc, sj), rg);
+                    acc4 e = acc_zero();
+                    for (int j = 0; j < N; j++) acc_term(e, iv2mt(S.Ps[rr][j]), iv2mt(fromc(gdesc->Eu_err[j * CCP_MAX_N + k])));
+                    wl = iadd(tu, acc_finish(e));
+                }
+                gres->last_frame[rr * ld + k] = toc(wl);
+                gres->flow_P[rr * CCP_MAX_DIM + k] = toc(tu);
                 gres->flow_P[rr * CCP_MAX_DIM + N + k] = toc(S.Ps[rr][k]);
             }
             if (tid < D) {

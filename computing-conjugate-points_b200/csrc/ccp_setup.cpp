@@ -217,7 +217,7 @@ static int setup_one(int n, const double* params, const ccp_setup_opts* o, ccp_f
     double scale  = (o && o->scale > 0) ? o->scale : (n == 2 ? 0.000016 : 0.000001);        // heteroclinic.cpp:80-87
     double coneL  = (o && o->cone_L > 0) ? o->cone_L : (n == 2 ? 0.00008 : 0.000015);
     double eigerr = (o && o->eig_err >= 0) ? o->eig_err : (n == 2 ? 2e-4 : 2e-5);
-    double xynbd  = (o && o->xy_nbd >= 0) ? o->xy_nbd : 1e-19;
+    double xynbd  = (o && o->xy_nbd >= 0) ? o->xy_nbd : 1e-12;              // XY_nbd x-part +-1e-12
     double pct    = (o && o->L_minus_percent > 0) ? o->L_minus_percent : 0.84;
     int newton    = (o && o->newton_steps > 0) ? o->newton_steps : 20;
 

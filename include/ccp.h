@@ -178,7 +178,8 @@ double ccp_front_flops(int n, int order, int grid, int steps);
    Re-states stage (i) of computeFrontAndConjugatePoints (heteroclinic.cpp:96-191, 324) in plain
    doubles so that synthetic sweeps can be generated without CAPD.  Not part of the timed path. */
 typedef struct {
-    double xy_nbd;        /* +- radius of the validated BVP neighbourhood in x (local coords)           */
+    double xy_nbd;        /* +- radius of the validated BVP neighbourhood in x (local coords); <0 -> 1e-12
+                             (the Krawczyk stage of host/ccp_bvp.hpp delivers 1e-13 .. 3e-13)  */
     double cone_L;        /* cone constant L (heteroclinic.cpp:80-87); <=0 -> reference default per n   */
     double eig_err;       /* +- magnitude of Eu_m_Error_Final entries; <0 -> 2e-4 (n=2) / 2e-5 (n>=3)   */
     double scale;         /* manifold scale; <=0 -> reference default per n                             */

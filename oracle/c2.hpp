@@ -160,6 +160,49 @@ static inline void frame_of_state(int n, const double (*Tc)[MAXN], const double 
     }
 }
 
+// ---- basis renormalisation of the frame (once per unit of time) ----
+// The columns of T = Dphi_t A_u all align with the fastest unstable direction (condition number ~1e5 at L_-), so the interval
+// determinant of the hull of T loses every digit as soon as the relative width of the entries (box of the front, amplified by
+// e^{lambda t}) exceeds 1/cond -- with the validated neighbourhood of the connecting orbit (1e-13 .. 1e-12) that is the last third
+// of the front.  The frame is only a BASIS of E^u: for any invertible point matrix H, det(top(T)) = det(top(T H)) / det(H), zeros and
+// (for det H > 0) signs unchanged.  H = (R factor of a floating-point Gram-Schmidt of Tc)^-1 is computed in round-to-nearest
+// (any H is valid; only determinism matters) and applied rigorously to every piece of the frame representation:
+//     Tc <- mid([Tc H]),  Theta_j <- mid([Theta_j H]),  R <- R H + residuals,  Err <- Err H   (Ps Err H = Ps (Err H)).
+// G encloses the product of the H^-1 (true frame = normalised frame * G, used for getLastFrame), sc encloses det(G).
+static inline bool renorm_matrix(int n, const double (*Tc)[MAXN], double (*H)[MAXN]) {
+    RoundNearestGuard rn;
+    const int D = 2 * n;
+    double Q[MAXD][MAXN], Rt[MAXN][MAXN];
+    for (int k = 0; k < n; k++) {
+        double v[MAXD];
+        for (int i = 0; i < D; i++) v[i] = Tc[i][k];
+        for (int m = 0; m < k; m++) {
+            double dp = 0.0;
+            for (int i = 0; i < D; i++) dp = dp + Q[i][m] * v[i];
+            Rt[m][k] = dp;
+            for (int i = 0; i < D; i++) v[i] = v[i] - dp * Q[i][m];
+        }
+        double nn = 0.0;
+        for (int i = 0; i < D; i++) nn = nn + v[i] * v[i];
+        nn = std::sqrt(nn);
+        if (!(nn > 0.0) || !std::isfinite(nn)) return false;
+        Rt[k][k] = nn;
+        for (int i = 0; i < D; i++) Q[i][k] = v[i] / nn;
+    }
+    for (int k = 0; k < n; k++) {                         // H = Rt^-1, upper triangular, positive diagonal
+        for (int i = 0; i < n; i++) H[i][k] = 0.0;
+        H[k][k] = 1.0 / Rt[k][k];
+        for (int i = k - 1; i >= 0; i--) {
+            double a = 0.0;
+            for (int m = i + 1; m <= k; m++) a = a + Rt[i][m] * H[m][k];
+            H[i][k] = (-a) / Rt[i][i];
+        }
+    }
+    for (int k = 0; k < n; k++) for (int i = 0; i <= k; i++) if (!std::isfinite(H[i][k])) return false;
+    for (int k = 0; k < n; k++) if (!(H[k][k] > 0.0)) return false;
+    return true;
+}
+
 static inline void run_front(const ccp_front_desc& d, ccp_front_result& res, std::vector<ccp_series_rec>* series) {
     std::memset(&res, 0, sizeof(res));
     res.first_failure = -1;
@@ -196,6 +239,10 @@ static inline void run_front(const ccp_front_desc& d, ccp_front_result& res, std
     r0m[D] = ptm(1.0);
     for (int j = 0; j < n; j++) for (int k = 0; k < n; k++) Errm[j][k] = iv2mt(Err[j][k]);
 
+    ival G[MAXN][MAXN], sc(1.0);                              // true frame = normalised frame * G ;  sc encloses det G > 0
+    for (int i = 0; i < n; i++) for (int k = 0; k < n; k++) G[i][k] = ival(i == k ? 1.0 : 0.0);
+    int renorms = 0;
+    const int renorm_mask = (1 << d.step_log2) - 1;         // once per unit of time
     Counter cnt;
     ival tprev(0.0);
     static thread_local PhiTables ct;
@@ -337,9 +384,11 @@ static inline void run_front(const ccp_front_desc& d, ccp_front_result& res, std
             }
             ival time(add_rd(tprev.lo, tl), add_ru(tprev.hi, th));
             ival dL = detN(FL, n), dR = detN(FR, n), dV = detN(FV, n);
+            if (renorms) { dL = dL * sc; dR = dR * sc; dV = dV * sc; }              // determinants of the TRUE frame
             const ival LR = dL * dR;
             const bool need_D = (series != nullptr) || !(LR.lo > 0 && definite(dV));
             ival dD = need_D ? jacobi_derivative(FV, FD, n) : ival(0.0);
+            if (renorms && need_D) dD = dD * sc;
             int idx = s * g + i;
             count_step(cnt, idx, time, dL, dR, dV, dD);
             if (series) { ccp_series_rec rec; rec.time = toc(time); rec.det_L = toc(dL); rec.det_R = toc(dR); rec.det_V = toc(dV); rec.det_D = toc(dD); series->push_back(rec); }
@@ -445,13 +494,62 @@ static inline void run_front(const ccp_front_desc& d, ccp_front_result& res, std
             for (int k = 0; k < n; k++) { Tc[i][k] = Tcn[i][k]; R[i][k] = Rn[i][k]; Ps[i][k] = Psn[i][k]; for (int j = 0; j < D; j++) Th[j][i][k] = Thn[j][i][k]; }
         }
         tprev = ival(add_rd(tprev.lo, hs), add_ru(tprev.hi, hs));
+        if (g > 0 && !last && ((s + 1) & renorm_mask) == 0) {
+            double Hm[MAXN][MAXN];
+            if (renorm_matrix(n, Tc, Hm)) {
+                double Tc2[MAXD][MAXN]; ival R2[MAXD][MAXN];
+                static thread_local double Th2[MAXD][MAXD][MAXN];
+                for (int i = 0; i < D; i++) for (int k = 0; k < n; k++) {
+                    ival t(0.0); for (int l = 0; l <= k; l++) ipfma(t, ival(Tc[i][l]), Hm[l][k]);
+                    Tc2[i][k] = mid_ru(t);
+                    ival rr = t - ival(Tc2[i][k]);
+                    for (int l = 0; l <= k; l++) ipfma(rr, R[i][l], Hm[l][k]);
+                    for (int j = 0; j < D; j++) {
+                        ival u(0.0); for (int l = 0; l <= k; l++) ipfma(u, ival(Th[j][i][l]), Hm[l][k]);
+                        Th2[j][i][k] = mid_ru(u);
+                        rr = rr + (u - ival(Th2[j][i][k])) * r0[j];
+                    }
+                    R2[i][k] = rr;
+                }
+                ival Err2[MAXN][MAXN], Hi[MAXN][MAXN], G2[MAXN][MAXN];
+                for (int j = 0; j < n; j++) for (int k = 0; k < n; k++) { ival t(0.0); for (int l = 0; l <= k; l++) ipfma(t, Err[j][l], Hm[l][k]); Err2[j][k] = t; }
+                for (int k = 0; k < n; k++) {                     // interval inverse of the upper triangular point matrix H
+                    for (int i = 0; i < n; i++) Hi[i][k] = ival(0.0);
+                    Hi[k][k] = ival(div_rd(1.0, Hm[k][k]), div_ru(1.0, Hm[k][k]));
+                    for (int i = k - 1; i >= 0; i--) {
+                        ival a(0.0); for (int m = i + 1; m <= k; m++) ipfma(a, Hi[m][k], Hm[i][m]);
+                        Hi[i][k] = (-a) / ival(Hm[i][i]);
+                    }
+                }
+                for (int i = 0; i < n; i++) for (int k = 0; k < n; k++) { ival a(0.0); for (int l = i; l < n; l++) a = a + Hi[i][l] * G[l][k]; G2[i][k] = a; }
+                for (int k = 0; k < n; k++) sc = sc * Hi[k][k];
+                for (int i = 0; i < D; i++) for (int k = 0; k < n; k++) { Tc[i][k] = Tc2[i][k]; R[i][k] = R2[i][k]; for (int j = 0; j < D; j++) Th[j][i][k] = Th2[j][i][k]; }
+                for (int j = 0; j < n; j++) for (int k = 0; k < n; k++) { Err[j][k] = Err2[j][k]; Errm[j][k] = iv2mt(Err2[j][k]); G[j][k] = G2[j][k]; }
+                renorms++;
+            }
+        }
         if (last) {   // topFrame::getLastFrame (topFrame.cpp:265-299): frame and front point at the end of the last step
             const int ld = CCP_MAX_N + 2;
             ival S1[MAXD][MAXN], Wl[MAXD][MAXN];
             frame_of_state(n, Tc, Th, R, Ps, r0, Errm, S1, Wl);
             for (int rr = 0; rr < D; rr++) for (int k = 0; k < n; k++) {
-                res.last_frame[rr * ld + k] = toc(Wl[rr][k]);
-                res.flow_P[rr * CCP_MAX_DIM + k] = toc((ival(Tc[rr][k]) + S1[rr][k]) + R[rr][k]);      // [D Phi_T(set)] A_u: unstable columns
+                ival wl = Wl[rr][k], tu = (ival(Tc[rr][k]) + S1[rr][k]) + R[rr][k];
+                if (renorms) {
+                    // back to the basis A_u of the descriptor, piece by piece so that the affine dependence on r0 survives:
+                    //   T = (Tc G) + sum_j (Theta_j G) r0_j + R G ;   W = T + Ps Err_0   (Err_0 = the descriptor's Eu_err; Err = Err_0 G^-1)
+                    ival tc(0.0), rg(0.0), sj(0.0);
+                    for (int l = 0; l <= k; l++) ipfma(tc, G[l][k], Tc[rr][l]);
+                    for (int j = 0; j < D; j++) {
+                        ival th(0.0); for (int l = 0; l <= k; l++) ipfma(th, G[l][k], Th[j][rr][l]);
+                        sj = sj + th * r0[j];
+                    }
+                    for (int l = 0; l <= k; l++) rg = rg + R[rr][l] * G[l][k];
+                    tu = (tc + sj) + rg;
+                    acc4 e; for (int j = 0; j < n; j++) acc_term(e, iv2mt(Ps[rr][j]), iv2mt(fromc(d.Eu_err[j * CCP_MAX_N + k])));
+                    wl = tu + acc_finish(e);
+                }
+                res.last_frame[rr * ld + k] = toc(wl);
+                res.flow_P[rr * CCP_MAX_DIM + k] = toc(tu);                                             // [D Phi_T(set)] A_u: unstable columns
                 res.flow_P[rr * CCP_MAX_DIM + n + k] = toc(Ps[rr][k]);                                  // stable columns
             }
             for (int i = 0; i < D; i++) {

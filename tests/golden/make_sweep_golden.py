@@ -12,7 +12,8 @@ sys.path.insert(0, ROOT)
 import __graft_entry__ as g
 
 pkg = g.load_package(); orc = g.load_oracle(); orc.lib(pkg.abi)
-descs, _ = pkg.setup_sweep(3, pkg.parameter_list(128, 8, 0.02, 0.06))
+# thin box (xy_nbd = 1e-19): the box on which the reference-structured algorithm certifies (tests/conftest.py:thin_opts)
+descs, _ = pkg.setup_sweep(3, pkg.parameter_list(128, 8, 0.02, 0.06), pkg.abi.SetupOpts.default(xy_nbd=1e-19))
 res, sec = orc.run_batch(pkg.abi, descs, orc.MODE_REF, threads=0)
 dst = os.path.join(os.path.dirname(os.path.abspath(__file__)), "sweep1024_ref.npz")
 np.savez_compressed(dst, status=np.array([r.status for r in res], np.int32), zero_count=np.array([r.zero_count for r in res], np.int32),

@@ -43,7 +43,8 @@ def _float_flow(n, params, x0, A, T):
 
 
 def _front_set(pkg, n, params):
-    desc, _ = pkg.setup_front(n, params)
+    # thin box: these are properties of the flow map itself (the boundary-value stage brings its own boxes), with tolerances sized for it
+    desc, _ = pkg.setup_front(n, params, pkg.abi.SetupOpts.default(xy_nbd=1e-19))
     D = 2 * n
     p_i = np.array([[desc.p_i[i].lo, desc.p_i[i].hi] for i in range(D)])
     Uxy = np.array([[desc.Uxy[i].lo, desc.Uxy[i].hi] for i in range(D)])

@@ -148,14 +148,16 @@ def test_compute_front_and_conjugate_points_on_gpu(pkg):
 def test_batch_driver_against_oracle_backend(pkg, orc):
     """computeFrontAndConjugatePointsBatch (host/ccp_driver.hpp): the complete proof for a sweep with all fronts in lock-step launches
     (SampleParameters, heteroclinic.cpp:429-491), against the oracle twins of the kernels: 6 fronts of Construct_ParameterList(6, 1);
-    the batch must reproduce the single-front driver's code on the probed fronts (codes 2 -2 1 -3 -2 1: with the reference's default
-    constants some fronts fail a stage, as in the reference's own sweep where such fronts are plotted as -1)."""
+    the batch must reproduce the single-front driver's code on the probed fronts (codes 2 -2 1 0 -2 1: the two fronts with c12 ~ 0 are
+    degenerate for the boundary-value stage and end with -2, as in the reference's own sweep where such fronts are plotted as -1; the
+    fourth front, (-c12, -c23), ended with -3 before the frame basis was renormalised once per unit of time (oracle/c2.hpp) and is now
+    proven to have no conjugate point with the rigorous Krawczyk neighbourhood)."""
     exe = os.path.join(ROOT, "tests", "cpp", "driver_sweep_dry")
     _build_with_oracle_backend(pkg, "driver_sweep_gpu.cpp", exe)
     r = subprocess.run([exe, "6", "1"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "batch == single-front driver on the probed fronts" in r.stdout
-    assert "codes: 2 -2 1 -3 -2 1" in r.stdout
+    assert "codes: 2 -2 1 0 -2 1" in r.stdout
     # the two-component system: a front with one conjugate point, a stable front (0, proven end to end), another with one
     r = subprocess.run([exe, "n2"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
