@@ -18,7 +18,9 @@ from .abi import FrontDesc, FrontResult, SeriesRec, SetupOpts, SetupInfo, Interv
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libccp_b200.so")
+SETUP_LIB_PATH = os.path.join(PKG_DIR, "libccp_setup.so")
 _lib = None
+_setup_lib = None
 
 
 class CcpError(RuntimeError):
@@ -46,9 +48,21 @@ def lib():
     return _lib
 
 
+def setup_lib():
+    """libccp_setup.so: the host-only descriptor generator (include/ccp_setup.h).  CPU-only consumers (the reference arm of
+    bench.py, the oracle tests) use this without ever mapping the CUDA library."""
+    global _setup_lib
+    if _setup_lib is None:
+        if not os.path.exists(SETUP_LIB_PATH):
+            raise CcpError("libccp_setup.so not built: run __graft_entry__.build()")
+        _setup_lib = abi.bind(C.CDLL(SETUP_LIB_PATH), abi.SETUP_SYMBOLS)
+    return _setup_lib
+
+
 def _check(rc, what):
     if rc != 0:
-        raise CcpError("%s failed with code %d: %s" % (what, rc, lib().ccp_last_error().decode()))
+        detail = lib().ccp_last_error().decode() if _lib is not None else ""
+        raise CcpError("%s failed with code %d: %s" % (what, rc, detail))
 
 
 # ----------------------------------------------------------------------------- descriptors (host only)
@@ -56,7 +70,7 @@ def parameter_list(N_c=24, N_r=4, r_min=0.02, r_max=0.06, b=(1.0, 0.975, 0.95)):
     """Construct_ParameterList (heteroclinic.cpp:386-427): N_c*N_r vectors (b1,b2,b3,c12,c23)."""
     out = np.zeros((N_c * N_r, 5), dtype=np.float64)
     b3 = (C.c_double * 3)(*b)
-    _check(lib().ccp_parameter_list(N_c, N_r, r_min, r_max, b3, out.ctypes.data_as(C.POINTER(C.c_double))), "ccp_parameter_list")
+    _check(setup_lib().ccp_parameter_list(N_c, N_r, r_min, r_max, b3, out.ctypes.data_as(C.POINTER(C.c_double))), "ccp_parameter_list")
     return out
 
 
@@ -67,7 +81,7 @@ def setup_sweep(n, params, opts=None, threads=0):
     descs = (FrontDesc * m)()
     infos = (SetupInfo * m)()
     o = opts if opts is not None else SetupOpts.default()
-    _check(lib().ccp_setup_sweep(n, params.ctypes.data_as(C.POINTER(C.c_double)), m, C.byref(o), descs, infos, threads), "ccp_setup_sweep")
+    _check(setup_lib().ccp_setup_sweep(n, params.ctypes.data_as(C.POINTER(C.c_double)), m, C.byref(o), descs, infos, threads), "ccp_setup_sweep")
     return descs, infos
 
 
@@ -193,17 +207,40 @@ class Engine:
     """One process, one GPU.  `frame_count_batch` is the drop-in for the reference's serial loop over
     `computeFrontAndConjugatePoints -> E_u.frameDet(...)` (heteroclinic.cpp:334,449-471)."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, n_devices=None):
+        """`device`: the GPU this process is bound to (one process per GPU, as under torchrun).  `n_devices` (instead): ONE process
+        drives GPUs 0..n_devices-1 (0 = all visible) through ccp_init_multi; `frame_count_batch_multi` then shards a batch over them."""
         L = lib()
         if L.ccp_device_count() <= 0:
             raise CcpError("no CUDA device visible: ccp_b200 has no CPU fallback")
-        _check(L.ccp_init(device), "ccp_init")
+        if n_devices is None:
+            _check(L.ccp_init(device), "ccp_init")
+        else:
+            _check(L.ccp_init_multi(n_devices), "ccp_init_multi")
         self.L = L
+
+    def bound_devices(self):
+        return int(self.L.ccp_bound_devices())
 
     def frame_count_batch(self, descs):
         m = len(descs)
         res = (FrontResult * m)()
         _check(self.L.ccp_frame_count_batch(descs, m, res), "ccp_frame_count_batch")
+        return res
+
+    def frame_count_batch_multi(self, descs):
+        """The batch over every bound GPU (front f on device f mod n_devices); records in front order."""
+        m = len(descs)
+        res = (FrontResult * m)()
+        _check(self.L.ccp_frame_count_batch_multi(descs, m, res), "ccp_frame_count_batch_multi")
+        return res
+
+    def frame_count_subdivided(self, descs, parts, which=abi.CCP_SUBDIV_UXY):
+        """BASELINE config 4: every front's box cut into parts**n sub-boxes (the reference's part() rule), each propagated and counted
+        independently, hull / tally per parameter on the device.  Returns one abi.SubdivResult per front."""
+        m = len(descs)
+        res = (abi.SubdivResult * m)()
+        _check(self.L.ccp_frame_count_subdivided(descs, m, parts, which, res), "ccp_frame_count_subdivided")
         return res
 
     def bound_dfu_batch(self, descs):
@@ -213,9 +250,14 @@ class Engine:
         _check(self.L.ccp_bound_dfu_batch(descs, m, res), "ccp_bound_dfu_batch")
         return res
 
-    def frame_count_batch_device(self, d_descs_ptr, m, d_results_ptr, stream_ptr=None):
-        _check(self.L.ccp_frame_count_batch_device(C.c_void_p(d_descs_ptr), m, C.c_void_p(d_results_ptr),
-                                                   C.c_void_p(stream_ptr) if stream_ptr else None), "ccp_frame_count_batch_device")
+    def frame_count_batch_device(self, d_descs_ptr, m, d_results_ptr, stream_ptr=None, n=None):
+        """Device-resident batch.  With `n` (components, uniform over the batch) the call only enqueues; without it the library reads
+        n from the first descriptor (a 4-byte copy and one stream synchronisation)."""
+        st = C.c_void_p(stream_ptr) if stream_ptr else None
+        if n is None:
+            _check(self.L.ccp_frame_count_batch_device(C.c_void_p(d_descs_ptr), m, C.c_void_p(d_results_ptr), st), "ccp_frame_count_batch_device")
+        else:
+            _check(self.L.ccp_frame_count_batch_device_n(C.c_void_p(d_descs_ptr), m, C.c_void_p(d_results_ptr), st, n), "ccp_frame_count_batch_device_n")
 
     def frame_count_series(self, desc, cap=None):
         res = FrontResult()

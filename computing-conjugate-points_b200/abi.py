@@ -95,15 +95,35 @@ class DfuResult(C.Structure):
     _fields_ = [("status", C.c_int32), ("parts", C.c_int32), ("DF", Interval * (CCP_MAX_DIM * CCP_MAX_DIM))]
 
 
+CCP_SUBDIV_UXY, CCP_SUBDIV_EU_ERR = 0, 1
+
+
+class SubdivResult(C.Structure):
+    """Hull / tally of the sub-boxes of one parameter (include/ccp.h: ccp_subdiv_result)."""
+    _fields_ = [
+        ("status", C.c_int32), ("sub_boxes", C.c_int32), ("certified", C.c_int32), ("zero_count", C.c_int32),
+        ("zero_min", C.c_int32), ("zero_max", C.c_int32), ("failures", C.c_int32), ("steps", C.c_int32),
+        ("last_frame", Interval * (CCP_MAX_DIM * (CCP_MAX_N + 2))),
+        ("first_frame", Interval * (CCP_MAX_DIM * (CCP_MAX_N + 1))),
+        ("det_first", Interval), ("det_last", Interval),
+        ("flow_P", Interval * (CCP_MAX_DIM * CCP_MAX_DIM)),
+    ]
+
+
 # every symbol include/ccp.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "ccp_device_count": (C.c_int, []),
     "ccp_init": (C.c_int, [C.c_int]),
+    "ccp_init_multi": (C.c_int, [C.c_int]),
+    "ccp_bound_devices": (C.c_int, []),
     "ccp_shutdown": (None, []),
     "ccp_last_error": (C.c_char_p, []),
     "ccp_version": (C.c_char_p, []),
     "ccp_frame_count_batch": (C.c_int, [C.POINTER(FrontDesc), C.c_size_t, C.POINTER(FrontResult)]),
+    "ccp_frame_count_batch_multi": (C.c_int, [C.POINTER(FrontDesc), C.c_size_t, C.POINTER(FrontResult)]),
     "ccp_frame_count_batch_device": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "ccp_frame_count_batch_device_n": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int]),
+    "ccp_frame_count_subdivided": (C.c_int, [C.POINTER(FrontDesc), C.c_size_t, C.c_int, C.c_int, C.POINTER(SubdivResult)]),
     "ccp_frame_count_series": (C.c_int, [C.POINTER(FrontDesc), C.POINTER(FrontResult), C.POINTER(SeriesRec), C.c_size_t, C.POINTER(C.c_size_t)]),
     "ccp_bound_dfu_batch": (C.c_int, [C.POINTER(DfuDesc), C.c_size_t, C.POINTER(DfuResult)]),
     "ccp_kernel_launches": (C.c_uint64, []),
@@ -111,14 +131,18 @@ SYMBOLS = {
     "ccp_debug_primitives": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_size_t]),
     "ccp_measure_fp64_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
     "ccp_front_flops": (C.c_double, [C.c_int, C.c_int, C.c_int, C.c_int]),
+}
+
+# every symbol include/ccp_setup.h declares (libccp_setup.so: host-only descriptor generator)
+SETUP_SYMBOLS = {
     "ccp_setup_front": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(SetupOpts), C.POINTER(FrontDesc), C.POINTER(SetupInfo)]),
     "ccp_setup_sweep": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.c_size_t, C.POINTER(SetupOpts), C.POINTER(FrontDesc), C.POINTER(SetupInfo), C.c_int]),
     "ccp_parameter_list": (C.c_int, [C.c_int, C.c_int, C.c_double, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 
 
-def bind(lib):
-    for name, (res, args) in SYMBOLS.items():
+def bind(lib, symbols=None):
+    for name, (res, args) in (SYMBOLS if symbols is None else symbols).items():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args

@@ -1002,7 +1002,8 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
     const int p = S.un.desc.order, g = S.un.desc.grid, step_log2 = S.un.desc.step_log2;
     const double L_minus = S.un.desc.L_minus;
     int status = CCP_OK;
-    if (S.un.desc.n != N || p < 2 || p > CCP_MAX_ORDER || g < 0 || g > GMAX || step_log2 < 1 || step_log2 > 20 || !(L_minus > 0) || !isfinite(L_minus))
+    if (S.un.desc.n != N || p < 2 || p > CCP_MAX_ORDER || g < 0 || g > GMAX || step_log2 < 1 || step_log2 > 20 || !(L_minus > 0) || !isfinite(L_minus) ||
+        ldexp(L_minus, step_log2) > 16777216.0)          // more than 2^24 steps: the 32-bit step and sub-interval counters would overflow
         status = CCP_ST_BAD_DESC;
     if (status != CCP_OK) {
         __syncthreads();
@@ -1533,7 +1534,7 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
 }
 
 template <int N>
-__global__ void __launch_bounds__(NT, 7) front_kernel(const ccp_front_desc* __restrict__ descs, ccp_front_result* __restrict__ results,
+__global__ void __launch_bounds__(NT, (N == 4 ? 4 : (N == 3 ? 7 : 8))) front_kernel(const ccp_front_desc* __restrict__ descs, ccp_front_result* __restrict__ results,
                                                       const int* __restrict__ index, int count, ccp_series_rec* series, int series_cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FrontSmem<N>& S = *reinterpret_cast<FrontSmem<N>*>(smem_raw);

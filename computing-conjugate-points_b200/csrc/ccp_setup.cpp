@@ -15,7 +15,7 @@
 //   getPointNbd / constructU                     localManifold.cpp:4-41,73-102
 // Error-box magnitudes that the reference obtains from its validation stages (Krawczyk
 // neighbourhood, eigenfunction error) are inputs here (ccp_setup_opts), see SURVEY.md 8(d).
-#include "../../include/ccp.h"
+#include "../../include/ccp_setup.h"
 #include <cmath>
 #include <cstring>
 #include <cfloat>

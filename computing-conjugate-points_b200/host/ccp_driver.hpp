@@ -13,6 +13,7 @@
 // -3 count failed, -4 L_+, -5 below L_-.
 #pragma once
 #include "ccp_l_plus.hpp"
+#include "../../include/ccp_setup.h"
 
 namespace ccp_host {
 

@@ -77,11 +77,14 @@ class topFrame {
 
 class propagateManifold {
   public:
-    // Host-side stages that stay in the caller's (CAPD) code; defaults accept.
-    //   below_Lminus : localManifold_Eig::checkConjugatePointsBelowLminus   (propagateManifold.cpp:145)
-    //   L_plus       : propagateManifold::lastEuFrame(A_frame, endPoint_LPlus) (propagateManifold.cpp:170, :192-240)
-    std::function<bool()> below_Lminus = [] { return true; };
-    std::function<bool(const topFrame&, const IVector&)> L_plus = [](const topFrame&, const IVector&) { return true; };
+    // Host-side stages that stay in the caller's code.  They are part of the proof and therefore MANDATORY: frameDet / frameDetBatch
+    // throw std::logic_error while a hook is unset -- a forgotten hook must never turn into a "validated" count.
+    //   below_Lminus : localManifold_Eig::checkConjugatePointsBelowLminus   (propagateManifold.cpp:145)      -> -5 when false
+    //   L_plus       : propagateManifold::lastEuFrame(A_frame, endPoint_LPlus) (propagateManifold.cpp:170, :192-240) -> -4 when false
+    // (host/ccp_local_manifold_eig.hpp and host/ccp_l_plus.hpp provide both without CAPD.)  frameDetUnchecked / frameDetBatchUnchecked
+    // are the explicit opt-out for tests and benchmarks of the count alone: they skip both stages and say so in their name.
+    std::function<bool()> below_Lminus;
+    std::function<bool(const topFrame&, const IVector&)> L_plus;
 
     // The data construct_InitCondU / construct_A_lin read from the CAPD objects (propagateManifold.cpp:6-81):
     //   params            All_parameters_interval          (b_1..b_n, c_12..)
@@ -108,6 +111,7 @@ class propagateManifold {
     // Same contract as the reference: count >= 0, -3 count failed, -4 L_+ failed, -5 below-L_- failed;
     // an engine / enclosure failure throws (the reference's CAPD would throw too; SampleParameters maps it to -10).
     int frameDet(interval L_minus, int grid, const IVector& endPoint_LPlus) {
+        require_hooks();
         if (!below_Lminus()) return -5;
         desc_.L_minus = L_minus.hi; desc_.grid = grid;
         ccp_front_result r{};
@@ -120,6 +124,12 @@ class propagateManifold {
         } else check(ccp_frame_count_batch(&desc_, 1, &r));
         return finish(r, std::move(series), endPoint_LPlus);
     }
+    // The frame count WITHOUT the two host-side proof stages (Prop. 2.5 below L_-, the L_+ condition): not a validated result.
+    int frameDetUnchecked(interval L_minus, int grid) {
+        below_Lminus = [] { return true; };
+        L_plus = [](const topFrame&, const IVector&) { return true; };
+        return frameDet(L_minus, grid, IVector());
+    }
 
     // The sweep of SampleParameters in one launch: all fronts go to the GPU together.
     static std::vector<int> frameDetBatch(std::vector<propagateManifold>& fronts, const std::vector<interval>& L_minus, int grid,
@@ -127,13 +137,19 @@ class propagateManifold {
         std::vector<ccp_front_desc> d(fronts.size());
         std::vector<ccp_front_result> r(fronts.size());
         std::vector<int> out(fronts.size(), -10);
+        for (auto& f : fronts) f.require_hooks();
         for (size_t i = 0; i < fronts.size(); i++) { fronts[i].desc_.L_minus = L_minus[i].hi; fronts[i].desc_.grid = grid; d[i] = fronts[i].desc_; }
-        check(ccp_frame_count_batch(d.data(), d.size(), r.data()));
+        // every GPU bound by ccp_init_multi takes part (front f on device f mod n_devices); with ccp_init it is one device
+        check(ccp_frame_count_batch_multi(d.data(), d.size(), r.data()));
         for (size_t i = 0; i < fronts.size(); i++) {
             if (!fronts[i].below_Lminus()) { out[i] = -5; continue; }
             try { out[i] = fronts[i].finish(r[i], {}, endPoints[i]); } catch (const std::exception&) { out[i] = -10; }
         }
         return out;
+    }
+    static std::vector<int> frameDetBatchUnchecked(std::vector<propagateManifold>& fronts, const std::vector<interval>& L_minus, int grid) {
+        for (auto& f : fronts) { f.below_Lminus = [] { return true; }; f.L_plus = [](const topFrame&, const IVector&) { return true; }; }
+        return frameDetBatch(fronts, L_minus, grid, std::vector<IVector>(fronts.size()));
     }
     const topFrame& frame() const { return frame_; }
     const ccp_front_desc& descriptor() const { return desc_; }
@@ -146,6 +162,10 @@ class propagateManifold {
         if (!L_plus(frame_, endPoint_LPlus)) return -4;
         std::vector<int> cp = frame_.countZeros();
         return cp[1] > 0 ? -3 : cp[0];
+    }
+    void require_hooks() const {
+        if (!below_Lminus || !L_plus)
+            throw std::logic_error("propagateManifold: the below-L_- and L_+ stages are not wired (set below_Lminus and L_plus, or call frameDetUnchecked)");
     }
     static void check(int rc) { if (rc != 0) throw std::runtime_error(std::string("ccp: ") + ccp_last_error()); }
     ccp_front_desc desc_{};

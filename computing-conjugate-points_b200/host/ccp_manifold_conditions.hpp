@@ -74,10 +74,14 @@ inline double maxEigenvalueSym(const IMatrix& Sin) {
         double num = C[i][i].hi, offD = 0;
         for (int j = 0; j < n; j++) if (j != i) { num = ia::up(num + ia::mag(C[i][j])); offD = ia::up(offD + ia::mag(D[i][j])); }
         const double den = ia::dn(D[i][i].lo - offD);
+        // non-finite input (NaN / inf entries) must never certify a bound: NaN compares false everywhere, which would otherwise
+        // leave mu at -inf (euclNorm 0, ml +inf).  +inf is the only sound answer.
+        if (!std::isfinite(num) || !std::isfinite(den) || !std::isfinite(offD) || !std::isfinite(D[i][i].hi)) return INFINITY;
         if (!(den > 0)) return INFINITY;               // D = X^T X strictly diagonally dominant  =>  X invertible (needed for Sylvester)
         // row i of mu D - C is dominant once  mu (D_ii - offD) >= num  for mu >= 0  (any mu >= 0 if num < 0),
         //                                     mu (D_ii + offD) >= num  for mu <  0  (needs num < 0)
         const double mi = (num >= 0) ? ia::up(num / den) : ia::up(num / ia::up(D[i][i].hi + offD));
+        if (!std::isfinite(mi)) return INFINITY;
         mu = std::max(mu, mi);
     }
     return mu;

@@ -117,7 +117,14 @@ enum {
 
 /* ---------------- engine life cycle ---------------- */
 int  ccp_device_count(void);
-int  ccp_init(int device);            /* binds this process to one GPU, creates stream + scratch       */
+int  ccp_init(int device);            /* binds this process to one GPU, creates stream + scratch.  A second call with the
+                                         same device is a no-op; with ANOTHER device it fails with CCP_E_ARG (call
+                                         ccp_shutdown first)                                                          */
+int  ccp_init_multi(int n_devices);   /* binds devices 0..n_devices-1 (<= 0: every visible GPU): one stream and staging per
+                                         device, all driven from the calling host thread.  The reference's sweep is the C++
+                                         loop heteroclinic.cpp:449-471; with this call its replacement uses the whole box
+                                         (ccp_frame_count_batch_multi).  Single-device entry points run on device 0.        */
+int  ccp_bound_devices(void);         /* number of GPUs bound by ccp_init / ccp_init_multi (0 before)                       */
 void ccp_shutdown(void);
 const char* ccp_last_error(void);
 const char* ccp_version(void);
@@ -127,9 +134,43 @@ const char* ccp_version(void);
    batch of fronts: host buffers in, host buffers out (H2D + kernel + D2H inside). */
 int ccp_frame_count_batch(const ccp_front_desc* fronts, size_t n_fronts, ccp_front_result* results);
 
+/* The same batch sharded over every bound GPU (ccp_init_multi): front f runs on device f mod n_devices, no exchange between
+   devices, the records land in `results` in front order.  With one bound device it is ccp_frame_count_batch.              */
+int ccp_frame_count_batch_multi(const ccp_front_desc* fronts, size_t n_fronts, ccp_front_result* results);
+
 /* Same, device-resident: `d_fronts`/`d_results` are device pointers, `stream` a cudaStream_t (or NULL
-   for the engine stream).  Asynchronous: returns after enqueueing.  */
+   for the engine stream); uniform n per batch.  ccp_frame_count_batch_device reads n from the first descriptor (a 4-byte
+   device-to-host copy and one stream synchronisation before the launch); ccp_frame_count_batch_device_n takes n from the
+   caller and only enqueues.  */
 int ccp_frame_count_batch_device(const void* d_fronts, size_t n_fronts, void* d_results, void* stream);
+int ccp_frame_count_batch_device_n(const void* d_fronts, size_t n_fronts, void* d_results, void* stream, int n);
+
+/* ---------------- BASELINE config 4: the initial box subdivided, fused propagate + count, hull / tally on the device ----------------
+   The box of every front is cut into parts^n sub-boxes with the reference's rule part() (utils.cpp:3-10; index rule of getSubdivision,
+   utils.cpp:309-321), each sub-box is propagated and counted independently (same kernel as ccp_frame_count_batch), and the sub-box
+   results of one parameter are reduced on the device: the counts are tallied (the parameter is certified iff every sub-box is certified
+   and all agree) and every enclosure of the result record is replaced by the interval hull over the sub-boxes.                        */
+enum {
+    CCP_SUBDIV_UXY    = 0,   /* the x-part of Uxy: local unstable coordinates of the neighbourhood of the connecting orbit (XY_nbd) */
+    CCP_SUBDIV_EU_ERR = 1    /* the rows of Eu_m_Error_Final (every column cut the same way)                                         */
+};
+typedef struct {
+    int32_t status;        /* worst status over the sub-boxes (CCP_OK = all ran)                                  */
+    int32_t sub_boxes;     /* parts^n                                                                            */
+    int32_t certified;     /* sub-boxes with status CCP_OK and failure_count == 0                                */
+    int32_t zero_count;    /* the common count if every sub-box is certified and all agree, else -1             */
+    int32_t zero_min, zero_max;   /* over the certified sub-boxes (-1 if none)                                  */
+    int32_t failures;      /* sum of failure_count                                                               */
+    int32_t steps;
+    /* interval hulls over the sub-boxes, same layout as ccp_front_result from last_frame on */
+    ccp_interval last_frame[CCP_MAX_DIM * (CCP_MAX_N + 2)];
+    ccp_interval first_frame[CCP_MAX_DIM * (CCP_MAX_N + 1)];
+    ccp_interval det_first, det_last;
+    ccp_interval flow_P[CCP_MAX_DIM * CCP_MAX_DIM];
+} ccp_subdiv_result;
+/* `parts` pieces per coordinate (1..64), `which` = CCP_SUBDIV_*; uniform n over the batch.  Host buffers in / out; the sub-box
+   descriptors and records never leave the device.  Fronts are processed in chunks that fit the device buffers (<= 2^17 sub-boxes). */
+int ccp_frame_count_subdivided(const ccp_front_desc* fronts, size_t n_fronts, int parts, int which, ccp_subdiv_result* results);
 
 /* One front with the full per-sub-interval series (topFrame::makePlot equivalent).  `cap` records
    available in `series`; *len receives steps*grid.  */
@@ -173,42 +214,6 @@ int ccp_measure_fp64_peak(int iters, double* tflops);
 
 /* FP64 work of one front under the implemented algorithm: flop (1 DFMA = 2) */
 double ccp_front_flops(int n, int order, int grid, int steps);
-
-/* ---------------- host-side setup of descriptors (non-rigorous float shooting) ----------------
-   Re-states stage (i) of computeFrontAndConjugatePoints (heteroclinic.cpp:96-191, 324) in plain
-   doubles so that synthetic sweeps can be generated without CAPD.  Not part of the timed path. */
-typedef struct {
-    double xy_nbd;        /* +- radius of the validated BVP neighbourhood in x (local coords); <0 -> 1e-12
-                             (the Krawczyk stage of host/ccp_bvp.hpp delivers 1e-13 .. 3e-13)  */
-    double cone_L;        /* cone constant L (heteroclinic.cpp:80-87); <=0 -> reference default per n   */
-    double eig_err;       /* +- magnitude of Eu_m_Error_Final entries; <0 -> 2e-4 (n=2) / 2e-5 (n>=3)   */
-    double scale;         /* manifold scale; <=0 -> reference default per n                             */
-    double L_minus_percent; /* <=0 -> 0.84 (heteroclinic.cpp:72)                                        */
-    double L_minus_override; /* >0 -> use this L_minus instead of sup(2*T*percent)                      */
-    int32_t order, step_log2, grid;   /* <=0 -> 20, 5, 14                                               */
-    int32_t newton_steps;             /* <=0 -> 20                                                      */
-} ccp_setup_opts;
-
-typedef struct {
-    double T;             /* shooting time after FindTime (boundaryValueProblem.cpp:118)                */
-    double L_minus;
-    double newton_residual;
-    double eig_unstable[CCP_MAX_N];
-    double x_local[CCP_MAX_N];
-    double y_local[CCP_MAX_N];
-    int32_t converged;
-    int32_t reserved;
-} ccp_setup_info;
-
-/* params = (b_1..b_n, c_12..c_{n-1,n}) as doubles */
-int ccp_setup_front(int n, const double* params, const ccp_setup_opts* opts,
-                    ccp_front_desc* out, ccp_setup_info* info);
-/* n_fronts parameter vectors, each 2n-1 doubles, `threads` host threads (<=0: all cores) */
-int ccp_setup_sweep(int n, const double* params, size_t n_fronts, const ccp_setup_opts* opts,
-                    ccp_front_desc* out, ccp_setup_info* info, int threads);
-/* the reference's own sweep generator, Construct_ParameterList (heteroclinic.cpp:386-427):
-   writes N_c*N_r vectors (b1,b2,b3,c12,c23) */
-int ccp_parameter_list(int N_c, int N_r, double r_min, double r_max, const double* b3, double* out);
 
 #ifdef __cplusplus
 }

@@ -207,7 +207,7 @@ static inline void run_front(const ccp_front_desc& d, ccp_front_result& res, std
     std::memset(&res, 0, sizeof(res));
     res.first_failure = -1;
     const int n = d.n, D = 2 * n, p = d.order, g = d.grid;
-    if (n < 2 || n > MAXN || p < 2 || p > MAXP || g < 0 || g > MAXG || d.step_log2 < 1 || d.step_log2 > 20 || !(d.L_minus > 0) || !std::isfinite(d.L_minus)) {
+    if (n < 2 || n > MAXN || p < 2 || p > MAXP || g < 0 || g > MAXG || d.step_log2 < 1 || d.step_log2 > 20 || !(d.L_minus > 0) || !std::isfinite(d.L_minus) || std::ldexp(d.L_minus, d.step_log2) > 16777216.0) {
         res.status = CCP_ST_BAD_DESC; return;
     }
     const double h = std::ldexp(1.0, -d.step_log2);

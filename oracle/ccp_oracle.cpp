@@ -17,6 +17,7 @@
 #include "c1.hpp"
 #include "c2.hpp"
 #include "dfu.hpp"
+#include "subdiv.hpp"
 #include <thread>
 #include <atomic>
 #include <chrono>
@@ -59,6 +60,25 @@ int orc_run_batch(const ccp_front_desc* d, size_t n_fronts, int mode, ccp_front_
     work();
     for (auto& t : th) t.join();
     if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return 0;
+}
+
+// BASELINE config 4 (twin of ccp_frame_count_subdivided): sub-box descriptors by part(), every sub-box through `mode`, hull / tally.
+// `sub_out` (optional, n_fronts * parts^n records) receives the sub-box records.
+int orc_subdivided(const ccp_front_desc* d, size_t n_fronts, int parts, int which, int mode, ccp_subdiv_result* res, ccp_front_result* sub_out, int threads) {
+    if (n_fronts == 0) return 0;
+    int total = 1;
+    for (int q = 0; q < d[0].n; q++) total *= parts;
+    std::vector<ccp_front_desc> sub((size_t)total * n_fronts);
+    std::vector<ccp_front_result> rec((size_t)total * n_fronts);
+    {
+        RoundUpGuard guard;
+        for (size_t f = 0; f < n_fronts; f++) for (int j = 0; j < total; j++) sub[f * total + j] = subdiv::sub_desc(d[f], j, parts, which);
+    }
+    double sec = 0;
+    orc_run_batch(sub.data(), sub.size(), mode, rec.data(), threads, &sec);
+    for (size_t f = 0; f < n_fronts; f++) subdiv::reduce(rec.data() + f * total, total, res[f]);
+    if (sub_out) std::memcpy(sub_out, rec.data(), rec.size() * sizeof(ccp_front_result));
     return 0;
 }
 

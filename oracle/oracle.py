@@ -81,3 +81,17 @@ def ival_op(abi, op, a, b):
     out = (C.c_double * 2)()
     lib(abi).orc_ival_op(op, a[0], a[1], b[0], b[1], out)
     return out[0], out[1]
+
+
+def subdivided(abi, descs, parts, which, mode=MODE_C2, threads=0, keep_sub=False):
+    """oracle/subdiv.hpp: twin of ccp_frame_count_subdivided (BASELINE config 4).  Returns (SubdivResult array, sub-box records or None)."""
+    L = lib(abi)
+    L.orc_subdivided.restype = C.c_int
+    L.orc_subdivided.argtypes = [C.POINTER(abi.FrontDesc), C.c_size_t, C.c_int, C.c_int, C.c_int, C.POINTER(abi.SubdivResult), C.c_void_p, C.c_int]
+    m = len(descs)
+    res = (abi.SubdivResult * m)()
+    sub = None
+    if keep_sub:
+        sub = (abi.FrontResult * (m * parts ** descs[0].n))()
+    L.orc_subdivided(descs, m, parts, which, mode, res, C.cast(sub, C.c_void_p) if sub is not None else None, threads)
+    return res, sub

@@ -373,7 +373,7 @@ static inline void run_front(const ccp_front_desc& D, ccp_front_result& res, std
     std::memset(&res, 0, sizeof(res));
     res.first_failure = -1;
     const int n = D.n, dim = 2 * n, p = D.order, g = D.grid;
-    if (n < 2 || n > MAXN || p < 2 || p > CCP_MAX_ORDER || g < 1 || g > CCP_MAX_GRID || D.step_log2 < 1 || D.step_log2 > 20 || !(D.L_minus > 0) || !std::isfinite(D.L_minus)) {
+    if (n < 2 || n > MAXN || p < 2 || p > CCP_MAX_ORDER || g < 1 || g > CCP_MAX_GRID || D.step_log2 < 1 || D.step_log2 > 20 || !(D.L_minus > 0) || !std::isfinite(D.L_minus) || std::ldexp(D.L_minus, D.step_log2) > 16777216.0) {
         res.status = CCP_ST_BAD_DESC; return;
     }
     ival b[MAXN], c[MAXN];

@@ -24,7 +24,7 @@ def ge():
 @pytest.fixture(scope="session")
 def pkg(ge):
     p = ge.load_package()
-    if not os.path.exists(p.LIB_PATH):
+    if not (os.path.exists(p.LIB_PATH) and os.path.exists(p.SETUP_LIB_PATH)):
         p.build()
     return p
 

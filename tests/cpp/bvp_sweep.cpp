@@ -3,6 +3,7 @@
 // fronts whose connecting orbit is verified (given the cone constant of the manifold validation) and the time per batched Krawczyk step.
 // Usage: bvp_sweep [N_c] [N_r]   (default 24 x 4 = the reference's own 96-point sweep).  Exit 0 = all verified, 77 = no GPU.
 #include "../../computing-conjugate-points_b200/host/ccp_bvp.hpp"
+#include "../../include/ccp_setup.h"
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>

@@ -11,5 +11,6 @@ int ccp_init(int) { return 0; }
 const char* ccp_last_error(void) { return "oracle backend"; }
 int ccp_bound_dfu_batch(const ccp_dfu_desc* d, size_t n, ccp_dfu_result* r) { return orc_bound_dfu(d, n, r); }
 int ccp_frame_count_batch(const ccp_front_desc* d, size_t n, ccp_front_result* r) { double s; return orc_run_batch(d, n, /*mode c2 = kernel twin*/ 2, r, 0, &s); }
+int ccp_frame_count_batch_multi(const ccp_front_desc* d, size_t n, ccp_front_result* r) { return ccp_frame_count_batch(d, n, r); }
 int ccp_frame_count_series(const ccp_front_desc*, ccp_front_result*, ccp_series_rec*, size_t, size_t*) { return CCP_E_NO_DEVICE; }
 }

@@ -66,6 +66,15 @@ int main() {
         const interval nv = euclNorm(v);
         CHECK(nv.lo == nv.hi && nv.hi >= 5.0 && nv.hi < 5.0 + 1e-14);
     }
+    {   // non-finite entries must never certify a bound: lambda_max = +inf  =>  euclLNorm +inf, ml -inf (rate / L_+ conditions then fail)
+        const double bad[3] = {std::nan(""), INFINITY, -INFINITY};
+        for (double b : bad) {
+            IMatrix A = {{interval(1.0), interval(0.25)}, {interval(0.25), interval(b)}};
+            CHECK(maxEigenvalueSym(A) == INFINITY && euclLNorm(A).hi == INFINITY && ml(A).lo == -INFINITY);
+            IMatrix B = {{interval(1.0), interval(b)}, {interval(0.5), interval(2.0)}};
+            CHECK(maxEigenvalueSym(B) == INFINITY && !(euclNorm(B).hi < INFINITY));
+        }
+    }
     std::printf("norm bounds ok\n");
 
     // ---- the n = 3 defaults at the equilibrium 0: Df(0) = [[0, I], [M, 0]], M = 1/2 [[b1,c12,0],[c12,b2,c23],[0,c23,b3]]

@@ -1,6 +1,7 @@
 // Exercises the C++ host shim the way the reference's driver would (heteroclinic.cpp:299-334):
 // build propagateManifold, call frameDet, read countZeros / getLastFrame.  Exit code 0 = ok, 77 = no GPU.
 #include "../../computing-conjugate-points_b200/host/ccp_bvp.hpp"
+#include "../../include/ccp_setup.h"
 #include "../../computing-conjugate-points_b200/host/ccp_local_manifold.hpp"
 #include <cmath>
 #include <cstdio>
@@ -20,7 +21,11 @@ int main() {
     for (int j = 0; j < 3; j++) for (int k = 0; k < 3; k++) E[j][k] = from_c(d.Eu_err[j * CCP_MAX_N + k]);
     propagateManifold E_u(n, par, A, p_i, Uxy, E, /*order*/ 20, /*stepsize*/ 5);
     E_u.plotting(false);
-    int unstable_e_values = E_u.frameDet(interval(info.L_minus), /*grid*/ 14, IVector(6));
+    // the two host-side proof stages are mandatory: a frameDet call with unset hooks must throw, never return a "validated" count
+    bool threw = false;
+    try { E_u.frameDet(interval(info.L_minus), 14, IVector(6)); } catch (const std::logic_error&) { threw = true; }
+    if (!threw) { std::printf("frameDet accepted unset proof hooks\n"); return 8; }
+    int unstable_e_values = E_u.frameDetUnchecked(interval(info.L_minus), /*grid*/ 14);
     std::printf("frameDet = %d, last frame U(0,0) in [%.6e, %.6e]\n", unstable_e_values, E_u.frame().getLastFrame()[0][0].lo, E_u.frame().getLastFrame()[0][0].hi);
     if (unstable_e_values != 2) return 3;
     E_u.L_plus = [](const topFrame&, const IVector&) { return false; };

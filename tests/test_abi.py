@@ -12,6 +12,12 @@ def test_library_exports_every_declared_symbol(pkg):
     missing = [s for s in sorted(declared) if not hasattr(lib, s)]
     assert not missing, missing
     assert declared == set(pkg.abi.SYMBOLS), declared ^ set(pkg.abi.SYMBOLS)
+    # the host-only descriptor generator has its own header and library (CPU-only consumers never map the CUDA library)
+    header = open(os.path.join(os.path.dirname(pkg.PKG_DIR), "include", "ccp_setup.h")).read()
+    declared = set(re.findall(r"\b(ccp_[a-z0-9_]+)\s*\(", header))
+    lib = C.CDLL(pkg.SETUP_LIB_PATH)
+    assert declared == set(pkg.abi.SETUP_SYMBOLS) and all(hasattr(lib, s) for s in declared)
+    assert not any(hasattr(C.CDLL(pkg.LIB_PATH), s) for s in declared), "the generator must not live in the CUDA library"
 
 
 def test_struct_sizes_match_header(pkg):

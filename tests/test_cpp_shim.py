@@ -11,7 +11,7 @@ EXE = os.path.join(ROOT, "tests", "cpp", "test_shim")
 
 def _build(pkg):
     cmd = ["g++", "-std=c++17", "-O1", "-o", EXE, os.path.join(ROOT, "tests", "cpp", "test_shim.cpp"),
-           "-L", pkg.PKG_DIR, "-lccp_b200", "-Wl,-rpath," + pkg.PKG_DIR]
+           "-L", pkg.PKG_DIR, "-lccp_b200", "-lccp_setup", "-Wl,-rpath," + pkg.PKG_DIR]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
 
@@ -38,7 +38,7 @@ def test_bvp_sweep_validates_reference_sweep_on_gpu(pkg):
     """Boundary-value stage for the reference's own 96-point sweep: every batched Krawczyk step is one launch
     of 4 x 96 validated integrations; all 96 connecting orbits must be verified (heteroclinic.cpp:186-281 loop)."""
     cmd = ["g++", "-std=c++17", "-O1", "-o", SWEEP, os.path.join(ROOT, "tests", "cpp", "bvp_sweep.cpp"),
-           "-L", pkg.PKG_DIR, "-lccp_b200", "-Wl,-rpath," + pkg.PKG_DIR]
+           "-L", pkg.PKG_DIR, "-lccp_b200", "-lccp_setup", "-Wl,-rpath," + pkg.PKG_DIR]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     r = subprocess.run([SWEEP, "24", "4"], capture_output=True, text=True)

@@ -28,6 +28,12 @@ def _worker(rank, world, port, n_total, out_dir):
     full = sweep.gather_records(torch.from_numpy(local.reshape(-1)), n_total, rank, world, rb)
     st, zc, fc = sweep.counts_from_records(full)
     np.save(os.path.join(out_dir, "r%d.npy" % rank), np.stack([st, zc, fc]))
+    # the copy-free form bench.py times: preallocated output, the collective's own [world, m_pad, record] layout, front order on the host
+    m_pad = sweep.padded_shard_len(n_total, world)
+    pre = torch.empty(world * m_pad * rb, dtype=torch.uint8)
+    raw = sweep.gather_records(torch.from_numpy(local.reshape(-1)), n_total, rank, world, rb, out=pre, ordered=False)
+    assert raw.shape == (world, m_pad, rb) and raw.data_ptr() == pre.data_ptr()
+    assert np.array_equal(sweep.front_order(raw, n_total).reshape(-1), full.numpy())
     dist.barrier()
     dist.destroy_process_group()
 

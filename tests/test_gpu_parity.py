@@ -139,15 +139,21 @@ def test_counts_match_reference_structured_oracle_on_sweep_sample(engine, pkg, o
     descs, _ = pkg.setup_sweep(3, params, thin_opts())
     gpu = engine.frame_count_batch(descs)
     ref, _ = orc.run_batch(pkg.abi, descs, orc.MODE_REF)
+    n_ref_ok = 0
     for g, r in zip(gpu, ref):
-        assert pkg.frame_det_code(g) == pkg.frame_det_code(r)            # counts and pass/fail exact
-        if g.failure_count == 0:
+        # counts exact wherever the reference-structured algorithm certifies; the kernel (frame basis renormalised) certifies all seven,
+        # the reference-structured one fails on the long front of the (-,-) quadrant even with the thin box
+        assert pkg.frame_det_code(g) >= 0
+        if pkg.frame_det_code(r) >= 0:
+            n_ref_ok += 1
+            assert pkg.frame_det_code(g) == pkg.frame_det_code(r)
             assert [g.conj_index[i] for i in range(g.n_conj)] == [r.conj_index[i] for i in range(r.n_conj)]
         for row in range(6):                                             # last frame enclosures of both contain the truth
             for col in range(5):
                 x, y = g.last_frame[row * 6 + col], r.last_frame[row * 6 + col]
                 assert max(x.lo, y.lo) <= min(x.hi, y.hi)
                 assert x.lo <= 0.5 * (y.lo + y.hi) <= x.hi
+    assert n_ref_ok >= 6
 
 
 @pytest.mark.parametrize("n,params,expected", [

@@ -13,7 +13,7 @@ EXE = os.path.join(ROOT, "tests", "cpp", "test_eig")
 
 def test_eigenvalue_mirror_host_only(pkg):
     cmd = ["g++", "-std=c++17", "-O1", "-o", EXE, os.path.join(ROOT, "tests", "cpp", "test_eig.cpp"),
-           "-L", pkg.PKG_DIR, "-lccp_b200", "-Wl,-rpath," + pkg.PKG_DIR]
+           "-L", pkg.PKG_DIR, "-lccp_b200", "-lccp_setup", "-Wl,-rpath," + pkg.PKG_DIR]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     r = subprocess.run([EXE], capture_output=True, text=True)
@@ -30,7 +30,7 @@ def test_manifold_conditions_mirror_host_only(pkg):
     rejected at radius 0.6 and for a cone that is too thin)."""
     exe = os.path.join(ROOT, "tests", "cpp", "test_conditions")
     cmd = ["g++", "-std=c++17", "-O1", "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_conditions.cpp"),
-           "-L", pkg.PKG_DIR, "-lccp_b200", "-Wl,-rpath," + pkg.PKG_DIR]
+           "-L", pkg.PKG_DIR, "-lccp_b200", "-lccp_setup", "-Wl,-rpath," + pkg.PKG_DIR]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     r = subprocess.run([exe], capture_output=True, text=True)
@@ -47,7 +47,7 @@ def test_local_manifold_eig_mirror_host_only(pkg):
     (2.12) accepted at radius 1e-3 and rejected where eps > 1."""
     exe = os.path.join(ROOT, "tests", "cpp", "test_eig_error")
     cmd = ["g++", "-std=c++17", "-O1", "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_eig_error.cpp"),
-           "-L", pkg.PKG_DIR, "-lccp_b200", "-Wl,-rpath," + pkg.PKG_DIR]
+           "-L", pkg.PKG_DIR, "-lccp_b200", "-lccp_setup", "-Wl,-rpath," + pkg.PKG_DIR]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     r = subprocess.run([exe], capture_output=True, text=True)
@@ -63,7 +63,7 @@ def test_l_plus_stage_mirror_host_only(pkg):
     result records.  The GPU-backed parts (construct_Manifold_at_LPlus, lastEuFrame) are compiled but not run here."""
     exe = os.path.join(ROOT, "tests", "cpp", "test_l_plus")
     cmd = ["g++", "-std=c++17", "-O1", "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_l_plus.cpp"),
-           "-L", pkg.PKG_DIR, "-lccp_b200", "-Wl,-rpath," + pkg.PKG_DIR]
+           "-L", pkg.PKG_DIR, "-lccp_b200", "-lccp_setup", "-Wl,-rpath," + pkg.PKG_DIR]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     r = subprocess.run([exe], capture_output=True, text=True)
@@ -89,12 +89,10 @@ def test_manifold_stages_against_oracle_dfu_backend(pkg, orc):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="first run on a B200 happens at round end (GPU budget of the round was spent before this test "
-                                        "existed); verified here against the oracle twin of the kernel, which the GPU matches bit for bit")
 def test_manifold_stages_on_gpu(pkg):
     exe = os.path.join(ROOT, "tests", "cpp", "manifold_gpu")
     cmd = ["g++", "-std=c++17", "-O1", "-o", exe, os.path.join(ROOT, "tests", "cpp", "manifold_gpu.cpp"),
-           "-L", pkg.PKG_DIR, "-lccp_b200", "-Wl,-rpath," + pkg.PKG_DIR]
+           "-L", pkg.PKG_DIR, "-lccp_b200", "-lccp_setup", "-Wl,-rpath," + pkg.PKG_DIR]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     r = subprocess.run([exe], capture_output=True, text=True)
@@ -106,7 +104,7 @@ def test_manifold_stages_on_gpu(pkg):
 def _build_with_oracle_backend(pkg, src, exe):
     bdir = os.path.join(ROOT, "oracle", "_build")
     cmd = ["g++", "-std=c++17", "-O1", "-o", exe, os.path.join(ROOT, "tests", "cpp", src), os.path.join(ROOT, "tests", "cpp", "oracle_dfu_backend.cpp"),
-           "-L", pkg.PKG_DIR, "-lccp_b200", "-L", bdir, "-loracle", "-Wl,-rpath," + bdir, "-Wl,-rpath," + pkg.PKG_DIR]
+           "-L", pkg.PKG_DIR, "-lccp_b200", "-lccp_setup", "-L", bdir, "-loracle", "-Wl,-rpath," + bdir, "-Wl,-rpath," + pkg.PKG_DIR]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
 
@@ -132,12 +130,10 @@ def test_compute_front_and_conjugate_points_against_oracle_backend(pkg, orc):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="first run on a B200 happens at round end (GPU budget of the round was spent before this test "
-                                        "existed); passes here against the oracle twins of the kernels, which the GPU matches bit for bit")
 def test_compute_front_and_conjugate_points_on_gpu(pkg):
     exe = os.path.join(ROOT, "tests", "cpp", "driver_gpu")
     cmd = ["g++", "-std=c++17", "-O1", "-o", exe, os.path.join(ROOT, "tests", "cpp", "driver_gpu.cpp"),
-           "-L", pkg.PKG_DIR, "-lccp_b200", "-Wl,-rpath," + pkg.PKG_DIR]
+           "-L", pkg.PKG_DIR, "-lccp_b200", "-lccp_setup", "-Wl,-rpath," + pkg.PKG_DIR]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     r = subprocess.run([exe], capture_output=True, text=True)
@@ -165,11 +161,10 @@ def test_batch_driver_against_oracle_backend(pkg, orc):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="first run on a B200 happens at round end; passes here against the oracle twins of the kernels")
 def test_batch_driver_reference_sweep_on_gpu(pkg):
     exe = os.path.join(ROOT, "tests", "cpp", "driver_sweep_gpu")
     cmd = ["g++", "-std=c++17", "-O1", "-o", exe, os.path.join(ROOT, "tests", "cpp", "driver_sweep_gpu.cpp"),
-           "-L", pkg.PKG_DIR, "-lccp_b200", "-Wl,-rpath," + pkg.PKG_DIR]
+           "-L", pkg.PKG_DIR, "-lccp_b200", "-lccp_setup", "-Wl,-rpath," + pkg.PKG_DIR]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     r = subprocess.run([exe, "24", "4"], capture_output=True, text=True)          # the reference's own 96-point sweep
