@@ -14,7 +14,8 @@
 // reversible: with S = diag(I, -I),  Phi^minus_T = S Phi_T S,  so the backward maps are the forward maps of the mirrored set
 // (S p_i, S A_i, Uxy), mirrored back:  image -> S image,  [D Phi^minus_T] A_i = S [D Phi_T (S A_i)].
 //
-// Integration parameters are the engine's (fixed step 2^-step_size, order); T is a point (the reference passes a thin interval).
+// Integration parameters are the engine's (order; step ladder 2^-step_size .. 2^-finest_step, see the constructor); T is a point (the
+// reference passes a thin interval).
 #pragma once
 #include "ccp_frame_det.hpp"
 #include <algorithm>
@@ -51,9 +52,16 @@ struct FlowSet {                 // what getPointNbd / (*pF).A hand to C0Rect2Se
 
 class boundaryValueProblem {
   public:
-    boundaryValueProblem(int n, const IVector& params, int order, int step_size) : n_(n), params_(params), order_(order), step_(step_size) {
+    // `step_size`: the validated integrations start with the step 2^-step_size.  The reference's solvers of this stage are adaptive
+    // (ITaylor without setStep, boundaryValueProblem.cpp:24-38: CAPD picks the step); here the step ladder is explicit: every integration
+    // of a launch first runs with the COARSE step (default 2^-3: with order 20 the truncation bound is still ~1e-22 and the a-priori
+    // enclosure of a step holds along the whole front) and the ones whose enclosure check fails (per-front status, CCP_ST_ENCLOSURE)
+    // are re-launched with the next finer step, down to 2^-finest_step.  The result of any rung is a valid enclosure.
+    boundaryValueProblem(int n, const IVector& params, int order, int step_size = 3, int finest_step = 6)
+        : n_(n), params_(params), order_(order), step_(step_size), finest_(finest_step < step_size ? step_size : finest_step) {
         if (n < 2 || n > CCP_MAX_N) throw std::invalid_argument("n out of range");
     }
+    int launches() const { return launches_; }            // launches of validated integrations so far (all rungs)
     // enclosure of the time-T image of the set (Gxy)
     IVector Gxy(const FlowSet& s, double T) { return run({s}, {T})[0].image; }
     // enclosure of [D Phi_T] * A_i over the set (DGxy before the factor DW)
@@ -80,7 +88,19 @@ class boundaryValueProblem {
                 for (int j = 0; j < D; j++) e.A_u[i * CCP_MAX_DIM + j] = sg * s.A_i[i][j];
             }
         }
-        if (ccp_frame_count_batch(d.data(), d.size(), r.data()) != 0) throw std::runtime_error(std::string("ccp: ") + ccp_last_error());
+        if (ccp_frame_count_batch_multi(d.data(), d.size(), r.data()) != 0) throw std::runtime_error(std::string("ccp: ") + ccp_last_error());
+        launches_++;
+        // step ladder: integrations whose a-priori enclosure failed with the coarse step are re-run with the next finer one
+        for (int st = step_ + 1; st <= finest_; st++) {
+            std::vector<size_t> redo;
+            for (size_t q = 0; q < d.size(); q++) if (r[q].status == CCP_ST_ENCLOSURE) redo.push_back(q);
+            if (redo.empty()) break;
+            std::vector<ccp_front_desc> d2(redo.size()); std::vector<ccp_front_result> r2(redo.size());
+            for (size_t k = 0; k < redo.size(); k++) { d2[k] = d[redo[k]]; d2[k].step_log2 = st; }
+            if (ccp_frame_count_batch_multi(d2.data(), d2.size(), r2.data()) != 0) throw std::runtime_error(std::string("ccp: ") + ccp_last_error());
+            launches_++;
+            for (size_t k = 0; k < redo.size(); k++) r[redo[k]] = r2[k];
+        }
         std::vector<Out> out(sets.size());
         for (size_t q = 0; q < sets.size(); q++) {
             Out& o = out[q];
@@ -138,22 +158,31 @@ class boundaryValueProblem {
 
     // boundaryValueProblem::NewtonStep (boundaryValueProblem.cpp:237-317) for many fronts (a parameter sweep): the image of
     // XY_pt + XY_nbd under the interval Krawczyk operator of G(x,y) = Phi_T(x) - Phi_{-T}(y) (last row: |x|^2 - r_u^2).
-    // The 4 validated integrations of every front -- 4 * in.size() -- are ONE launch.
+    // The validated integrations of every front -- 4 * in.size(), 2 * in.size() while XY_nbd = 0 -- are ONE launch (per rung of the step ladder).
     std::vector<StepOut> NewtonStepBatch(const std::vector<StepIn>& in) {
         const int n = n_, D = 2 * n;
         const IVector zero(n, interval(0.0));
-        std::vector<FlowSet> sets; std::vector<double> times;
-        for (const StepIn& q : in) {
+        // The operator needs G at the POINT (C^0 images of XY_pt, sets 0 and 1) and DG over the BOX (C^1 maps of XY_pt + XY_nbd, sets 2
+        // and 3).  In the Newton phase of the driver (heteroclinic.cpp:186-191: 20 steps with XY_nbd = 0) box and point coincide, and
+        // since one integration delivers image and derivative alike only two of the four are launched.
+        std::vector<FlowSet> sets; std::vector<double> times; std::vector<size_t> slot(4 * in.size());
+        for (size_t fi = 0; fi < in.size(); fi++) {
+            const StepIn& q = in[fi];
             IVector X_pt(q.XY_pt.begin(), q.XY_pt.begin() + n), Y_pt(q.XY_pt.begin() + n, q.XY_pt.end());
             IVector X_nbd(q.XY_nbd.begin(), q.XY_nbd.begin() + n), Y_nbd(q.XY_nbd.begin() + n, q.XY_nbd.end());
+            bool thin = true;
+            for (const interval& e : q.XY_nbd) thin = thin && e.lo == 0.0 && e.hi == 0.0;
             FlowSet f[4] = {getPointNbd(q.unstable, X_pt, zero), getPointNbd(q.stable, Y_pt, zero), getPointNbd(q.unstable, X_pt, X_nbd), getPointNbd(q.stable, Y_pt, Y_nbd)};
-            for (FlowSet& g : f) { g.params = q.params; sets.push_back(g); times.push_back(q.T); }
+            for (int k = 0; k < 4; k++) {
+                if (thin && k >= 2) { slot[4 * fi + k] = slot[4 * fi + k - 2]; continue; }
+                f[k].params = q.params; slot[4 * fi + k] = sets.size(); sets.push_back(f[k]); times.push_back(q.T);
+            }
         }
         const std::vector<Out> all = run(sets, times);
         std::vector<StepOut> res(in.size());
         for (size_t f = 0; f < in.size(); f++) {
             const StepIn& q = in[f];
-            const Out* o = &all[4 * f];
+            const Out o[4] = {all[slot[4 * f]], all[slot[4 * f + 1]], all[slot[4 * f + 2]], all[slot[4 * f + 3]]};
             res[f].success = false; res[f].kraw_image.assign(D, interval(0.0));
             bool okflow = true; for (int k = 0; k < 4; k++) okflow = okflow && o[k].status == CCP_OK;
             if (!okflow) continue;                                   // like a CAPD exception inside one parameter value: this front fails, the sweep goes on
@@ -281,7 +310,7 @@ class boundaryValueProblem {
     }
 
   private:
-    int n_; IVector params_; int order_, step_;
+    int n_; IVector params_; int order_, step_, finest_; int launches_ = 0;
 };
 
 } // namespace ccp_host

@@ -64,7 +64,7 @@ inline int computeFrontAndConjugatePoints(int dimension, const std::vector<doubl
     for (int i = 0; i < n; i++) r_u_sqr = ia::add(r_u_sqr, ia::sqr(XY_pt[i]));
     r_u_sqr = interval(r_u_sqr.lo);
 
-    boundaryValueProblem BVP(n, All_parameters_interval, order, stepsize);
+    boundaryValueProblem BVP(n, All_parameters_interval, order);                  // adaptive in the reference: step ladder from 2^-3 (ccp_bvp.hpp)
     boundaryValueProblem::Manifold Mu{A, localUnstable.F.p, L, false}, Ms{A, localStable.F.p, L, true};
     auto midVector = [](const IVector& v) { IVector m(v.size()); for (size_t i = 0; i < v.size(); i++) m[i] = interval(ia::mid(v[i])); return m; };
     const double T = BVP.FindTime(Mu, Ms, XY_pt, info.T);
@@ -192,7 +192,7 @@ inline std::vector<int> computeFrontAndConjugatePointsBatch(int dimension, const
     };
     checkBoth(&DriverReport::conditions_first);
 
-    boundaryValueProblem BVP(n, PI.empty() ? IVector(2 * n - 1, interval(0.0)) : PI[0], order, stepsize);
+    boundaryValueProblem BVP(n, PI.empty() ? IVector(2 * n - 1, interval(0.0)) : PI[0], order);
     {   // FindTime
         std::vector<boundaryValueProblem::TimeIn> in; std::vector<size_t> who;
         for (size_t q = 0; q < m; q++) if (alive(q)) { in.push_back({F[q].Mu, F[q].Ms, F[q].XY_pt, F[q].T, PI[q]}); who.push_back(q); }

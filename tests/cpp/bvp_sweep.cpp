@@ -1,7 +1,7 @@
 // Boundary-value stage for a parameter sweep: the driver's Newton / Krawczyk loop (heteroclinic.cpp:186-281) for M
 // fronts of Construct_ParameterList at once -- every NewtonStepBatch is ONE launch of 4*M validated integrations.  Prints the number of
 // fronts whose connecting orbit is verified (given the cone constant of the manifold validation) and the time per batched Krawczyk step.
-// Usage: bvp_sweep [N_c] [N_r]   (default 24 x 4 = the reference's own 96-point sweep).  Exit 0 = all verified, 77 = no GPU.
+// Usage: bvp_sweep [N_c] [N_r] [step_size]   (default 24 x 4 = the reference's own 96-point sweep, first rung of the step ladder 2^-3).  Exit 0 = all verified, 77 = no GPU.
 #include "../../computing-conjugate-points_b200/host/ccp_bvp.hpp"
 #include "../../include/ccp_setup.h"
 #include <chrono>
@@ -19,7 +19,8 @@ int main(int argc, char** argv) {
     std::vector<ccp_front_desc> d(M); std::vector<ccp_setup_info> info(M);
     ccp_setup_opts o{}; o.xy_nbd = -1; o.cone_L = -1; o.eig_err = -1; o.scale = -1; o.L_minus_percent = -1; o.L_minus_override = -1;
     if (ccp_setup_sweep(n, P.data(), M, &o, d.data(), info.data(), 0) != 0) return 3;
-    boundaryValueProblem BVP(n, IVector(5, interval(0.0)), 20, 5);
+    const int step_size = argc > 3 ? std::atoi(argv[3]) : 3;                    // fixed step 2^-step_size of the validated integrations
+    boundaryValueProblem BVP(n, IVector(5, interval(0.0)), 20, step_size);
     std::vector<boundaryValueProblem::StepIn> in(M);
     for (size_t f = 0; f < M; f++) {
         boundaryValueProblem::StepIn& q = in[f];

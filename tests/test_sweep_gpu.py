@@ -33,7 +33,7 @@ def test_sample_parameters_with_the_real_engine(engine, pkg, orc, tmp_path):
     assert engine.kernel_launches() - launches == 2                      # 24 fronts, 14 done before the crash: chunks of 7 and 3
     cpu, _ = orc.run_batch(pkg.abi, descs, orc.MODE_C2)
     want = [pkg.frame_det_code(r) if pkg.frame_det_code(r) >= 0 else -1 for r in cpu]
-    assert counts == want and set(counts) <= {0, 1, 2}
+    assert counts == want and set(counts) <= {-1, 0, 1, 2} and sum(c >= 0 for c in counts) >= 20
     ref_path = str(tmp_path / "expected.txt")
     sweep.write_plot_parameters(ref_path, params, want)
     assert open(path).read() == open(ref_path).read()
