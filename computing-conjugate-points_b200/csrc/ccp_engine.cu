@@ -12,6 +12,7 @@
 #include <cstddef>
 #include <mutex>
 #include <string>
+#include <cstdlib>
 
 namespace {
 
@@ -65,7 +66,10 @@ template <int N> int launch(Dev& dv, const ccp_front_desc* d_desc, ccp_front_res
     // one CTA of ccp::NT threads per front; the grid is sized to the number of CTAs that are resident at once
     // (multiple of the SM count) and strides over the batch.
     int grid = count < dv.grid_limit[N] ? count : dv.grid_limit[N];
-    ccp::front_kernel<N><<<grid, ccp::NT, sizeof(ccp::FrontSmem<N>), st>>>(d_desc, d_res, d_index, count, series, series_cap);
+    static const int dbg_align = getenv("CCP_DBG_ALIGN") ? atoi(getenv("CCP_DBG_ALIGN")) : 1;          // experiment knobs (scripts/)
+    static const int dbg_pad = getenv("CCP_DBG_SMEM_PAD") ? atoi(getenv("CCP_DBG_SMEM_PAD")) : 0;
+    if (dbg_pad) { cudaFuncSetAttribute(ccp::front_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ccp::FrontSmem<N>) + dbg_pad); }
+    ccp::front_kernel<N><<<grid, ccp::NT, sizeof(ccp::FrontSmem<N>) + dbg_pad, st>>>(d_desc, d_res, d_index, count, series, series_cap, dbg_align);
     E.launches++;
     CK(cudaGetLastError());
     return 0;
@@ -129,6 +133,18 @@ int init_device(Dev& dv, int device) {
     if ((rc = prepare_kernel<2>(dv))) return rc;
     if ((rc = prepare_kernel<3>(dv))) return rc;
     if ((rc = prepare_kernel<4>(dv))) return rc;
+    {   // reciprocal tables of the front kernel (constant memory of THIS device), computed by the device's own directed divisions
+        constexpr int NI = ccp::KMAX + 2;
+        double* d_tab = nullptr;
+        CK(cudaMalloc(&d_tab, sizeof(double) * 3 * NI));
+        ccp::inv_table_kernel<<<1, 64, 0, dv.stream>>>(d_tab);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyToSymbolAsync(ccp::c_invlo, d_tab, sizeof(double) * NI, 0, cudaMemcpyDeviceToDevice, dv.stream));
+        CK(cudaMemcpyToSymbolAsync(ccp::c_invhi, d_tab + NI, sizeof(double) * NI, 0, cudaMemcpyDeviceToDevice, dv.stream));
+        CK(cudaMemcpyToSymbolAsync(ccp::c_invs, d_tab + 2 * NI, sizeof(double) * NI, 0, cudaMemcpyDeviceToDevice, dv.stream));
+        CK(cudaStreamSynchronize(dv.stream));
+        CK(cudaFree(d_tab));
+    }
     CK(cudaFuncSetAttribute(ccp::dfu_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ccp::DfuSmem<2>)));
     CK(cudaFuncSetAttribute(ccp::dfu_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ccp::DfuSmem<3>)));
     CK(cudaFuncSetAttribute(ccp::dfu_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ccp::DfuSmem<4>)));

@@ -34,8 +34,51 @@ __device__ unsigned long long g_prof[16];
 #define PROF(i) do {} while (0)
 #endif
 
+// ---- soft per-SM alignment of co-resident fronts -------------------------------------------------------------------------------
+// The step loop is ~100 KB of straight-line SASS, far beyond the instruction caches (L0 6 KB, L1.5 32 KB): seven co-resident fronts
+// that drift apart stream that code from L2 seven times per step (ncu: stalled_no_instruction 0.2 per issue with one front per SM,
+// 1.3 with seven).  Fronts of one SM therefore meet once per step at a barrier in global memory, keyed by %smid, so that they walk
+// through the code together and share the fetched lines.  The barrier is only a performance hint: membership is dynamic (a CTA
+// registers when it starts and leaves when it is done), every wait is bounded by SM_ALIGN_TIMEOUT cycles, and any inconsistency
+// (time-outs, kernels of two streams sharing an SM) heals at the next release.  Results never depend on it.
+constexpr long long SM_ALIGN_TIMEOUT = 40000;
+constexpr int SM_ALIGN_SLOTS = 512;
+struct __align__(16) SmAlign { unsigned members, count, gen, pad; };       // one 16-byte record per SM: one L2 sector serves a whole wait
+__device__ SmAlign g_sm_align[SM_ALIGN_SLOTS];
+__device__ __forceinline__ unsigned sm_id() { unsigned v; asm volatile("mov.u32 %0, %%smid;" : "=r"(v)); return v % SM_ALIGN_SLOTS; }
+__device__ __forceinline__ void sm_align_release(SmAlign& a) { *(volatile unsigned*)&a.count = 0u; atomicAdd(&a.gen, 1u); }
+__device__ __forceinline__ void sm_align_join(unsigned sm) { atomicAdd(&g_sm_align[sm].members, 1u); }
+__device__ __forceinline__ void sm_align_leave(unsigned sm) {
+    SmAlign& a = g_sm_align[sm];
+    const unsigned left = atomicSub(&a.members, 1u) - 1u;
+    if (left > 0u && *(volatile unsigned*)&a.count >= left) sm_align_release(a);      // the others may be waiting for this CTA
+}
+// called by ONE thread of the CTA; the CTA synchronises afterwards.  count = arrivals of the current generation; whoever completes it
+// resets the count and opens the next generation.  A waiter that gives up simply goes on (its arrival stays counted, so the others are
+// still released when the last one arrives).
+__device__ __forceinline__ void sm_align_wait(unsigned sm) {
+    SmAlign& a = g_sm_align[sm];
+    const unsigned gen = *(volatile unsigned*)&a.gen;
+    const unsigned members = *(volatile unsigned*)&a.members;
+    if (members <= 1u) return;
+    const unsigned arrived = atomicAdd(&a.count, 1u) + 1u;
+    if (arrived >= members) { sm_align_release(a); return; }
+    const long long t0 = clock64();
+    while (*(volatile unsigned*)&a.gen == gen && clock64() - t0 < SM_ALIGN_TIMEOUT) { }
+}
+
 constexpr int KMAX = CCP_MAX_ORDER + 1;
 constexpr int GMAX = CCP_MAX_GRID;
+// [rd(1/k), ru(1/k)] and ru(ru(1/k) (1 + 2^-50)) (radius factor of the (mid,t) scaling by 1/k, mt_scale), k <= KMAX + 1: the same for
+// every front, filled once per device by inv_table_kernel (ccp_engine.cu) with the device's own directed divisions
+__constant__ double c_invlo[KMAX + 2], c_invhi[KMAX + 2], c_invs[KMAX + 2];
+__global__ void inv_table_kernel(double* out) {
+    const int k = threadIdx.x;
+    if (k >= KMAX + 2) return;
+    out[k] = k >= 1 ? __ddiv_rd(1.0, (double)k) : 0.0;
+    out[KMAX + 2 + k] = k >= 1 ? __ddiv_ru(1.0, (double)k) : 0.0;
+    out[2 * (KMAX + 2) + k] = k >= 1 ? __dmul_ru(__ddiv_ru(1.0, (double)k), 1.0000000000000009) : 0.0;
+}
 
 // Series index map of the table array T (one row = one Taylor series, KMAX coefficients, 16 B each).
 // Row stride 21*16 B = 84 words => 8 consecutive rows hit 8 disjoint 4-bank groups: LDS.128 conflict-free.
@@ -75,7 +118,6 @@ template <int N> struct ParM { mt B[N], B3[N], B6[N], Cm[N], Cp[N], C2m[N], C2p[
 template <int N> struct PostTab {
     static constexpr int D = 2 * N;
     ival Xi[D + 1][D][D];                    // second variation DPhi'[c_j] over the hull, j < D; Xi[D]: direction = the box r
-    ival dJ[D][D];                           // sum_j Xi_j r0_j + Xi_D
     mt dJm[D][D], Jm[D][D], Jcm[D][D];       // (mid,t) forms of dJ, J, Jc for the set update
     double magXu[N][D], magXv[N][D];
     ival DT[3 * (GMAX + 1)];                 // determinants of the grid loop
@@ -93,9 +135,14 @@ template <int N>
 struct FrontSmem {
     static constexpr int D = 2 * N;
     static constexpr int NE = (N > 1) ? (N - 1) : 1;
-    static constexpr int TROWS = (int)((sizeof(PostTab<N>) + KMAX * sizeof(mt) - 1) / (KMAX * sizeof(mt))) > Lay<N>::NS ? (int)((sizeof(PostTab<N>) + KMAX * sizeof(mt) - 1) / (KMAX * sizeof(mt))) : Lay<N>::NS;
-    mt T[TROWS][KMAX];                       // Taylor tables of the centre trajectory; PostTab overlays them once they are dead
-    ival Fk[KMAX][N][N];
+    // Table array: Taylor tables of the centre trajectory.  Once they are dead, PostTab overlays rows [0, PTROWS) and the frame tables
+    // Fk[KMAX][N][N] (exactly N*N rows) live in the LAST N*N rows -- rows the frame-table phase no longer reads (they hold Psi^v and z,
+    // or lie beyond the tables), so building Fk there needs no extra copy.  This keeps a front of n = 3 below 28,160 B: 8 fronts per SM.
+    static constexpr int PTROWS = (int)((sizeof(PostTab<N>) + KMAX * sizeof(mt) - 1) / (KMAX * sizeof(mt)));
+    static constexpr int TROWS = PTROWS + N * N > Lay<N>::NS ? PTROWS + N * N : Lay<N>::NS;
+    static constexpr int FKROW = TROWS - N * N;
+    mt T[TROWS][KMAX];
+    __device__ __forceinline__ ival (*fk())[N][N] { return reinterpret_cast<ival (*)[N][N]>(&T[FKROW][0]); }
     // front set x + C r0 + r (double buffered)
     double x[2][D], C[2][D][D];
     ival r[2][D];
@@ -109,11 +156,7 @@ struct FrontSmem {
     ParM<N> pm;
     mt r0m[D + 1], Errm[N][N];               // (mid,t) forms; r0m[D] = 1 weights the direction "box r"
     double boxFd[N][N];
-    double invlo[KMAX + 2], invhi[KMAX + 2]; // [rd(1/k), ru(1/k)]
-    double invs[KMAX + 2];                   // ru(ru(1/k) (1 + 2^-50)): radius factor of the (mid,t) scaling by 1/k (mt_scale)
     double gp[GMAX + 1];                     // grid points of the current step (utils.cpp:219-223)
-    ival dtime[GMAX];
-    int dec[GMAX];
     int flag;
     int renorms;                             // basis renormalisations applied so far (renormalise)
     ival G[N][N], sc;                        // true frame = normalised frame * G ;  sc encloses det G > 0
@@ -123,13 +166,15 @@ struct FrontSmem {
         ival scratch[Lay<N>::NB + Lay<N>::NC + 2 * N];   // table loop: Cauchy sums awaiting combination; then [0,0]; then the newest g, q
         mt JCr[2 * N][2 * N];                // set update: J*C - C+
         struct { double Hm[N][N]; ival Hi[N][N]; int ok; } rn;   // renormalise: H and the enclosure of its inverse
-        ccp_front_desc desc;                 // start of the front only
     } un;
 };
 
 static_assert(sizeof(PostTab<2>) <= sizeof(FrontSmem<2>::T) && sizeof(PostTab<3>) <= sizeof(FrontSmem<3>::T) && sizeof(PostTab<4>) <= sizeof(FrontSmem<4>::T),
               "PostTab must fit into the table array");
-static_assert(FrontSmem<3>::TROWS == Lay<3>::NS, "n = 3: the overlay must not enlarge the table array (7 CTAs per SM)");
+static_assert(FrontSmem<3>::TROWS == Lay<3>::NS, "n = 3: the overlay must not enlarge the table array");
+static_assert(sizeof(FrontSmem<3>) <= 28160, "n = 3: 8 fronts per SM (228 KB of shared memory, 1 KB reserved per CTA)");
+static_assert(FrontSmem<2>::FKROW > Lay<2>::PU(1, 3) && FrontSmem<3>::FKROW > Lay<3>::PU(2, 5) && FrontSmem<4>::FKROW > Lay<4>::PU(3, 7), "Fk must not overlay the Psi^u rows it is built from");
+static_assert(sizeof(ccp_front_desc) <= sizeof(FrontSmem<2>::T), "the descriptor is staged in the table array");
 static_assert(sizeof(ccp_front_desc) % 16 == 0, "descriptors are staged with 16-byte loads");
 static_assert(sizeof(ccp_front_result) % 16 == 0, "result records are 16-byte aligned");
 
@@ -610,7 +655,7 @@ __device__ __noinline__ void second_variation(FrontSmem<N>& S, PostTab<N>& PT, i
         acc4 a = acc_zero();
 #pragma unroll
         for (int l = 0; l < N; l++) acc_term(a, H.M0[i][l], H.W[1][l]);
-        H.W[3][i] = iv2mt(idivk_tab(acc_finish(a), S.invlo, S.invhi, 6));
+        H.W[3][i] = iv2mt(idivk_tab(acc_finish(a), c_invlo, c_invhi, 6));
     }
     for (int t = tid; t < (D + 1) * N; t += NT) {
         const int j = t / N, m = t % N;
@@ -632,7 +677,7 @@ __device__ __noinline__ void second_variation(FrontSmem<N>& S, PostTab<N>& PT, i
         for (int l = 1; l < N; l++) if (l == m) { dm0 = d0[l]; dm1 = d1[l]; }
         PT.u.x.DD[j][0][m] = dm0; PT.u.x.DD[j][1][m] = dm1;
         PT.u.x.DD[j][2][m] = iv2mt(ihalf(acc_finish(a2)));
-        PT.u.x.DD[j][3][m] = iv2mt(idivk_tab(acc_finish(a3), S.invlo, S.invhi, 6));
+        PT.u.x.DD[j][3][m] = iv2mt(idivk_tab(acc_finish(a3), c_invlo, c_invhi, 6));
     }
     __syncthreads();
     // X2a: product series (w_i d_m)_k, k <= 3, all N x N pairs
@@ -687,7 +732,7 @@ __device__ __noinline__ void second_variation(FrontSmem<N>& S, PostTab<N>& PT, i
         for (int l = 0; l < N; l++) acc_term(p10, NN[1][i][l], H.M0[l][k]);
         const ival P00 = acc_finish(p00), P01 = acc_finish(p01), P10 = acc_finish(p10);
         const ival N0 = mt2iv(NN[0][i][k]), N1 = mt2iv(NN[1][i][k]), N2 = mt2iv(NN[2][i][k]), N3 = mt2iv(NN[3][i][k]);
-        const double* il = S.invlo; const double* ih = S.invhi;
+        const double* il = c_invlo; const double* ih = c_invhi;
         const ival X3 = idivk_tab(iadd(N2, ihalf(P00)), il, ih, 3);
         const ival Z = pt(0.0);
         const ival hN0 = ihalf(N0);
@@ -721,7 +766,7 @@ __device__ __noinline__ void second_variation(FrontSmem<N>& S, PostTab<N>& PT, i
             mg = __fma_ru(PT.u.x.AM[j][row][col], j < D ? imag(S.r0[j]) : 1.0, mg);
         }
         const ival dj = acc_finish(a);
-        PT.dJ[row][col] = dj; PT.dJm[row][col] = iv2mt(dj);
+        PT.dJm[row][col] = iv2mt(dj);
         const ival jc = S.Jc[row][col], jf = iadd(jc, ihull(dj, pt(0.0)));
         S.J[row][col] = jf; PT.Jm[row][col] = iv2mt(jf); PT.Jcm[row][col] = iv2mt(jc);
         if (row < N) PT.magXu[row][col] = mg; else PT.magXv[row - N][col] = mg;
@@ -736,7 +781,7 @@ __device__ __noinline__ void second_variation(FrontSmem<N>& S, PostTab<N>& PT, i
         double s0 = __dmul_ru(S.mj.rho_psi, sm), s1 = __dmul_ru(S.mj.rho_psi_d, sm);
 #pragma unroll
         for (int cc = 0; cc < D; cc++) { const double wm = imag(S.Ws[cc][bb]); s0 = __fma_ru(PT.magXu[a][cc], wm, s0); s1 = __fma_ru(PT.magXv[a][cc], wm, s1); }
-        S.Fk[0][a][bb] = iadd(S.Fk[0][a][bb], sym(s0));
+        S.fk()[0][a][bb] = iadd(S.fk()[0][a][bb], sym(s0));
         S.boxFd[a][bb] = s1;
     }
     __syncthreads();
@@ -985,7 +1030,7 @@ __device__ __noinline__ void deriv_entries(const ival* __restrict__ Fk0, const d
 // ------------------------------------------------------------------------------------------------
 template <int N>
 __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gdesc, ccp_front_result* __restrict__ gres,
-                          ccp_series_rec* __restrict__ series, int series_cap) {
+                          ccp_series_rec* __restrict__ series, int series_cap, unsigned align_sm) {
     using L = Lay<N>;
     constexpr int D = 2 * N;
     const int tid = threadIdx.x;
@@ -995,14 +1040,15 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
     // ---- stage the descriptor: coalesced 16-byte loads HBM -> shared ----
     {
         const int4* src = reinterpret_cast<const int4*>(gdesc);
-        int4* dst = reinterpret_cast<int4*>(&S.un.desc);
+        int4* dst = reinterpret_cast<int4*>(&T[0][0]);       // staged in the (still unused) table array
         for (int i = tid; i < (int)(sizeof(ccp_front_desc) / 16); i += NT) dst[i] = src[i];
     }
     __syncthreads();
-    const int p = S.un.desc.order, g = S.un.desc.grid, step_log2 = S.un.desc.step_log2;
-    const double L_minus = S.un.desc.L_minus;
+    const ccp_front_desc& sdesc = *reinterpret_cast<const ccp_front_desc*>(&T[0][0]);
+    const int p = sdesc.order, g = sdesc.grid, step_log2 = sdesc.step_log2;
+    const double L_minus = sdesc.L_minus;
     int status = CCP_OK;
-    if (S.un.desc.n != N || p < 2 || p > CCP_MAX_ORDER || g < 0 || g > GMAX || step_log2 < 1 || step_log2 > 20 || !(L_minus > 0) || !isfinite(L_minus) ||
+    if (sdesc.n != N || p < 2 || p > CCP_MAX_ORDER || g < 0 || g > GMAX || step_log2 < 1 || step_log2 > 20 || !(L_minus > 0) || !isfinite(L_minus) ||
         ldexp(L_minus, step_log2) > 16777216.0)          // more than 2^24 steps: the 32-bit step and sub-interval counters would overflow
         status = CCP_ST_BAD_DESC;
     if (status != CCP_OK) {
@@ -1015,7 +1061,7 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
     }
     const double h = ldexp(1.0, -step_log2);
     {
-        const ccp_front_desc& d = S.un.desc;
+        const ccp_front_desc& d = sdesc;
         if (tid < N) S.bpar[tid] = fromc(d.b[tid]);
         if (tid < N - 1) S.cpar[tid] = fromc(d.c[tid]);
         if (tid < D) {
@@ -1029,10 +1075,9 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
         if (tid >= 32 && tid < 32 + D + 1) { const int j = tid - 32; S.r0m[j] = j < D ? iv2mt(fromc(d.Uxy[j])) : ptm(1.0); }
         for (int t = tid; t < N * N; t += NT) { const int j = t / N, k = t % N; S.Errm[j][k] = iv2mt(fromc(d.Eu_err[j * CCP_MAX_N + k])); }
         for (int t = tid; t < N * N; t += NT) { int j = t / N, k = t % N; S.Err[j][k] = fromc(d.Eu_err[j * CCP_MAX_N + k]); }
-        if (tid >= 32 && tid < 32 + KMAX + 2) { const int k = tid - 32; if (k >= 1) { S.invlo[k] = __ddiv_rd(1.0, (double)k); S.invhi[k] = __ddiv_ru(1.0, (double)k); S.invs[k] = __dmul_ru(__ddiv_ru(1.0, (double)k), 1.0000000000000009); } else { S.invlo[0] = S.invhi[0] = S.invs[0] = 0.0; } }
     }
     for (int t = tid; t < (int)(sizeof(ccp_front_result) / 8); t += NT) reinterpret_cast<double*>(gres)[t] = 0.0;
-    __syncthreads();                                // the descriptor (un.desc) is dead from here on
+    __syncthreads();                                // the staged descriptor is dead from here on
     if (tid == 0) { S.mj = majorant<N>(S.bpar, S.cpar, p, h); S.flag = 0; S.renorms = 0; S.sc = pt(1.0); }
     if (tid >= 32 && tid < 32 + N * N) { const int t = tid - 32; S.G[t / N][t % N] = pt(t / N == t % N ? 1.0 : 0.0); }
     if (tid == 32) majorant2<N>(S.bpar, S.cpar, h, S.g15);
@@ -1128,6 +1173,7 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
         PROF_T0();
         TRC_DECL();
         TRC(1);
+        if (align_sm != ~0u) { if (tid == 0) sm_align_wait(align_sm); __syncthreads(); }
         const bool last = (s == Stot - 1);
         const double hs = last ? __dadd_ru(L_minus, -tprev.hi) : h;
         const int nxt = cur ^ 1;
@@ -1209,10 +1255,10 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
         };
         // phi warp, B lanes: the Cauchy sum (H w)[kc] is v'[kc]:  v[kc+1] = sum/(kc+1), u[kc+2] = v[kc+1]/(kc+2), z = -u  (no scratch round trip)
         auto store_vuz = [&](int kc, const ival& f) {
-            const mt vn = mt_scale(iv2mt(f), S.invhi[kc + 1], S.invs[kc + 1]);
+            const mt vn = mt_scale(iv2mt(f), c_invhi[kc + 1], c_invs[kc + 1]);
             T[0][rowV + kc + 1] = vn;
             if (kc + 2 <= p) {
-                const mt un = mt_scale(vn, S.invhi[kc + 2], S.invs[kc + 2]);
+                const mt un = mt_scale(vn, c_invhi[kc + 2], c_invs[kc + 2]);
                 T[0][rowU + kc + 2] = un;
                 mt zn; zn.m = -un.m; zn.t = un.t;
                 T[0][rowZ + kc + 2] = zn;
@@ -1223,7 +1269,7 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
             if (lane < N * D) {
                 const ival s0 = S.un.scratch[cs0], s1 = S.un.scratch[cs1], s2 = S.un.scratch[cs2];
                 const mt pvk = Tf[rowV + kc];
-                const double ih = S.invhi[kc + 1], ihs = S.invs[kc + 1];
+                const double ih = c_invhi[kc + 1], ihs = c_invs[kc + 1];
                 T[0][rowV + kc + 1] = mt_scale(iv2mt(iadd(iadd(s0, s1), s2)), ih, ihs);
                 T[0][rowU + kc + 1] = kc == 0 ? pvk : mt_scale(pvk, ih, ihs);
             }
@@ -1342,15 +1388,6 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
         __syncthreads();
         PROF(2);
         TRC(4);
-        // ---- frame tables F_k = Psi^u_k * Ws (the box for truncation and for Psi(phi) - Psi(x) is added to F_0 below) ----
-        //      grid == 0: flow map only (boundaryValueProblem::Gxy / DGxy; include/ccp.h flow_P): no frame tables, no grid loop
-        if (g > 0) for (int t = tid; t < (p + 1) * N * N; t += NT) {
-            const int k = t / (N * N), a = (t / N) % N, bb = t % N;
-            acc4 ac = acc_zero();
-#pragma unroll
-            for (int cc = 0; cc < D; cc++) acc_term(ac, T[L::PU(a, cc)][k], S.Wm[cc][bb]);
-            S.Fk[k][a][bb] = acc_finish(ac);
-        }
         // ---- first / last frame data (topFrame::getFirstFrame / getLastFrame): rare ----
         if (s == 0) {
             for (int t = tid; t < D * N; t += NT) { const int rr = t / N, k = t % N; gres->first_frame[rr * (CCP_MAX_N + 1) + k] = toc(S.Ws[rr][k]); }
@@ -1367,6 +1404,16 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
             ival du, dv; phi_prime<N>(S, Tf, tid, p, cur, hs, tl, hs, mj, du, dv);
             gres->last_frame[tid * ld + N] = toc(du);
             gres->last_frame[(N + tid) * ld + N] = toc(dv);
+        }
+        if ((s == 0 || last) && g > 0) __syncthreads();      // phi_prime read Psi^v rows that the frame tables are about to overlay
+        // ---- frame tables F_k = Psi^u_k * Ws (the box for truncation and for Psi(phi) - Psi(x) is added to F_0 below) ----
+        //      grid == 0: flow map only (boundaryValueProblem::Gxy / DGxy; include/ccp.h flow_P): no frame tables, no grid loop
+        if (g > 0) for (int t = tid; t < (p + 1) * N * N; t += NT) {
+            const int k = t / (N * N), a = (t / N) % N, bb = t % N;
+            acc4 ac = acc_zero();
+#pragma unroll
+            for (int cc = 0; cc < D; cc++) acc_term(ac, T[L::PU(a, cc)][k], S.Wm[cc][bb]);
+            S.fk()[k][a][bb] = acc_finish(ac);
         }
         __syncthreads();                            // Fk complete; all Taylor tables and un.scratch are dead from here (PT overlays them)
         PROF(3);
@@ -1385,7 +1432,7 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
             constexpr int NN = N * N, NGRP = 32 / NN, PPL = (GMAX + NGRP - 1) / NGRP;
             const int c = lane % NN, grp = lane / NN;
             if (grp < NGRP) {
-                const ival* q = &S.Fk[0][0][0] + p * NN + c;
+                const ival* q = &S.fk()[0][0][0] + p * NN + c;
                 ival acc[PPL];
                 double tl[PPL], th[PPL];
                 const ival top = *q;
@@ -1425,7 +1472,7 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
 #pragma unroll
             for (int a = 0; a < N; a++)
 #pragma unroll
-                for (int bb = 0; bb < N; bb++) Fm[a][bb] = (t == 0) ? S.Fk[0][a][bb] : EV[(t * N + a) * N + bb];
+                for (int bb = 0; bb < N; bb++) Fm[a][bb] = (t == 0) ? S.fk()[0][a][bb] : EV[(t * N + a) * N + bb];
             const ival dt = Det<N>::det(Fm);
             DT[t] = S.renorms ? imul_nl(dt, S.sc) : dt;          // determinant of the TRUE frame (renormalise)
         }
@@ -1449,7 +1496,7 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
                     for (int a = 0; a < N; a++)
 #pragma unroll
                         for (int bb = 0; bb < N; bb++) Fm[a][bb] = EV[((g + 1 + gi) * N + a) * N + bb];
-                    deriv_entries<N>(&S.Fk[0][0][0], &S.boxFd[0][0], p, tl, th, Dm);
+                    deriv_entries<N>(&S.fk()[0][0][0], &S.boxFd[0][0], p, tl, th, Dm);
                     dD = jacobi_derivative<N>(Fm, Dm);
                     if (S.renorms) dD = imul_nl(dD, S.sc);
                 }
@@ -1534,15 +1581,18 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
 }
 
 template <int N>
-__global__ void __launch_bounds__(NT, (N == 4 ? 4 : (N == 3 ? 7 : 8))) front_kernel(const ccp_front_desc* __restrict__ descs, ccp_front_result* __restrict__ results,
-                                                      const int* __restrict__ index, int count, ccp_series_rec* series, int series_cap) {
+__global__ void __launch_bounds__(NT, (N == 4 ? 4 : 8)) front_kernel(const ccp_front_desc* __restrict__ descs, ccp_front_result* __restrict__ results,
+                                                      const int* __restrict__ index, int count, ccp_series_rec* series, int series_cap, int flags) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FrontSmem<N>& S = *reinterpret_cast<FrontSmem<N>*>(smem_raw);
+    const unsigned align_sm = ((flags & 1) && series == nullptr && count > 1) ? sm_id() : ~0u;      // single fronts (plots) run alone
+    if (align_sm != ~0u && threadIdx.x == 0) sm_align_join(align_sm);
     for (int w = blockIdx.x; w < count; w += gridDim.x) {
         const int f = index ? index[w] : w;
-        run_front<N>(S, descs + f, results + f, series, series_cap);
+        run_front<N>(S, descs + f, results + f, series, series_cap, align_sm);
         __syncthreads();
     }
+    if (align_sm != ~0u && threadIdx.x == 0) sm_align_leave(align_sm);
 }
 
 } // namespace ccp

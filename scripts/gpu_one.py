@@ -3,6 +3,9 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import __graft_entry__ as ge
 pkg = ge.load_package(); abi = pkg.abi
+if os.environ.get("CCP_LIB"):                      # experiment builds (e.g. libccp_b200_x.so)
+    import ctypes as C, ccp_b200
+    ccp_b200._lib = abi.bind(C.CDLL(os.path.join(pkg.PKG_DIR, os.environ["CCP_LIB"])))
 eng = pkg.Engine(0)
 nf = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 L = float(sys.argv[2]) if len(sys.argv) > 2 else 0.0
