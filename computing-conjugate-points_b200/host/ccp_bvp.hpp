@@ -20,6 +20,7 @@
 #include "ccp_frame_det.hpp"
 #include <algorithm>
 #include <cmath>
+#include <thread>
 
 namespace ccp_host {
 
@@ -43,6 +44,23 @@ inline interval sqr(const interval& a) {
 inline interval sqrt(const interval& a) { return interval(a.lo > 0 ? std::max(0.0, dn(std::sqrt(a.lo))) : 0.0, up(std::sqrt(std::max(a.hi, 0.0)))); }
 }
 
+// The per-front host algebra of a batched step (descriptor marshalling, Krawczyk operator, 6x6 interval products) is independent
+// between fronts: with 1,024 fronts it is longer than the launch itself when run on one host thread, so the loops over fronts are
+// split over the host cores.  Exceptions must not escape f.
+template <class F> inline void parallel_for(size_t n, F f) {
+    const size_t hw = std::max(1u, std::thread::hardware_concurrency());
+    const size_t nt = std::min(hw, n / 16);                 // below 32 fronts a thread costs more than it saves
+    if (nt <= 1) { for (size_t i = 0; i < n; i++) f(i); return; }
+    std::vector<std::thread> th;
+    const size_t chunk = (n + nt - 1) / nt;
+    for (size_t t = 0; t < nt; t++) {
+        const size_t lo = t * chunk, hi = std::min(n, lo + chunk);
+        if (lo >= hi) break;
+        th.emplace_back([=] { for (size_t i = lo; i < hi; i++) f(i); });
+    }
+    for (auto& x : th) x.join();
+}
+
 struct FlowSet {                 // what getPointNbd / (*pF).A hand to C0Rect2Set / C1Rect2Set
     IVector p_i, Uxy;            // 2n each
     DMatrix A_i;                 // 2n x 2n point matrix
@@ -62,6 +80,7 @@ class boundaryValueProblem {
         if (n < 2 || n > CCP_MAX_N) throw std::invalid_argument("n out of range");
     }
     int launches() const { return launches_; }            // launches of validated integrations so far (all rungs)
+    double kernel_ms() const { return kernel_ms_; }       // device time of those launches (slowest device per launch)
     // enclosure of the time-T image of the set (Gxy)
     IVector Gxy(const FlowSet& s, double T) { return run({s}, {T})[0].image; }
     // enclosure of [D Phi_T] * A_i over the set (DGxy before the factor DW)
@@ -73,7 +92,7 @@ class boundaryValueProblem {
         const int D = 2 * n_;
         std::vector<ccp_front_desc> d(sets.size());
         std::vector<ccp_front_result> r(sets.size());
-        for (size_t q = 0; q < sets.size(); q++) {
+        parallel_for(sets.size(), [&](size_t q) {
             const FlowSet& s = sets[q];
             ccp_front_desc& e = d[q];
             e = ccp_front_desc{};
@@ -87,9 +106,9 @@ class boundaryValueProblem {
                 e.Uxy[i] = to_c(s.Uxy[i]);
                 for (int j = 0; j < D; j++) e.A_u[i * CCP_MAX_DIM + j] = sg * s.A_i[i][j];
             }
-        }
+        });
         if (ccp_frame_count_batch_multi(d.data(), d.size(), r.data()) != 0) throw std::runtime_error(std::string("ccp: ") + ccp_last_error());
-        launches_++;
+        launches_++; kernel_ms_ += ccp_last_kernel_ms();
         // step ladder: integrations whose a-priori enclosure failed with the coarse step are re-run with the next finer one
         for (int st = step_ + 1; st <= finest_; st++) {
             std::vector<size_t> redo;
@@ -98,11 +117,11 @@ class boundaryValueProblem {
             std::vector<ccp_front_desc> d2(redo.size()); std::vector<ccp_front_result> r2(redo.size());
             for (size_t k = 0; k < redo.size(); k++) { d2[k] = d[redo[k]]; d2[k].step_log2 = st; }
             if (ccp_frame_count_batch_multi(d2.data(), d2.size(), r2.data()) != 0) throw std::runtime_error(std::string("ccp: ") + ccp_last_error());
-            launches_++;
+            launches_++; kernel_ms_ += ccp_last_kernel_ms();
             for (size_t k = 0; k < redo.size(); k++) r[redo[k]] = r2[k];
         }
         std::vector<Out> out(sets.size());
-        for (size_t q = 0; q < sets.size(); q++) {
+        parallel_for(sets.size(), [&](size_t q) {
             Out& o = out[q];
             o.status = r[q].status;
             o.image.resize(D); o.deriv_A.assign(D, IVector(D));
@@ -112,7 +131,7 @@ class boundaryValueProblem {
                 o.image[i] = m(r[q].last_frame[i * (CCP_MAX_N + 2) + n_ + 1]);
                 for (int j = 0; j < D; j++) o.deriv_A[i][j] = m(r[q].flow_P[i * CCP_MAX_DIM + j]);
             }
-        }
+        });
         return out;
     }
 
@@ -165,27 +184,33 @@ class boundaryValueProblem {
         // The operator needs G at the POINT (C^0 images of XY_pt, sets 0 and 1) and DG over the BOX (C^1 maps of XY_pt + XY_nbd, sets 2
         // and 3).  In the Newton phase of the driver (heteroclinic.cpp:186-191: 20 steps with XY_nbd = 0) box and point coincide, and
         // since one integration delivers image and derivative alike only two of the four are launched.
-        std::vector<FlowSet> sets; std::vector<double> times; std::vector<size_t> slot(4 * in.size());
+        std::vector<size_t> slot(4 * in.size()), first(in.size() + 1, 0);
+        std::vector<char> thin(in.size(), 1);
         for (size_t fi = 0; fi < in.size(); fi++) {
+            for (const interval& e : in[fi].XY_nbd) thin[fi] = thin[fi] && e.lo == 0.0 && e.hi == 0.0;
+            first[fi + 1] = first[fi] + (thin[fi] ? 2 : 4);
+        }
+        std::vector<FlowSet> sets(first[in.size()]); std::vector<double> times(first[in.size()]);
+        parallel_for(in.size(), [&](size_t fi) {
             const StepIn& q = in[fi];
             IVector X_pt(q.XY_pt.begin(), q.XY_pt.begin() + n), Y_pt(q.XY_pt.begin() + n, q.XY_pt.end());
             IVector X_nbd(q.XY_nbd.begin(), q.XY_nbd.begin() + n), Y_nbd(q.XY_nbd.begin() + n, q.XY_nbd.end());
-            bool thin = true;
-            for (const interval& e : q.XY_nbd) thin = thin && e.lo == 0.0 && e.hi == 0.0;
-            FlowSet f[4] = {getPointNbd(q.unstable, X_pt, zero), getPointNbd(q.stable, Y_pt, zero), getPointNbd(q.unstable, X_pt, X_nbd), getPointNbd(q.stable, Y_pt, Y_nbd)};
+            const int nk = thin[fi] ? 2 : 4;
             for (int k = 0; k < 4; k++) {
-                if (thin && k >= 2) { slot[4 * fi + k] = slot[4 * fi + k - 2]; continue; }
-                f[k].params = q.params; slot[4 * fi + k] = sets.size(); sets.push_back(f[k]); times.push_back(q.T);
+                if (k >= nk) { slot[4 * fi + k] = slot[4 * fi + k - 2]; continue; }
+                FlowSet fs = getPointNbd(k % 2 ? q.stable : q.unstable, k % 2 ? Y_pt : X_pt, k < 2 ? zero : (k % 2 ? Y_nbd : X_nbd));
+                fs.params = q.params;
+                slot[4 * fi + k] = first[fi] + k; sets[first[fi] + k] = std::move(fs); times[first[fi] + k] = q.T;
             }
-        }
+        });
         const std::vector<Out> all = run(sets, times);
         std::vector<StepOut> res(in.size());
-        for (size_t f = 0; f < in.size(); f++) {
+        parallel_for(in.size(), [&](size_t f) {
             const StepIn& q = in[f];
             const Out o[4] = {all[slot[4 * f]], all[slot[4 * f + 1]], all[slot[4 * f + 2]], all[slot[4 * f + 3]]};
             res[f].success = false; res[f].kraw_image.assign(D, interval(0.0));
             bool okflow = true; for (int k = 0; k < 4; k++) okflow = okflow && o[k].status == CCP_OK;
-            if (!okflow) continue;                                   // like a CAPD exception inside one parameter value: this front fails, the sweep goes on
+            if (!okflow) return;                                     // like a CAPD exception inside one parameter value: this front fails, the sweep goes on
             IVector X_pt(q.XY_pt.begin(), q.XY_pt.begin() + n), X_nbd(q.XY_nbd.begin(), q.XY_nbd.begin() + n);
             const IVector& G_x = o[0].image; const IVector& G_y = o[1].image;
             IVector G(D);
@@ -213,7 +238,7 @@ class boundaryValueProblem {
                 for (int j = 0; j < 2 * D; j++) M[c][j] /= dv;
                 for (int r = 0; r < D; r++) if (r != c) { const double fct = M[r][c]; for (int j = 0; j < 2 * D; j++) M[r][j] -= fct * M[c][j]; }
             }
-            if (singular) continue;
+            if (singular) return;
             // new_Nbd = -C G + (I - C DG) XY_nbd
             IVector new_Nbd(D);
             for (int i = 0; i < D; i++) {
@@ -231,7 +256,7 @@ class boundaryValueProblem {
             bool ok = gy.lo > 0 || gy.hi < 0;
             for (int i = 0; i < D && ok; i++) ok = q.XY_nbd[i].lo < new_Nbd[i].lo && new_Nbd[i].hi < q.XY_nbd[i].hi;     // subsetInterior
             res[f].success = ok;
-        }
+        });
         return res;
     }
     // the reference's single-front signature
@@ -310,7 +335,7 @@ class boundaryValueProblem {
     }
 
   private:
-    int n_; IVector params_; int order_, step_, finest_; int launches_ = 0;
+    int n_; IVector params_; int order_, step_, finest_; int launches_ = 0; double kernel_ms_ = 0.0;
 };
 
 } // namespace ccp_host
