@@ -1173,7 +1173,7 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
         PROF_T0();
         TRC_DECL();
         TRC(1);
-        if (align_sm != ~0u) { if (tid == 0) sm_align_wait(align_sm); __syncthreads(); }
+        if (align_sm != ~0u) { if (tid == 0) sm_align_wait(align_sm); __syncthreads(); }    // once per step: every 2nd step or twice per step are both slower (profiles/r2_v22_align_experiments.txt)
         const bool last = (s == Stot - 1);
         const double hs = last ? __dadd_ru(L_minus, -tprev.hi) : h;
         const int nxt = cur ^ 1;
