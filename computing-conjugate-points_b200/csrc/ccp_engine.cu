@@ -145,6 +145,12 @@ int init_device(Dev& dv, int device) {
         CK(cudaStreamSynchronize(dv.stream));
         CK(cudaFree(d_tab));
     }
+    // per-lane constants of the table loop (ccp_kernel.cuh: g_lanec), one table per n
+    ccp::lanec_table_kernel<2><<<1, ccp::NT, 0, dv.stream>>>();
+    ccp::lanec_table_kernel<3><<<1, ccp::NT, 0, dv.stream>>>();
+    ccp::lanec_table_kernel<4><<<1, ccp::NT, 0, dv.stream>>>();
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(dv.stream));
     CK(cudaFuncSetAttribute(ccp::dfu_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ccp::DfuSmem<2>)));
     CK(cudaFuncSetAttribute(ccp::dfu_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ccp::DfuSmem<3>)));
     CK(cudaFuncSetAttribute(ccp::dfu_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ccp::DfuSmem<4>)));

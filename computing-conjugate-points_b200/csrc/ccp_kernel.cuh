@@ -10,6 +10,7 @@
 // of the frame's dependence on the front's box and centres advanced by increments), operation for operation.
 #pragma once
 #include "ccp_interval.cuh"
+#include <cuda/std/type_traits>
 #include "../../include/ccp.h"
 
 namespace ccp {
@@ -47,7 +48,7 @@ struct __align__(16) SmAlign { unsigned members, count, gen, pad; };       // on
 __device__ SmAlign g_sm_align[SM_ALIGN_SLOTS];
 __device__ __forceinline__ unsigned sm_id() { unsigned v; asm volatile("mov.u32 %0, %%smid;" : "=r"(v)); return v % SM_ALIGN_SLOTS; }
 __device__ __forceinline__ void sm_align_release(SmAlign& a) { *(volatile unsigned*)&a.count = 0u; atomicAdd(&a.gen, 1u); }
-__device__ __forceinline__ void sm_align_join(unsigned sm) { atomicAdd(&g_sm_align[sm].members, 1u); }
+__device__ __forceinline__ unsigned sm_align_join(unsigned sm) { return atomicAdd(&g_sm_align[sm].members, 1u); }
 __device__ __forceinline__ void sm_align_leave(unsigned sm) {
     SmAlign& a = g_sm_align[sm];
     const unsigned left = atomicSub(&a.members, 1u) - 1u;
@@ -151,6 +152,8 @@ struct FrontSmem {
     ival R[D][N], Ps[D][N], S0[D][N];
     mt Rm[D][N], Tdm[D][N], Psm[D][N];       // (mid,t) forms of R, S0 + R, Ps (step start) for the set update
     ival r0[D], Err[N][N], X[D], y[D], Jc[D][D], Kc[D][D], J[D][D], Ws[D][N], bpar[N], cpar[NE];   // y, Kc: increments Phi(x) - x, DPhi(x) - I
+    // During the table loop Jc, Kc, J are dead: they hold the second scratch set (order J+1 of a stage), a dummy slot and, from INV_OFF, the reciprocal table
+    static constexpr int INV_OFF = 3 * D * D - (KMAX + 2);
     mt Wm[D][N];
     HullM<N> hm;
     ParM<N> pm;
@@ -162,6 +165,8 @@ struct FrontSmem {
     ival G[N][N], sc;                        // true frame = normalised frame * G ;  sc encloses det G > 0
     Majorant mj;
     double g15[2];
+    struct { int zero_count, failure_count, first_failure, n_conj; ival tprev, det_first, det_last; } st;
+    struct { int p, g, step_log2, Stot, renorm_mask, series_cap; double L_minus, h; const ccp_front_desc* gdesc; ccp_front_result* gres; ccp_series_rec* series; } cfg;      // the front's configuration: read where it is used instead of living in registers     // tallies of the front (warp 0) and the time reached: in shared memory, not in registers that would be live across the whole step
     union alignas(16) {
         ival scratch[Lay<N>::NB + Lay<N>::NC + 2 * N];   // table loop: Cauchy sums awaiting combination; then [0,0]; then the newest g, q
         mt JCr[2 * N][2 * N];                // set update: J*C - C+
@@ -174,6 +179,7 @@ static_assert(sizeof(PostTab<2>) <= sizeof(FrontSmem<2>::T) && sizeof(PostTab<3>
 static_assert(FrontSmem<3>::TROWS == Lay<3>::NS, "n = 3: the overlay must not enlarge the table array");
 static_assert(sizeof(FrontSmem<3>) <= 28160, "n = 3: 8 fronts per SM (228 KB of shared memory, 1 KB reserved per CTA)");
 static_assert(FrontSmem<2>::FKROW > Lay<2>::PU(1, 3) && FrontSmem<3>::FKROW > Lay<3>::PU(2, 5) && FrontSmem<4>::FKROW > Lay<4>::PU(3, 7), "Fk must not overlay the Psi^u rows it is built from");
+static_assert(offsetof(FrontSmem<3>, Kc) == offsetof(FrontSmem<3>, Jc) + sizeof(FrontSmem<3>::Jc) && offsetof(FrontSmem<3>, J) == offsetof(FrontSmem<3>, Kc) + sizeof(FrontSmem<3>::Kc), "Jc, Kc, J are contiguous");
 static_assert(sizeof(ccp_front_desc) <= sizeof(FrontSmem<2>::T), "the descriptor is staged in the table array");
 static_assert(sizeof(ccp_front_desc) % 16 == 0, "descriptors are staged with 16-byte loads");
 static_assert(sizeof(ccp_front_result) % 16 == 0, "result records are 16-byte aligned");
@@ -467,63 +473,83 @@ __device__ __forceinline__ TaskR make_taskr(const Task& t) {
     r.ok = opaqueu((unsigned)t.out | ((unsigned)(t.kind + 1) << 16));
     return r;
 }
-// Cauchy sums of TWO consecutive orders (kk, kk+1) of one task in one pass over the operands.  Summation order of every sum
-// (oracle/c1.hpp:cauchy_order): interior terms j = 1..order-1 ascending, then the end terms j = 0 and j = order.  The end terms
-// are the only ones that involve coefficients of that order, so while the sum of order kk is completed (s0), the interior of
-// order kk+1 (s1) is accumulated from the same two loads: 2 LDS.128 + 8 DFMA per term, 8 independent FMA chains.
-//   s0 += a[j-1] * b[kk+1-j]   (term j-1 of order kk)        s1 += a[j] * b[kk+1-j]   (term j of order kk+1)
+// Cauchy sums of the orders J (s0) and J+1 (s1), J even, of one task in one pass over the operands.  Summation order of every sum
+// (oracle/c1.hpp:cauchy_order): interior terms l = 1..order-1 ascending, then the end terms l = 0 and l = order:
+//   order J   :  sum_{l=1}^{J-1} a[l] b[J-l]   +  a0 b[J]    +  a[J] b0
+//   order J+1 :  sum_{l=1}^{J}   a[l] b[J+1-l] +  a0 b[J+1]  +  a[J+1] b0
 // a(0), b(0) live at their own offsets (w0 = u0 - 1/2 and z0 = 1 - u0 differ from u only in order 0).
-__device__ __forceinline__ void run_block(const mt* __restrict__ Tf, const TaskR& t, int kk, acc4& s0, acc4& s1) {
-    s0 = acc_zero(); s1 = acc_zero();
-    if (kk >= 1) {
+// pass_early: everything that does not involve a[J], a[J+1] (for the products H*w and M*Psi^u these are the coefficients the stage is
+// waiting for) and precedes them in the summation order: 2 LDS.128 + 8 DFMA per term, 8 independent FMA chains.
+// FAST = the stage is known to have J >= 2 and a second order (every stage of an even-order run but the first): no branches, so that
+// the two orders' dependent chains end up in one basic block and the scheduler interleaves them (a warp issues in order).
+template <bool FAST>
+__device__ __forceinline__ void pass_early(const mt* __restrict__ Tf, const TaskR& t, int J, acc4& s0, acc4& s1) {
+    if (FAST || J >= 2) {
         const mt* pa = Tf + t.offA() + 1;
-        const mt* pb = Tf + t.offB() + kk;
-        mt xp = *pa;
-        const mt y1 = *pb;
-        mt x = pa[1], y = pb[-1];                                // operands of the NEXT term are loaded one term ahead; the
-        acc_term(s1, xp, y1);                                    // j = 1     // last prefetch reads a valid, unused table slot
-        pa += 2; pb -= 2;
+        const mt* pb = Tf + t.offB() + J;
+        mt x = *pa, yp = *pb, y = pb[-1];                        // x = a[l], yp = b[J+1-l], y = b[J-l];  operands of the NEXT term are
+        pa++; pb -= 2;                                           // loaded one term ahead; the last prefetch reads valid, unused table slots
 #pragma unroll 2
-        for (int j = 2; j <= kk; j++) { const mt xn = *pa, yn = *pb; acc_term(s0, xp, y); acc_term(s1, x, y); xp = x; x = xn; y = yn; pa++; pb--; }
-        acc_term(s0, Tf[t.offa0()], Tf[t.offB() + kk]);
-        acc_term(s0, xp, Tf[t.offb0()]);                         // xp = a[kk]
-    } else {
-        acc_term(s0, Tf[t.offa0()], Tf[t.offb0()]);
+        for (int l = 1; l < J; l++) { const mt xn = *pa, yn = *pb; acc_term(s1, x, yp); acc_term(s0, x, y); yp = y; x = xn; y = yn; pa++; pb--; }
+        acc_term(s0, Tf[t.offa0()], Tf[t.offB() + J]);
     }
 }
-// end terms of order ord >= 1:  s += a0 * b[ord];  s += a[ord] * b0
-__device__ __forceinline__ void run_ends(const mt* __restrict__ Tf, const TaskR& t, int ord, acc4& s) {
-    acc_term(s, Tf[t.offa0()], Tf[t.offB() + ord]);
-    acc_term(s, Tf[t.offA() + ord], Tf[t.offb0()]);
+// pass_late: the remaining terms, in order.  two = the stage has a second order.
+template <bool FAST>
+__device__ __forceinline__ void pass_late(const mt* __restrict__ Tf, const TaskR& t, int J, bool two, acc4& s0, acc4& s1) {
+    const mt a0 = Tf[t.offa0()], b0 = Tf[t.offb0()];
+    if (FAST || J >= 2) {
+        const mt aJ = Tf[t.offA() + J];
+        acc_term(s0, aJ, b0);
+        if (FAST || two) {
+            acc_term(s1, aJ, Tf[t.offB() + 1]);
+            acc_term(s1, a0, Tf[t.offB() + J + 1]);
+            acc_term(s1, Tf[t.offA() + J + 1], b0);
+        }
+    } else {
+        acc_term(s0, a0, b0);
+        if (two) { acc_term(s1, a0, Tf[t.offB() + 1]); acc_term(s1, Tf[t.offA() + 1], b0); }
+    }
 }
 // Two tasks that SHARE their first operand series (Psi warp: one M-series times two columns of Psi): 3 LDS.128 + 16 DFMA per term.
-__device__ __forceinline__ void run_block_pair(const mt* __restrict__ Tf, const TaskR& t0, const TaskR& t1, int kk,
-                                               acc4& a0, acc4& a1, acc4& b0, acc4& b1) {
-    a0 = acc_zero(); a1 = acc_zero(); b0 = acc_zero(); b1 = acc_zero();
-    const mt x0 = Tf[t0.offa0()];
-    if (kk >= 1) {
-        const mt* pa = Tf + t0.offA() + 1; const mt* pb = Tf + t0.offB() + kk; const mt* qb = Tf + t1.offB() + kk;
-        mt xp = *pa;
-        const mt yk = *pb, zk = *qb;
-        mt x = pa[1], y = pb[-1], z = qb[-1];
-        acc_term(a1, xp, yk); acc_term(b1, xp, zk);              // j = 1
-        pa += 2; pb -= 2; qb -= 2;
+template <bool FAST>
+__device__ __forceinline__ void pair_early(const mt* __restrict__ Tf, const TaskR& t0, const TaskR& t1, int J,
+                                           acc4& a0, acc4& a1, acc4& b0, acc4& b1) {
+    if (FAST || J >= 2) {
+        const mt* pa = Tf + t0.offA() + 1; const mt* pb = Tf + t0.offB() + J; const mt* qb = Tf + t1.offB() + J;
+        mt x = *pa, yp = *pb, zp = *qb, y = pb[-1], z = qb[-1];
+        pa++; pb -= 2; qb -= 2;
 #pragma unroll 2
-        for (int j = 2; j <= kk; j++) {
+        for (int l = 1; l < J; l++) {
             const mt xn = *pa, yn = *pb, zn = *qb;
-            acc_term(a0, xp, y); acc_term(b0, xp, z); acc_term(a1, x, y); acc_term(b1, x, z);
-            xp = x; x = xn; y = yn; z = zn; pa++; pb--; qb--;
+            acc_term(a1, x, yp); acc_term(b1, x, zp); acc_term(a0, x, y); acc_term(b0, x, z);
+            yp = y; zp = z; x = xn; y = yn; z = zn; pa++; pb--; qb--;
         }
-        acc_term(a0, x0, yk); acc_term(b0, x0, zk);
-        acc_term(a0, xp, Tf[t0.offb0()]); acc_term(b0, xp, Tf[t1.offb0()]);
-    } else {
-        acc_term(a0, x0, Tf[t0.offb0()]); acc_term(b0, x0, Tf[t1.offb0()]);
+        const mt x0 = Tf[t0.offa0()];
+        acc_term(a0, x0, Tf[t0.offB() + J]); acc_term(b0, x0, Tf[t1.offB() + J]);
     }
 }
-__device__ __forceinline__ void run_ends_pair(const mt* __restrict__ Tf, const TaskR& t0, const TaskR& t1, int ord, acc4& a, acc4& b) {
-    const mt x0 = Tf[t0.offa0()], xk = Tf[t0.offA() + ord];
-    acc_term(a, x0, Tf[t0.offB() + ord]); acc_term(b, x0, Tf[t1.offB() + ord]);
-    acc_term(a, xk, Tf[t0.offb0()]);      acc_term(b, xk, Tf[t1.offb0()]);
+template <bool FAST>
+__device__ __forceinline__ void pair_late(const mt* __restrict__ Tf, const TaskR& t0, const TaskR& t1, int J, bool two,
+                                          acc4& a0, acc4& a1, acc4& b0, acc4& b1) {
+    const mt x0 = Tf[t0.offa0()], y0 = Tf[t0.offb0()], z0 = Tf[t1.offb0()];
+    if (FAST || J >= 2) {
+        const mt xJ = Tf[t0.offA() + J];
+        acc_term(a0, xJ, y0); acc_term(b0, xJ, z0);
+        if (FAST || two) {
+            acc_term(a1, xJ, Tf[t0.offB() + 1]);     acc_term(b1, xJ, Tf[t1.offB() + 1]);
+            acc_term(a1, x0, Tf[t0.offB() + J + 1]); acc_term(b1, x0, Tf[t1.offB() + J + 1]);
+            const mt xJ1 = Tf[t0.offA() + J + 1];
+            acc_term(a1, xJ1, y0); acc_term(b1, xJ1, z0);
+        }
+    } else {
+        acc_term(a0, x0, y0); acc_term(b0, x0, z0);
+        if (two) {
+            acc_term(a1, x0, Tf[t0.offB() + 1]); acc_term(b1, x0, Tf[t1.offB() + 1]);
+            const mt x1 = Tf[t0.offA() + 1];
+            acc_term(a1, x1, y0); acc_term(b1, x1, z0);
+        }
+    }
 }
 // product with a parameter interval of known sign: c = sg * [pl, ph], 0 <= pl <= ph.  Same end points as imul_nl(a, c).
 __device__ __forceinline__ SPar make_spar(const ival& c) {
@@ -1025,122 +1051,68 @@ __device__ __noinline__ void deriv_entries(const ival* __restrict__ Fk0, const d
         }
 }
 
-// ------------------------------------------------------------------------------------------------
-// One CTA (NT threads) = one front.  `series` (optional) receives steps*grid records.
-// ------------------------------------------------------------------------------------------------
-template <int N>
-__device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gdesc, ccp_front_result* __restrict__ gres,
-                          ccp_series_rec* __restrict__ series, int series_cap, unsigned align_sm) {
+// ---- per-lane constants of the table loop: fixed for the whole front (they depend on the lane and on n only).  Packed into a few words
+//      that travel to table_loop in registers; unpacking is one shift/mask per use. ----
+struct LaneC {
+    TaskR tA, tB, tC, tD;    // phi warp: tA = this lane's A or B task;  Psi warp: tA/tB and tC/tD = this lane's pairs of C tasks (rounds 0, 1)
+    unsigned cs;             // cs0 | cs1 << 8 | cs2 << 16 | gslot << 24       scratch slots (combine stages); gslot 255 = none
+    unsigned ap;             // ap0 | ap1 << 6 | ap2 << 12 | mscale << 18 | mcst << 19 | (mrole + 1) << 20
+    unsigned rvu;            // rowV | rowU << 16       table offsets (row * KMAX)
+    unsigned rz;             // rowZ
+    __device__ __forceinline__ int cs0() const { return (int)(cs & 0xffu); }
+    __device__ __forceinline__ int cs1() const { return (int)((cs >> 8) & 0xffu); }
+    __device__ __forceinline__ int cs2() const { return (int)((cs >> 16) & 0xffu); }
+    __device__ __forceinline__ int gslot() const { return (int)(cs >> 24); }
+    __device__ __forceinline__ int ap0() const { return (int)(ap & 0x3fu); }
+    __device__ __forceinline__ int ap1() const { return (int)((ap >> 6) & 0x3fu); }
+    __device__ __forceinline__ int ap2() const { return (int)((ap >> 12) & 0x3fu); }
+    __device__ __forceinline__ int mscale() const { return (int)((ap >> 18) & 1u); }
+    __device__ __forceinline__ int mcst() const { return (int)((ap >> 19) & 1u); }
+    __device__ __forceinline__ int mrole() const { return (int)(ap >> 20) - 1; }
+    __device__ __forceinline__ int rowV() const { return (int)(rvu & 0xffffu); }
+    __device__ __forceinline__ int rowU() const { return (int)(rvu >> 16); }
+    __device__ __forceinline__ int rowZ() const { return (int)rz; }
+};
+template <int N> struct TLC {                      // scratch layout of the table loop
     using L = Lay<N>;
-    constexpr int D = 2 * N;
-    const int tid = threadIdx.x;
-    mt (*T)[KMAX] = S.T;
-    (void)sizeof(PhaseCheck<N>);
-
-    // ---- stage the descriptor: coalesced 16-byte loads HBM -> shared ----
-    {
-        const int4* src = reinterpret_cast<const int4*>(gdesc);
-        int4* dst = reinterpret_cast<int4*>(&T[0][0]);       // staged in the (still unused) table array
-        for (int i = tid; i < (int)(sizeof(ccp_front_desc) / 16); i += NT) dst[i] = src[i];
-    }
-    __syncthreads();
-    const ccp_front_desc& sdesc = *reinterpret_cast<const ccp_front_desc*>(&T[0][0]);
-    const int p = sdesc.order, g = sdesc.grid, step_log2 = sdesc.step_log2;
-    const double L_minus = sdesc.L_minus;
-    int status = CCP_OK;
-    if (sdesc.n != N || p < 2 || p > CCP_MAX_ORDER || g < 0 || g > GMAX || step_log2 < 1 || step_log2 > 20 || !(L_minus > 0) || !isfinite(L_minus) ||
-        ldexp(L_minus, step_log2) > 16777216.0)          // more than 2^24 steps: the 32-bit step and sub-interval counters would overflow
-        status = CCP_ST_BAD_DESC;
-    if (status != CCP_OK) {
-        __syncthreads();
-        if (tid == 0) {
-            ccp_front_result z; memset(&z, 0, sizeof(z)); z.status = status; z.first_failure = -1;
-            *gres = z;
-        }
-        return;
-    }
-    const double h = ldexp(1.0, -step_log2);
-    {
-        const ccp_front_desc& d = sdesc;
-        if (tid < N) S.bpar[tid] = fromc(d.b[tid]);
-        if (tid < N - 1) S.cpar[tid] = fromc(d.c[tid]);
-        if (tid < D) {
-            ival pi = fromc(d.p_i[tid]);
-            double xm = mid_ru(pi);
-            S.x[0][tid] = xm; S.r[0][tid] = isub(pi, pt(xm)); S.r0[tid] = fromc(d.Uxy[tid]);
-        }
-        for (int t = tid; t < D * D; t += NT) { int i = t / D, j = t % D; double a = d.A_u[i * CCP_MAX_DIM + j]; S.C[0][i][j] = a; if (j < N) { S.Tc[i][j] = a; S.R[i][j] = pt(0.0); } else S.Ps[i][j - N] = pt(a); }
-        for (int t = tid; t < D * D * N; t += NT) (&S.Th[0][0][0])[t] = 0.0;
-        for (int t = tid; t < N * N; t += NT) { mt z; z.m = 0.0; z.t = 0.0; S.hm.M0[t / N][t % N] = z; S.hm.M1[t / N][t % N] = z; }
-        if (tid >= 32 && tid < 32 + D + 1) { const int j = tid - 32; S.r0m[j] = j < D ? iv2mt(fromc(d.Uxy[j])) : ptm(1.0); }
-        for (int t = tid; t < N * N; t += NT) { const int j = t / N, k = t % N; S.Errm[j][k] = iv2mt(fromc(d.Eu_err[j * CCP_MAX_N + k])); }
-        for (int t = tid; t < N * N; t += NT) { int j = t / N, k = t % N; S.Err[j][k] = fromc(d.Eu_err[j * CCP_MAX_N + k]); }
-    }
-    for (int t = tid; t < (int)(sizeof(ccp_front_result) / 8); t += NT) reinterpret_cast<double*>(gres)[t] = 0.0;
-    __syncthreads();                                // the staged descriptor is dead from here on
-    if (tid == 0) { S.mj = majorant<N>(S.bpar, S.cpar, p, h); S.flag = 0; S.renorms = 0; S.sc = pt(1.0); }
-    if (tid >= 32 && tid < 32 + N * N) { const int t = tid - 32; S.G[t / N][t % N] = pt(t / N == t % N ? 1.0 : 0.0); }
-    if (tid == 32) majorant2<N>(S.bpar, S.cpar, h, S.g15);
-    if (tid < N) {                                  // oracle/c2.hpp:make_par
-        const int i = tid;
-        mt z; z.m = 0.0; z.t = 0.0;
-        const ival b = S.bpar[i];
-        S.pm.B[i] = iv2mt(b); S.pm.B3[i] = iv2mt(imulk(b, 3)); S.pm.B6[i] = iv2mt(imulk(b, 6)); S.pm.halfB[i] = ihalf(b);
-        S.pm.Cm[i] = i > 0 ? iv2mt(S.cpar[i > 0 ? i - 1 : 0]) : z;                 S.pm.Cp[i] = i < N - 1 ? iv2mt(S.cpar[i < N - 1 ? i : 0]) : z;
-        S.pm.C2m[i] = i > 0 ? iv2mt(imulk(S.cpar[i > 0 ? i - 1 : 0], 2)) : z;      S.pm.C2p[i] = i < N - 1 ? iv2mt(imulk(S.cpar[i < N - 1 ? i : 0], 2)) : z;
-        S.pm.C2[i] = S.pm.C2p[i];
-        for (int l = 0; l < N; l++) for (int sl = 0; sl < 3; sl++) {
-            mt v = z;
-            if (i == l) v = sl == 0 ? S.pm.B6[i] : (sl == 1 ? S.pm.C2m[i] : S.pm.C2p[i]);
-            else if (l == i + 1) v = sl < 2 ? S.pm.C2p[i] : z;                    // 2 c_i
-            else if (l == i - 1) v = sl < 2 ? S.pm.C2m[i] : z;                    // 2 c_{i-1}
-            S.pm.PN[i][l][sl] = v;
-        }
-    }
-    __syncthreads();
-    Majorant mj = S.mj; mj.g1 = S.g15[0]; mj.g5 = S.g15[1];
-    if (!mj.ok) status = CCP_ST_ENCLOSURE;
-
-    // slot = task handled by this lane pair; consecutive slots go to different warps so that every phase is spread
-    // evenly over the 4 warp schedulers
-    const int wq = tid >> 5, lane = tid & 31;
+    static constexpr int ZSLOT = L::NB + L::NC;      // always-zero slot (missing chain neighbours)
+    static constexpr int GS = ZSLOT + 1;             // scratch slots of g_i (N) and q_e (N-1) of the newest order
+    static constexpr int MB = L::NA + L::NB;         // phi warp lanes: A tasks 0..NA-1 | B tasks NA..MB-1 | M/H lanes MB..MB+3N-2
+    static_assert(MB + 3 * N - 1 <= 32, "phi warp: A, B and M/H lanes side by side");
+    static_assert(GS + 2 * N - 1 < 255, "scratch slots fit 8 bits");
+};
+template <int N>
+__device__ inline LaneC make_lanec(int tid) {
+    using L = Lay<N>;
+    constexpr int D = 2 * N, ZSLOT = TLC<N>::ZSLOT, GS = TLC<N>::GS, MB = TLC<N>::MB, PZ = 2 * N - 1;
     constexpr int CROUNDS = PhaseCheck<N>::CROUNDS;
-    // phi warp: tA, tB = this lane's A and B task;  Psi warp: tA, tB, tC = this lane's C tasks of rounds 0, 1, 2
+    const int wq = tid >> 5, lane = tid & 31;
+    LaneC c;
     int pi0, pi1, pi2, pi3;
     pair_tasks<N>(wq == 1 ? lane : -1, pi0, pi1);
     pair_tasks<N>((wq == 1 && CROUNDS > 1) ? 32 + lane : -1, pi2, pi3);
-    const TaskR tA = make_taskr(wq == 0 ? (lane < L::NA ? decode_task<N>(0, lane) : decode_task<N>(1, lane - L::NA)) : decode_task<N>(2, pi0));
-    const TaskR tB = make_taskr(decode_task<N>(2, wq == 0 ? (1 << 20) : pi1));
-    const TaskR tC = make_taskr(decode_task<N>(2, pi2)), tD = make_taskr(decode_task<N>(2, pi3));
-    const mt* const Tf = &T[0][0];
-    // ---- per-lane operands of the three "combine" stages, fixed for the whole front.  Every stage is ONE branch-free
-    //      instruction stream (missing neighbours: zero parameter, clamped slot).
-    //        phi warp, lanes MB..       : one (mid,t) dot product of three parameter * series slots (parameter tables S.pm, g / q of the
-    //                                     newest order from the A lanes through scratch):  Md_i[k] = [k==0] b_i/2 - (3 b_i g_i + c g_{i-1} + c g_{i+1}),
-    //                                     Mo_e[k] = 2 c_e q_e,  H_i[k] = -(b_i g_i + c g_{i-1} + c g_{i+1})   (v' = H w)
-    //        Psi warp, lanes < N*D      : Pv[k] = (X0 + X1 + X2)/k from the C sums (scratch); Pu[k] = Pv[k-1]/k
-    //      The B lanes of the phi warp turn their own Cauchy sum (H w)[k] into v[k+1], u[k+2], z[k+2] (store_vuz).
-    constexpr int ZSLOT = L::NB + L::NC;
-    constexpr int GS = ZSLOT + 1;                    // scratch slots of g_i (N) and q_e (N-1) of the newest order
-    static_assert(sizeof(S.un) >= (GS + 2 * N - 1) * sizeof(ival), "scratch slots");
-    constexpr int PZ = 2 * N - 1;
+    c.tA = make_taskr(wq == 0 ? (lane < L::NA ? decode_task<N>(0, lane) : decode_task<N>(1, lane - L::NA)) : decode_task<N>(2, pi0));
+    c.tB = make_taskr(decode_task<N>(2, wq == 0 ? (1 << 20) : pi1));
+    c.tC = make_taskr(decode_task<N>(2, pi2)); c.tD = make_taskr(decode_task<N>(2, pi3));
+    // operands of the "combine" stages.  Every stage is ONE branch-free instruction stream (missing neighbours: zero parameter, clamped slot).
+    //   phi warp, lanes MB..    : one (mid,t) dot product of three parameter * series slots (parameter tables S.pm, g / q of the newest order from
+    //                             the A lanes through scratch):  Md_i[k] = [k==0] b_i/2 - (3 b_i g_i + c g_{i-1} + c g_{i+1}),
+    //                             Mo_e[k] = 2 c_e q_e,  H_i[k] = -(b_i g_i + c g_{i-1} + c g_{i+1})   (v' = H w)
+    //   Psi warp, lanes < N*D   : Pv[k] = (X0 + X1 + X2)/k from the C sums (scratch); Pu[k] = Pv[k-1]/k
+    //   The B lanes of the phi warp turn their own Cauchy sum (H w)[k] into v[k+1], u[k+2], z[k+2].
     int cs0 = ZSLOT, cs1 = ZSLOT, cs2 = ZSLOT, rowV = 0, rowU = 0, rowZ = 0;
-    int ap0 = PZ, ap1 = PZ, ap2 = PZ, mscale = 1, gslot = -1;
-    double mcst = 0;
-    // phi warp lanes: A tasks 0..NA-1 | B tasks NA..NA+N-1 (they turn their own sum into v, u, z) | MB.. : Md_i, Mo_e, H_i from the newest g, q
-    constexpr int MB = L::NA + L::NB;
-    static_assert(MB + 3 * N - 1 <= 32, "phi warp: A, B and M/H lanes side by side");
+    int ap0 = PZ, ap1 = PZ, ap2 = PZ, mscale = 1, gslot = 255, mcst = 0;
     const int mrole = (wq == 0 && lane >= MB && lane < MB + 3 * N - 1) ? lane - MB : -1;      // < N: Md_i, < 2N-1: Mo_e, else H_i
     if (wq == 0) {
         if (lane >= L::NA && lane < MB) {                    // B lane: v, u, z rows of component i
             const int i = lane - L::NA;
             rowV = L::V(i) * KMAX; rowU = L::U(i) * KMAX; rowZ = L::Z(i) * KMAX;
-        } else if (mrole >= 0 && (mrole < N || mrole >= 2 * N - 1)) {   // Md_i = [k = 0] b_i/2 - (3 b_i g_i + c_{i-1} g_{i-1} + c_i g_{i+1}),  H_i = -(b_i g_i + c_{i-1} g_{i-1} + c_i g_{i+1})
+        } else if (mrole >= 0 && (mrole < N || mrole >= 2 * N - 1)) {   // Md_i, H_i
             const bool isH = mrole >= 2 * N - 1;
             const int i = isH ? mrole - (2 * N - 1) : mrole;
             cs0 = GS + i; cs1 = GS + (i > 0 ? i - 1 : 0); cs2 = GS + (i < N - 1 ? i + 1 : N - 1);       // clamped: missing neighbours carry zero parameters
             ap0 = (isH ? 0 : N) + i; ap1 = 3 * N + i; ap2 = 4 * N + i;                                    // B or B3 | Cm | Cp in S.pm
-            mscale = 1; mcst = isH ? 0.0 : 1.0; rowV = (isH ? L::G(i) : L::MD(i)) * KMAX;                // mscale: negate;  mcst: add b_i/2 at order 0
+            mscale = 1; mcst = isH ? 0 : 1; rowV = (isH ? L::G(i) : L::MD(i)) * KMAX;                    // mscale: negate;  mcst: add b_i/2 at order 0
         } else if (mrole >= N) {                             // Mo_e = 2 c_e q_e
             const int e = mrole - N;
             cs0 = cs1 = cs2 = GS + N + e; ap0 = 7 * N + e; ap1 = ap2 = 3 * N;                             // C2 | zero (Cm[0]) | zero
@@ -1155,31 +1127,244 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
         if (i < N - 1) cs2 = c0;
         rowV = L::PV(i, cc) * KMAX; rowU = L::PU(i, cc) * KMAX;
     }
-    ap0 = opaque(ap0); ap1 = opaque(ap1); ap2 = opaque(ap2); mscale = opaque(mscale); gslot = opaque(gslot);
-    cs0 = opaque(cs0); cs1 = opaque(cs1); cs2 = opaque(cs2); rowV = opaque(rowV); rowU = opaque(rowU); rowZ = opaque(rowZ);
+    c.cs = opaqueu((unsigned)cs0 | ((unsigned)cs1 << 8) | ((unsigned)cs2 << 16) | ((unsigned)gslot << 24));
+    c.ap = opaqueu((unsigned)ap0 | ((unsigned)ap1 << 6) | ((unsigned)ap2 << 12) | ((unsigned)mscale << 18) | ((unsigned)mcst << 19) | ((unsigned)(mrole + 1) << 20));
+    c.rvu = opaqueu((unsigned)rowV | ((unsigned)rowU << 16));
+    c.rz = opaqueu((unsigned)rowZ);
+    return c;
+}
 
-    const int Stot = step_count(L_minus, h);
-    const int renorm_mask = (1 << step_log2) - 1;            // basis renormalisation once per unit of time
-    int zero_count = 0, failure_count = 0, first_failure = -1, n_conj = 0;      // maintained by thread 0
-    ival tprev = pt(0.0);
-    int cur = 0;
-    ival det_first = pt(0.0), det_last = pt(0.0);                                // thread 0
+// The lane constants are the same for every front of one n: a table in global memory, filled once per device (lanec_table_kernel, launched
+// by ccp_init) and read through the read-only path at the start of every table loop -- 64 bytes per lane instead of 16 registers that
+// would be live across the whole step.
+__device__ uint4 g_lanec[CCP_MAX_N + 1][NT][4];
+template <int N> __global__ void lanec_table_kernel() {
+    const LaneC c = make_lanec<N>(threadIdx.x);
+    uint4* o = g_lanec[N][threadIdx.x];
+    o[0] = make_uint4(c.tA.ab, c.tA.zz, c.tA.ok, c.tB.ab); o[1] = make_uint4(c.tB.zz, c.tB.ok, c.tC.ab, c.tC.zz);
+    o[2] = make_uint4(c.tC.ok, c.tD.ab, c.tD.zz, c.tD.ok); o[3] = make_uint4(c.cs, c.ap, c.rvu, c.rz);
+}
+
+// ---- Taylor tables of the centre trajectory, two orders per stage (called by all threads of the CTA once per step; its own function so
+//      that the register allocation of the hot loop is not shared with the long-lived state of the step loop).
+//      u'' = F(u): the coefficients of order k+2 depend on those of order <= k only, so the orders J, J+1 (J even) are independent of each
+//      other and are produced together; the stages form the dependent chain (10 of them for p = 20 instead of 20 orders).  Stage (J, J+1):
+//        phi warp:  pass: A lanes full sums g, q [J], [J+1];  B lanes the part of (H w)[J], (H w)[J+1] that does not need H[J], H[J+1]
+//                   -> M/H lanes: Md, Mo, H of both orders  -> (bar: the M-series travel to the Psi warp)
+//                   -> B lanes: the terms with H[J], H[J+1], then v[J+1], v[J+2], u[J+2], u[J+3], z
+//        Psi warp:  pass: the part of (M Psi^u)[J], [J+1] that does not need M[J], M[J+1]  -> (bar)  -> the terms with M[J], M[J+1]
+//                   -> Pv[J+1], Pv[J+2], Pu[J+2], Pu[J+3]
+//      Every sum keeps the summation order of oracle/c1.hpp:cauchy_order (interior terms ascending, then the end terms j = 0 and
+//      j = order): only the schedule differs from an order-by-order loop, the values are bit-identical. ----
+template <int N>
+__device__ __noinline__ void table_loop(FrontSmem<N>& S) {
+    LaneC lc;
+    {
+        const uint4* q = g_lanec[N][threadIdx.x];
+        const uint4 w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2), w3 = __ldg(q + 3);
+        lc.tA.ab = w0.x; lc.tA.zz = w0.y; lc.tA.ok = w0.z; lc.tB.ab = w0.w; lc.tB.zz = w1.x; lc.tB.ok = w1.y;
+        lc.tC.ab = w1.z; lc.tC.zz = w1.w; lc.tC.ok = w2.x; lc.tD.ab = w2.y; lc.tD.zz = w2.z; lc.tD.ok = w2.w;
+        lc.cs = w3.x; lc.ap = w3.y; lc.rvu = w3.z; lc.rz = w3.w;
+    }
+    const int p = S.cfg.p;
+    constexpr int D = 2 * N, GS = TLC<N>::GS;
+    constexpr int CROUNDS = PhaseCheck<N>::CROUNDS;
+    const int tid = threadIdx.x, wq = tid >> 5, lane = tid & 31;
+    mt (*T)[KMAX] = S.T;
+    const mt* const Tf = &T[0][0];
+#define cs0 lq.cs0()
+#define cs1 lq.cs1()
+#define cs2 lq.cs2()
+#define ap0 lq.ap0()
+#define ap1 lq.ap1()
+#define ap2 lq.ap2()
+#define rowV lq.rowV()
+#define rowU lq.rowU()
+#define rowZ lq.rowZ()
+#define gslot lq.gslot()
+#define mscale lq.mscale()
+#define mcst lq.mcst()
+#define mrole lq.mrole()
+#undef PROF
+#undef TRC
+#define PROF(i) do {} while (0)
+#define TRC(i) do {} while (0)
+        ival* const scr0 = S.un.scratch;                     // sums / g, q of order J
+        ival* const scr1 = &S.Jc[0][0];                      // ... of order J+1 (Jc, Kc are dead during the table loop)
+        mt* const dummy = reinterpret_cast<mt*>(scr1) + GS + 2 * N - 1;        // target of the stores that fall beyond order p
+        const mt* const inv = reinterpret_cast<const mt*>(scr1) + FrontSmem<N>::INV_OFF;   // (RU(1/k), RU(RU(1/k)(1 + 2^-50))), refilled every step (Jc, Kc, J are dead here)
+        static_assert(FrontSmem<N>::INV_OFF >= GS + 2 * N, "second scratch set + dummy slot, then the reciprocal table");
+        auto stage = [&](auto fast_tag, const int J) {
+            constexpr bool FAST = decltype(fast_tag)::value;
+            const bool two = FAST || (J + 1 < p);                 // uniform: the stage has a second order
+            const bool three = J + 3 <= p;                        // u, z, Pu of order J+3 exist
+            // the packed lane constants are laundered once per stage: everything derived from them (table addresses, scratch slots) is
+            // recomputed here with a few ALU operations instead of being hoisted out of the stage loop into registers that spill
+            LaneC lq = lc;
+            lq.tA.ab = opaqueu(lq.tA.ab); lq.tA.zz = opaqueu(lq.tA.zz); lq.tA.ok = opaqueu(lq.tA.ok);
+            lq.tB.ab = opaqueu(lq.tB.ab); lq.tB.zz = opaqueu(lq.tB.zz); lq.tB.ok = opaqueu(lq.tB.ok);
+            if (CROUNDS > 1) {
+                lq.tC.ab = opaqueu(lq.tC.ab); lq.tC.zz = opaqueu(lq.tC.zz); lq.tC.ok = opaqueu(lq.tC.ok);
+                lq.tD.ab = opaqueu(lq.tD.ab); lq.tD.zz = opaqueu(lq.tD.zz); lq.tD.ok = opaqueu(lq.tD.ok);
+            }
+            lq.cs = opaqueu(lq.cs); lq.ap = opaqueu(lq.ap); lq.rvu = opaqueu(lq.rvu); lq.rz = opaqueu(lq.rz);
+            const TaskR tA = lq.tA, tB = lq.tB, tC = lq.tC, tD = lq.tD;
+            if (wq == 0) {
+                PROF(12);
+                TRC(100 + J);
+                const int kind = tA.kind();
+                acc4 s0, s1;
+                s0 = acc_zero(); s1 = acc_zero();                 // defined on every path (lanes without a task keep the zeros): accumulators that are only
+                if (kind >= 0) pass_early<FAST>(Tf, tA, J, s0, s1);      // defined inside a divergent branch get spilled across the barrier below
+                if (kind == 0) {
+                    acc4 t0 = s0, t1 = s1;                        // A lanes: g, q of both orders -> scratch (they only travel to the M/H lanes)
+                    pass_late<FAST>(Tf, tA, J, two, t0, t1);
+                    const mt g0 = iv2mt(acc_finish(t0)), g1 = iv2mt(acc_finish(t1));
+                    reinterpret_cast<mt*>(scr0)[gslot] = g0;
+                    (two ? reinterpret_cast<mt*>(scr1) + gslot : dummy)[0] = g1;
+                }
+                __syncwarp();
+                PROF(8);
+                TRC(300 + J);
+                if (mrole >= 0) {                                 // M/H lanes: one (mid,t) dot product per order: parameter * g (or q), three slots
+                    const mt* const pmt = &S.pm.B[0];             // B | B3 | B6 | Cm | Cp | C2m | C2p | C2, N entries each
+                    const mt p0 = pmt[ap0], p1 = pmt[ap1], p2 = pmt[ap2];
+                    const mt* const gq0 = reinterpret_cast<const mt*>(scr0); const mt* const gq1 = reinterpret_cast<const mt*>(scr1);
+                    acc4 c0 = acc_zero(), c1 = acc_zero();
+                    acc_term(c0, p0, gq0[cs0]); acc_term(c1, p0, gq1[cs0]);
+                    acc_term(c0, p1, gq0[cs1]); acc_term(c1, p1, gq1[cs1]);
+                    acc_term(c0, p2, gq0[cs2]); acc_term(c1, p2, gq1[cs2]);
+                    ival d0 = acc_finish(c0), d1 = acc_finish(c1);
+                    if (mscale) { d0 = ineg(d0); d1 = ineg(d1); }
+                    if (!FAST && J == 0 && mcst) d0 = iadd(S.pm.halfB[mrole], d0);      // Md_i[0] = b_i/2 - (...)
+                    T[0][rowV + J] = iv2mt(d0);
+                    (two ? &T[0][rowV + J + 1] : dummy)[0] = iv2mt(d1);
+                }
+                __syncwarp();
+                TRC(400 + J);
+                bar_pair();                                       // Md, Mo of orders J, J+1 are in the tables
+                TRC(500 + J);
+                if (kind == 1) {                                  // B lanes: (H w)[kc] is v'[kc]:  v[kc+1] = sum/(kc+1), u[kc+2] = v[kc+1]/(kc+2), z = -u
+                    const mt i1 = inv[J + 1], i2 = inv[J + 2], i3 = inv[J + 3];
+                    pass_late<FAST>(Tf, tA, J, two, s0, s1);
+                    const mt v1 = mt_scale(iv2mt(acc_finish(s0)), i1.m, i1.t), v2 = mt_scale(iv2mt(acc_finish(s1)), i2.m, i2.t);
+                    const mt u2 = mt_scale(v1, i2.m, i2.t), u3 = mt_scale(v2, i3.m, i3.t);
+                    mt z2, z3; z2.m = -u2.m; z2.t = u2.t; z3.m = -u3.m; z3.t = u3.t;
+                    T[0][rowV + J + 1] = v1;
+                    (two ? &T[0][rowV + J + 2] : dummy)[0] = v2;
+                    (two ? &T[0][rowU + J + 2] : dummy)[0] = u2;  (two ? &T[0][rowZ + J + 2] : dummy)[0] = z2;
+                    (three ? &T[0][rowU + J + 3] : dummy)[0] = u3; (three ? &T[0][rowZ + J + 3] : dummy)[0] = z3;
+                }
+                __syncwarp();
+                PROF(9);
+            } else {
+                TRC(700 + J);
+                // variational tables: products M * Psi^u of orders J, J+1 (pairs of tasks sharing the M-series)
+                acc4 a0, a1, b0, b1, c0, c1, d0, d1;
+                const bool r0 = tA.kind() == 2, r1 = CROUNDS > 1 && tC.kind() == 2;
+                // every lane runs the passes (lanes without a task: on row 0, results dropped into the dummy slot) -- no divergence, and the
+                // accumulators that live across the barrier are defined unconditionally
+                ival* const dmy = reinterpret_cast<ival*>(dummy);
+                a0 = acc_zero(); a1 = acc_zero(); b0 = acc_zero(); b1 = acc_zero(); c0 = acc_zero(); c1 = acc_zero(); d0 = acc_zero(); d1 = acc_zero();
+                if (r0) pair_early<FAST>(Tf, tA, tB, J, a0, a1, b0, b1);
+                if (r1) pair_early<FAST>(Tf, tC, tD, J, c0, c1, d0, d1);
+                TRC(400 + J);
+                bar_pair();
+                TRC(500 + J);
+                if (r0) {
+                    pair_late<FAST>(Tf, tA, tB, J, two, a0, a1, b0, b1);
+                    const ival fa0 = acc_finish(a0), fb0 = acc_finish(b0), fa1 = acc_finish(a1), fb1 = acc_finish(b1);
+                    (r0 ? scr0 + tA.out() : dmy)[0] = fa0; (r0 ? scr0 + tB.out() : dmy)[0] = fb0;
+                    (r0 ? scr1 + tA.out() : dmy)[0] = fa1; (r0 ? scr1 + tB.out() : dmy)[0] = fb1;      // scr1 sums of a missing order are never used
+                }
+                if (r1) {
+                    pair_late<FAST>(Tf, tC, tD, J, two, c0, c1, d0, d1);
+                    const ival fc0 = acc_finish(c0), fd0 = acc_finish(d0), fc1 = acc_finish(c1), fd1 = acc_finish(d1);
+                    (r1 ? scr0 + tC.out() : dmy)[0] = fc0; (r1 ? scr0 + tD.out() : dmy)[0] = fd0;
+                    (r1 ? scr1 + tC.out() : dmy)[0] = fc1; (r1 ? scr1 + tD.out() : dmy)[0] = fd1;
+                }
+                __syncwarp();
+                TRC(800 + J);
+                if (lane < N * D) {                               // scratch sums of order kc -> Pv[kc+1];  Pu[kc+2] = Pv[kc+1]/(kc+2)   (Pu[1] = Pv[0] comes with the order-0 data)
+                    const mt i1 = inv[J + 1], i2 = inv[J + 2], i3 = inv[J + 3];
+                    const ival x0 = scr0[cs0], x1 = scr0[cs1], x2 = scr0[cs2], y0 = scr1[cs0], y1 = scr1[cs1], y2 = scr1[cs2];
+                    const mt pv1 = mt_scale(iv2mt(iadd(iadd(x0, x1), x2)), i1.m, i1.t), pv2 = mt_scale(iv2mt(iadd(iadd(y0, y1), y2)), i2.m, i2.t);
+                    const mt pu2 = mt_scale(pv1, i2.m, i2.t), pu3 = mt_scale(pv2, i3.m, i3.t);
+                    T[0][rowV + J + 1] = pv1;
+                    (two ? &T[0][rowV + J + 2] : dummy)[0] = pv2;
+                    (two ? &T[0][rowU + J + 2] : dummy)[0] = pu2;
+                    (three ? &T[0][rowU + J + 3] : dummy)[0] = pu3;
+                }
+                __syncwarp();
+            }
+        };
+
+        for (int J = 0; J < p; J += 2) {
+            if (J >= 2 && J + 1 < p) stage(cuda::std::true_type{}, J);
+            else stage(cuda::std::false_type{}, J);
+        }
+#undef cs0
+#undef cs1
+#undef cs2
+#undef ap0
+#undef ap1
+#undef ap2
+#undef rowV
+#undef rowU
+#undef rowZ
+#undef gslot
+#undef mscale
+#undef mcst
+#undef mrole
+#undef PROF
+#undef TRC
+}
+#ifdef CCP_TRACE
+#define TRC(id) do { if (blockIdx.x == 0 && s == 500 && (threadIdx.x & 31) == 0 && trc_n < 255) { g_trace[threadIdx.x >> 5][2 * trc_n] = clock64(); g_trace[threadIdx.x >> 5][2 * trc_n + 1] = (id); trc_n++; g_trace_n[threadIdx.x >> 5] = trc_n; } } while (0)
+#else
+#define TRC(id) do {} while (0)
+#endif
+#ifdef CCP_PROFILE
+#define PROF(i) do { long long prof_n = clock64(); if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&g_prof[i], (unsigned long long)(prof_n - prof_t)); prof_t = prof_n; } while (0)
+#else
+#define PROF(i) do {} while (0)
+#endif
+
+// ------------------------------------------------------------------------------------------------
+// One integrator step of one front (all threads of the CTA).  Its own function, with the front's configuration and tallies in shared
+// memory, so that no long-lived state of the front occupies registers across the phases of a step.  Returns the status.
+// ------------------------------------------------------------------------------------------------
+template <int N>
+__device__ __noinline__ int step_body(FrontSmem<N>& S, const int s, const unsigned align_sm, const int align_phase) {
+    using L = Lay<N>;
+    constexpr int D = 2 * N;
+    const int tid = threadIdx.x, wq = tid >> 5, lane = tid & 31;
+    mt (*T)[KMAX] = S.T;
+    const mt* const Tf = &T[0][0];
+    const Majorant& mj = S.mj;
     // PT overlays the Taylor tables once they are dead: second-variation data, EV[arg][row][col] frame enclosures, DT[.] determinants
     PostTab<N>& PT = *reinterpret_cast<PostTab<N>*>(&T[0][0]);
     ival* const EV = PT.u.EV;
     ival* const DT = PT.DT;
-
-    for (int s = 0; s < Stot && status == CCP_OK; s++) {
+    const int p = S.cfg.p, g = S.cfg.g, Stot = S.cfg.Stot;
+    const double L_minus = S.cfg.L_minus, h = S.cfg.h;
+    ccp_front_result* const gres = S.cfg.gres;
+    const ccp_front_desc* const gdesc = S.cfg.gdesc;
+    ccp_series_rec* const series = S.cfg.series;
+    const int series_cap = S.cfg.series_cap;
+    const int cur = s & 1, nxt = cur ^ 1;
+    int status = CCP_OK;
+    {
         PROF_T0();
         TRC_DECL();
         TRC(1);
-        if (align_sm != ~0u) { if (tid == 0) sm_align_wait(align_sm); __syncthreads(); }    // once per step: every 2nd step or twice per step are both slower (profiles/r2_v22_align_experiments.txt)
+        if (align_sm != ~0u && align_phase == 0) { if (tid == 0) sm_align_wait(align_sm); __syncthreads(); }    // once per step: every 2nd step or twice per step are both slower (profiles/r2_v22_align_experiments.txt)
         const bool last = (s == Stot - 1);
-        const double hs = last ? __dadd_ru(L_minus, -tprev.hi) : h;
-        const int nxt = cur ^ 1;
+        const double hs = last ? __dadd_ru(L_minus, -S.st.tprev.hi) : h;
         // grid points of this step: gp[i] = inf(i*h/grid), gp[grid] = h  (same for every full step)
         if ((s == 0 || last) && tid >= 32 && tid <= 32 + g) { const int i = tid - 32; S.gp[i] = (i < g) ? __ddiv_rd(__dmul_rd((double)i, hs), (double)g) : hs; }
-        if (tid == NT - 1) S.un.scratch[ZSLOT] = pt(0.0);     // the union was reused by the set update of the previous step
+        if (tid >= 32 && tid < 32 + KMAX + 2) { mt v; v.m = c_invhi[tid - 32]; v.t = c_invs[tid - 32]; reinterpret_cast<mt*>(&S.Jc[0][0])[FrontSmem<N>::INV_OFF + tid - 32] = v; }      // reciprocal table of the table loop (Jc, Kc, J are dead until the step image)
+        if (tid == NT - 1) { S.un.scratch[TLC<N>::ZSLOT] = pt(0.0); (&S.Jc[0][0])[TLC<N>::ZSLOT] = pt(0.0); }     // zero slots of both scratch sets (the union was reused by the set update, Jc is rewritten every step)
         // ---- hull of the phi-set ----
         if (tid < D) {
             ival a = pt(S.x[cur][tid]);
@@ -1192,8 +1377,8 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
         __syncthreads();
         {
             const int fl = S.flag;
-            if (fl & 1) { status = CCP_ST_NONFINITE; break; }
-            if (fl & 2) { status = CCP_ST_ENCLOSURE; break; }
+            if (fl & 1) return CCP_ST_NONFINITE;
+            if (fl & 2) return CCP_ST_ENCLOSURE;
         }
         // ---- order 0 of all tables (centre x); Psi = identity ----
         if (tid < N) {
@@ -1211,142 +1396,17 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
             const int i = t / D, cc = t % D;
             T[L::PU(i, cc)][0] = iv2mt(pt(cc == i ? 1.0 : 0.0));
             T[L::PV(i, cc)][0] = iv2mt(pt(cc == N + i ? 1.0 : 0.0));
+            T[L::PU(i, cc)][1] = iv2mt(pt(cc == N + i ? 1.0 : 0.0));       // Pu[1] = Pv[0]/1
         }
         __syncthreads();
         PROF(0);
         TRC(2);
-        // ---- Taylor tables, order by order.  Warp 0 builds the front tables of order k while warp 1 builds the variational
-        //      tables of order k-1 from the M-series warp 0 finished one iteration earlier; the two warps meet once per order
-        //      (bar.sync 1), everything else is __syncwarp. ----
-        // The A tasks run one order AHEAD of the B tasks: g[k+1] only needs u[<= k+1] = v[<= k]/(k+1), which is known before
-        // the product H*w of order k is -- so no lane ever waits for another lane's sum.  The M/H lanes of the phi warp turn
-        // g, q of the newest order into the M-series and H with one branch-free instruction stream.
-        // Orders are processed in blocks of two (run_block): long pass = sums of order k complete + interior of order k+1,
-        // combine(k), then the two end terms of order k+1 (they need the coefficients combine(k) just produced), combine(k+1).
-        // Prologue: g, q, M of order 0.
-        if (wq == 0) {
-            if (tA.kind() == 0) {
-                acc4 s0, s1; run_block(Tf, tA, 0, s0, s1);
-                reinterpret_cast<mt*>(S.un.scratch)[gslot] = iv2mt(acc_finish(s0));
-            }
-            __syncwarp();
-            if (mrole >= 0) {
-                const mt* const gq = reinterpret_cast<const mt*>(S.un.scratch);
-                const mt* const pmt = &S.pm.B[0];                       // B | B3 | B6 | Cm | Cp | C2m | C2p | C2, N entries each
-                acc4 ac = acc_zero();
-                acc_term(ac, pmt[ap0], gq[cs0]); acc_term(ac, pmt[ap1], gq[cs1]); acc_term(ac, pmt[ap2], gq[cs2]);
-                ival dd = acc_finish(ac);
-                if (mscale) dd = ineg(dd);
-                if (mcst != 0.0) dd = iadd(S.pm.halfB[mrole], dd);      // Md_i[0] = b_i/2 - (...)
-                T[0][rowV] = iv2mt(dd);
-            }
-        }
-        bar_pair();
-        // phi warp, M/H lanes: g, q of order kc+1 (scratch) -> Md, Mo, H of order kc+1
-        auto combine_phi = [&](int kc) {
-            if (mrole >= 0 && kc + 1 <= p - 1) {
-                const mt* const gq = reinterpret_cast<const mt*>(S.un.scratch);
-                const mt* const pmt = &S.pm.B[0];
-                acc4 ac = acc_zero();                                   // one (mid,t) dot product: parameter * g (or q), three slots
-                acc_term(ac, pmt[ap0], gq[cs0]); acc_term(ac, pmt[ap1], gq[cs1]); acc_term(ac, pmt[ap2], gq[cs2]);
-                const ival f = acc_finish(ac);
-                T[0][rowV + kc + 1] = iv2mt(mscale ? ineg(f) : f);
-            }
-        };
-        // phi warp, B lanes: the Cauchy sum (H w)[kc] is v'[kc]:  v[kc+1] = sum/(kc+1), u[kc+2] = v[kc+1]/(kc+2), z = -u  (no scratch round trip)
-        auto store_vuz = [&](int kc, const ival& f) {
-            const mt vn = mt_scale(iv2mt(f), c_invhi[kc + 1], c_invs[kc + 1]);
-            T[0][rowV + kc + 1] = vn;
-            if (kc + 2 <= p) {
-                const mt un = mt_scale(vn, c_invhi[kc + 2], c_invs[kc + 2]);
-                T[0][rowU + kc + 2] = un;
-                mt zn; zn.m = -un.m; zn.t = un.t;
-                T[0][rowZ + kc + 2] = zn;
-            }
-        };
-        // Psi warp: scratch sums of order kc -> Pv[kc+1];  Pu[kc+1] = Pv[kc]/(kc+1)
-        auto combine_psi = [&](int kc) {
-            if (lane < N * D) {
-                const ival s0 = S.un.scratch[cs0], s1 = S.un.scratch[cs1], s2 = S.un.scratch[cs2];
-                const mt pvk = Tf[rowV + kc];
-                const double ih = c_invhi[kc + 1], ihs = c_invs[kc + 1];
-                T[0][rowV + kc + 1] = mt_scale(iv2mt(iadd(iadd(s0, s1), s2)), ih, ihs);
-                T[0][rowU + kc + 1] = kc == 0 ? pvk : mt_scale(pvk, ih, ihs);
-            }
-        };
-        for (int k = 0; k < p; k += 2) {
-            const bool two = k + 1 < p;                           // uniform: the block has a second order
-            if (wq == 0) {
-                PROF(12);
-                TRC(100 + k);
-                // A lanes: g, q of orders k+1, k+2;  B lanes: products g*w of orders k, k+1
-                const int isA = tA.kind() == 0;
-                const int kk = k + isA;
-                const bool act0 = tA.kind() >= 0 && kk <= (isA ? p - 1 : p);
-                const bool act1 = tA.kind() >= 0 && kk + 1 <= p - 1;
-                acc4 s0, s1;
-                if (act0) {
-                    run_block(Tf, tA, kk, s0, s1);
-                    const ival sum = acc_finish(s0);
-                    if (isA) reinterpret_cast<mt*>(S.un.scratch)[gslot] = iv2mt(sum);      // g, q only travel to the M/H lanes
-                    else store_vuz(kk, sum);
-                }
-                __syncwarp();
-                PROF(8);
-                TRC(300 + k);
-                combine_phi(k);
-                if (two) {
-                    bar_pair();
-                    TRC(100 + k + 1);
-                    if (act1) {
-                        run_ends(Tf, tA, kk + 1, s1);
-                        const ival sum = acc_finish(s1);
-                        if (isA) reinterpret_cast<mt*>(S.un.scratch)[gslot] = iv2mt(sum);
-                        else store_vuz(kk + 1, sum);
-                    }
-                    __syncwarp();
-                    TRC(300 + k + 1);
-                    combine_phi(k + 1);
-                }
-            } else {
-                TRC(700 + k);
-                // variational tables: products M * Psi^u of orders k, k+1 (pairs of tasks sharing the M-series)
-                acc4 a0, a1, b0, b1, c0, c1, d0, d1;
-                if (tA.kind() == 2) {
-                    run_block_pair(Tf, tA, tB, k, a0, a1, b0, b1);
-                    S.un.scratch[tA.out()] = acc_finish(a0); S.un.scratch[tB.out()] = acc_finish(b0);
-                }
-                if (CROUNDS > 1 && tC.kind() == 2) {
-                    run_block_pair(Tf, tC, tD, k, c0, c1, d0, d1);
-                    S.un.scratch[tC.out()] = acc_finish(c0); S.un.scratch[tD.out()] = acc_finish(d0);
-                }
-                __syncwarp();
-                TRC(800 + k);
-                combine_psi(k);
-                if (two) {
-                    bar_pair();                                   // M[k+1] and Pu[k+1] are now in the tables
-                    TRC(700 + k + 1);
-                    if (tA.kind() == 2) {
-                        run_ends_pair(Tf, tA, tB, k + 1, a1, b1);
-                        S.un.scratch[tA.out()] = acc_finish(a1); S.un.scratch[tB.out()] = acc_finish(b1);
-                    }
-                    if (CROUNDS > 1 && tC.kind() == 2) {
-                        run_ends_pair(Tf, tC, tD, k + 1, c1, d1);
-                        S.un.scratch[tC.out()] = acc_finish(c1); S.un.scratch[tD.out()] = acc_finish(d1);
-                    }
-                    __syncwarp();
-                    TRC(800 + k + 1);
-                    combine_psi(k + 1);
-                }
-            }
-            PROF(9);
-            TRC(400 + k);
-            bar_pair();
-            PROF(10);
-            TRC(500 + k);
-        }
+        table_loop<N>(S);                                         // Taylor tables of the centre trajectory (two orders per stage)
+        bar_pair();                                               // both warps are done with the tables
+        PROF(10);
         PROF(1);
         TRC(3);
+        if (align_sm != ~0u && align_phase != 0) { if (tid == 0) sm_align_wait(align_sm); __syncthreads(); }      // the other half of an SM's fronts meets the same barrier half a step later
         // ---- step image: y = Phi(x), Jc = DPhi(x) (centre tables); frame at step start W = ((Tc + sum_j Theta_j r0_j) + R) + Ps Err ----
         //      One instruction stream per warp: the first threads evaluate TWO increment series each (interleaved Horner chains), the
         //      last D*N threads form the frame entries.
@@ -1485,6 +1545,7 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
             ival timeI = pt(0.0);
             if (gi < g) {
                 const double tl = S.gp[gi], th = S.gp[gi + 1];
+                const ival tprev = S.st.tprev;
                 timeI = mk(__dadd_rd(tprev.lo, tl), __dadd_ru(tprev.hi, th));
                 const ival dL = DT[gi], dR = DT[gi + 1], dV = DT[g + 1 + gi];
                 const ival LR = imul_nl(dL, dR);
@@ -1513,29 +1574,27 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
             const unsigned fmask = __ballot_sync(FULLM, (decision & 3) == 2);
             const unsigned nmask = __ballot_sync(FULLM, (decision & 4) != 0);
             if (nmask && lane == 0) S.flag |= 1;
-            if (fmask && failure_count == 0) first_failure = s * g + (__ffs(fmask) - 1);
-            failure_count += __popc(fmask);
-            if (zmask) {
-                if ((decision & 3) == 1) {
-                    const int slot = n_conj + __popc(zmask & ((1u << lane) - 1u));
-                    if (slot < CCP_MAX_CONJ) { gres->conj_time[slot] = toc(timeI); gres->conj_index[slot] = s * g + gi; }
-                }
-                n_conj += __popc(zmask); zero_count += __popc(zmask);
+            const int n_conj = S.st.n_conj;                   // every lane reads the tally before lane 0 updates it
+            __syncwarp();
+            if (zmask && (decision & 3) == 1) {
+                const int slot = n_conj + __popc(zmask & ((1u << lane) - 1u));
+                if (slot < CCP_MAX_CONJ) { gres->conj_time[slot] = toc(timeI); gres->conj_index[slot] = s * g + gi; }
             }
             if (lane == 0) {
-                if (s == 0) det_first = DT[g + 1];
-                if (last) det_last = DT[2 * g];
+                if (fmask) { if (S.st.failure_count == 0) S.st.first_failure = s * g + (__ffs(fmask) - 1); S.st.failure_count += __popc(fmask); }
+                if (zmask) { S.st.n_conj = n_conj + __popc(zmask); S.st.zero_count += __popc(zmask); }
+                if (s == 0) S.st.det_first = DT[g + 1];
+                if (last) S.st.det_last = DT[2 * g];
             }
         }
         }
         PROF(5);
         TRC(7);
+        if (tid == 0) { const ival tp = S.st.tprev; S.st.tprev = mk(__dadd_rd(tp.lo, hs), __dadd_ru(tp.hi, hs)); }      // read again after the barriers of the set update
         if (set_update<N>(S, PT, cur, nxt)) status = CCP_ST_NONFINITE;
         PROF(6);
         TRC(8);
-        tprev = mk(__dadd_rd(tprev.lo, hs), __dadd_ru(tprev.hi, hs));
-        cur = nxt;
-        if (g > 0 && !last && status == CCP_OK && ((s + 1) & renorm_mask) == 0) renormalise<N>(S);
+        if (g > 0 && !last && status == CCP_OK && ((s + 1) & S.cfg.renorm_mask) == 0) renormalise<N>(S);
         if (last && status == CCP_OK) {            // topFrame::getLastFrame: frame and front point at the end of the last step
             constexpr int ld = CCP_MAX_N + 2;
             for (int t = tid; t < D * N; t += NT) {
@@ -1565,31 +1624,132 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
                 gres->flow_P[rr * CCP_MAX_DIM + N + k] = toc(S.Ps[rr][k]);
             }
             if (tid < D) {
-                ival a = pt(S.x[cur][tid]);
-                for (int j = 0; j < D; j++) ipfma(a, S.r0[j], S.C[cur][tid][j]);          // fused: one rounding per bound and term
-                gres->last_frame[tid * ld + N + 1] = toc(iadd(a, S.r[cur][tid]));
+                ival a = pt(S.x[nxt][tid]);                       // nxt: the set after the update
+                for (int j = 0; j < D; j++) ipfma(a, S.r0[j], S.C[nxt][tid][j]);          // fused: one rounding per bound and term
+                gres->last_frame[tid * ld + N + 1] = toc(iadd(a, S.r[nxt][tid]));
             }
         }
     }
+    return status;
+}
+
+// ------------------------------------------------------------------------------------------------
+// One CTA (NT threads) = one front.  `series` (optional) receives steps*grid records.
+// ------------------------------------------------------------------------------------------------
+template <int N>
+__device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gdesc, ccp_front_result* __restrict__ gres,
+                          ccp_series_rec* __restrict__ series, int series_cap, unsigned align_sm, int align_phase) {
+    using L = Lay<N>;
+    constexpr int D = 2 * N;
+    const int tid = threadIdx.x;
+    mt (*T)[KMAX] = S.T;
+    (void)sizeof(PhaseCheck<N>);
+
+    // ---- stage the descriptor: coalesced 16-byte loads HBM -> shared ----
+    {
+        const int4* src = reinterpret_cast<const int4*>(gdesc);
+        int4* dst = reinterpret_cast<int4*>(&T[0][0]);       // staged in the (still unused) table array
+        for (int i = tid; i < (int)(sizeof(ccp_front_desc) / 16); i += NT) dst[i] = src[i];
+    }
+    __syncthreads();
+    const ccp_front_desc& sdesc = *reinterpret_cast<const ccp_front_desc*>(&T[0][0]);
+    const int p = sdesc.order, g = sdesc.grid, step_log2 = sdesc.step_log2;
+    const double L_minus = sdesc.L_minus;
+    int status = CCP_OK;
+    if (sdesc.n != N || p < 2 || p > CCP_MAX_ORDER || g < 0 || g > GMAX || step_log2 < 1 || step_log2 > 20 || !(L_minus > 0) || !isfinite(L_minus) ||
+        ldexp(L_minus, step_log2) > 16777216.0)          // more than 2^24 steps: the 32-bit step and sub-interval counters would overflow
+        status = CCP_ST_BAD_DESC;
+    if (status != CCP_OK) {
+        __syncthreads();
+        if (tid == 0) {
+            ccp_front_result z; memset(&z, 0, sizeof(z)); z.status = status; z.first_failure = -1;
+            *gres = z;
+        }
+        return;
+    }
+    const double h = ldexp(1.0, -step_log2);
+    {
+        const ccp_front_desc& d = sdesc;
+        if (tid < N) S.bpar[tid] = fromc(d.b[tid]);
+        if (tid < N - 1) S.cpar[tid] = fromc(d.c[tid]);
+        if (tid < D) {
+            ival pi = fromc(d.p_i[tid]);
+            double xm = mid_ru(pi);
+            S.x[0][tid] = xm; S.r[0][tid] = isub(pi, pt(xm)); S.r0[tid] = fromc(d.Uxy[tid]);
+        }
+        for (int t = tid; t < D * D; t += NT) { int i = t / D, j = t % D; double a = d.A_u[i * CCP_MAX_DIM + j]; S.C[0][i][j] = a; if (j < N) { S.Tc[i][j] = a; S.R[i][j] = pt(0.0); } else S.Ps[i][j - N] = pt(a); }
+        for (int t = tid; t < D * D * N; t += NT) (&S.Th[0][0][0])[t] = 0.0;
+        for (int t = tid; t < N * N; t += NT) { mt z; z.m = 0.0; z.t = 0.0; S.hm.M0[t / N][t % N] = z; S.hm.M1[t / N][t % N] = z; }
+        if (tid >= 32 && tid < 32 + D + 1) { const int j = tid - 32; S.r0m[j] = j < D ? iv2mt(fromc(d.Uxy[j])) : ptm(1.0); }
+        for (int t = tid; t < N * N; t += NT) { const int j = t / N, k = t % N; S.Errm[j][k] = iv2mt(fromc(d.Eu_err[j * CCP_MAX_N + k])); }
+        for (int t = tid; t < N * N; t += NT) { int j = t / N, k = t % N; S.Err[j][k] = fromc(d.Eu_err[j * CCP_MAX_N + k]); }
+    }
+    for (int t = tid; t < (int)(sizeof(ccp_front_result) / 8); t += NT) reinterpret_cast<double*>(gres)[t] = 0.0;
+    __syncthreads();                                // the staged descriptor is dead from here on
+    if (tid == 0) { S.mj = majorant<N>(S.bpar, S.cpar, p, h); S.flag = 0; S.renorms = 0; S.sc = pt(1.0); }
+    if (tid >= 32 && tid < 32 + N * N) { const int t = tid - 32; S.G[t / N][t % N] = pt(t / N == t % N ? 1.0 : 0.0); }
+    if (tid == 32) majorant2<N>(S.bpar, S.cpar, h, S.g15);
+    if (tid < N) {                                  // oracle/c2.hpp:make_par
+        const int i = tid;
+        mt z; z.m = 0.0; z.t = 0.0;
+        const ival b = S.bpar[i];
+        S.pm.B[i] = iv2mt(b); S.pm.B3[i] = iv2mt(imulk(b, 3)); S.pm.B6[i] = iv2mt(imulk(b, 6)); S.pm.halfB[i] = ihalf(b);
+        S.pm.Cm[i] = i > 0 ? iv2mt(S.cpar[i > 0 ? i - 1 : 0]) : z;                 S.pm.Cp[i] = i < N - 1 ? iv2mt(S.cpar[i < N - 1 ? i : 0]) : z;
+        S.pm.C2m[i] = i > 0 ? iv2mt(imulk(S.cpar[i > 0 ? i - 1 : 0], 2)) : z;      S.pm.C2p[i] = i < N - 1 ? iv2mt(imulk(S.cpar[i < N - 1 ? i : 0], 2)) : z;
+        S.pm.C2[i] = S.pm.C2p[i];
+        for (int l = 0; l < N; l++) for (int sl = 0; sl < 3; sl++) {
+            mt v = z;
+            if (i == l) v = sl == 0 ? S.pm.B6[i] : (sl == 1 ? S.pm.C2m[i] : S.pm.C2p[i]);
+            else if (l == i + 1) v = sl < 2 ? S.pm.C2p[i] : z;                    // 2 c_i
+            else if (l == i - 1) v = sl < 2 ? S.pm.C2m[i] : z;                    // 2 c_{i-1}
+            S.pm.PN[i][l][sl] = v;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) { S.mj.g1 = S.g15[0]; S.mj.g5 = S.g15[1]; S.st.zero_count = 0; S.st.failure_count = 0; S.st.first_failure = -1; S.st.n_conj = 0; S.st.tprev = pt(0.0); S.st.det_first = pt(0.0); S.st.det_last = pt(0.0); }
+    __syncthreads();
+    const Majorant& mj = S.mj;                              // stays in shared memory: a register copy would be live across the whole step loop
+    if (!mj.ok) status = CCP_ST_ENCLOSURE;
+
+    if (tid == 0) {
+        S.cfg.p = p; S.cfg.g = g; S.cfg.step_log2 = step_log2; S.cfg.Stot = step_count(L_minus, h); S.cfg.renorm_mask = (1 << step_log2) - 1;      // basis renormalisation once per unit of time
+        S.cfg.series_cap = series_cap; S.cfg.L_minus = L_minus; S.cfg.h = h; S.cfg.gdesc = gdesc; S.cfg.gres = gres; S.cfg.series = series;
+    }
+    __syncthreads();
+    const int Stot = S.cfg.Stot;
+    for (int s = 0; s < Stot && status == CCP_OK; s++) status = step_body<N>(S, s, align_sm, align_phase);
     __syncthreads();
     if (tid == 0) {
-        gres->status = status; gres->zero_count = zero_count; gres->failure_count = failure_count;
+        const int n_conj = S.st.n_conj;
+        gres->status = status; gres->zero_count = S.st.zero_count; gres->failure_count = S.st.failure_count;
         gres->series_length = Stot * g; gres->steps = Stot; gres->n_conj = n_conj < CCP_MAX_CONJ ? n_conj : CCP_MAX_CONJ;
-        gres->first_failure = first_failure; gres->reserved = 0;
-        gres->det_first = toc(det_first); gres->det_last = toc(det_last);
+        gres->first_failure = S.st.first_failure; gres->reserved = 0;
+        gres->det_first = toc(S.st.det_first); gres->det_last = toc(S.st.det_last);
     }
 }
 
+#ifndef CCP_MINB
+#define CCP_MINB 8
+#endif
+#ifdef CCP_MAXREG
+#define CCP_KERNEL_ATTR __maxnreg__(CCP_MAXREG)
+#else
+#define CCP_KERNEL_ATTR __launch_bounds__(NT, (N == 4 ? 4 : CCP_MINB))
+#endif
 template <int N>
-__global__ void __launch_bounds__(NT, (N == 4 ? 4 : 8)) front_kernel(const ccp_front_desc* __restrict__ descs, ccp_front_result* __restrict__ results,
+__global__ void CCP_KERNEL_ATTR front_kernel(const ccp_front_desc* __restrict__ descs, ccp_front_result* __restrict__ results,
                                                       const int* __restrict__ index, int count, ccp_series_rec* series, int series_cap, int flags) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FrontSmem<N>& S = *reinterpret_cast<FrontSmem<N>*>(smem_raw);
     const unsigned align_sm = ((flags & 1) && series == nullptr && count > 1) ? sm_id() : ~0u;      // single fronts (plots) run alone
-    if (align_sm != ~0u && threadIdx.x == 0) sm_align_join(align_sm);
+    __shared__ int s_ord;
+    if (threadIdx.x == 0) s_ord = align_sm != ~0u ? (int)sm_align_join(align_sm) : 0;
+    __syncthreads();
+    const int pm = (flags >> 1) & 7;                          // experiment: which bit of the per-SM ordinal selects the half-step offset (0 = none)
+    const int align_phase = pm ? (s_ord >> (pm - 1)) & 1 : 0;
     for (int w = blockIdx.x; w < count; w += gridDim.x) {
         const int f = index ? index[w] : w;
-        run_front<N>(S, descs + f, results + f, series, series_cap, align_sm);
+        run_front<N>(S, descs + f, results + f, series, series_cap, align_sm, align_phase);
         __syncthreads();
     }
     if (align_sm != ~0u && threadIdx.x == 0) sm_align_leave(align_sm);
