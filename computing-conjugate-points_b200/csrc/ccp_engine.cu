@@ -66,7 +66,7 @@ template <int N> int launch(Dev& dv, const ccp_front_desc* d_desc, ccp_front_res
     // one CTA of ccp::NT threads per front; the grid is sized to the number of CTAs that are resident at once
     // (multiple of the SM count) and strides over the batch.
     int grid = count < dv.grid_limit[N] ? count : dv.grid_limit[N];
-    static const int dbg_align = getenv("CCP_DBG_ALIGN") ? atoi(getenv("CCP_DBG_ALIGN")) : 1;          // experiment knobs (scripts/): 0 = no per-SM alignment
+    static const int dbg_align = getenv("CCP_DBG_ALIGN") ? atoi(getenv("CCP_DBG_ALIGN")) : 17;         // experiment knobs (scripts/): bit 0 = per-SM alignment, bit 4 = warp roles exchanged in every second CTA of a sub-partition pair
     static const int dbg_pad = getenv("CCP_DBG_SMEM_PAD") ? atoi(getenv("CCP_DBG_SMEM_PAD")) : 0;
     if (dbg_pad) { cudaFuncSetAttribute(ccp::front_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ccp::FrontSmem<N>) + dbg_pad); }
     ccp::front_kernel<N><<<grid, ccp::NT, sizeof(ccp::FrontSmem<N>) + dbg_pad, st>>>(d_desc, d_res, d_index, count, series, series_cap, dbg_align);

@@ -161,6 +161,7 @@ struct FrontSmem {
     double boxFd[N][N];
     double gp[GMAX + 1];                     // grid points of the current step (utils.cpp:219-223)
     int flag;
+    int vswap;                               // 0 or 32: the two warps of the front exchange their roles (tid = threadIdx.x ^ vswap), see front_kernel
     int renorms;                             // basis renormalisations applied so far (renormalise)
     ival G[N][N], sc;                        // true frame = normalised frame * G ;  sc encloses det G > 0
     Majorant mj;
@@ -639,7 +640,7 @@ __device__ __forceinline__ ival frame_entry(const FrontSmem<N>& S, int cc, int b
 template <int N>
 __device__ __noinline__ void second_variation(FrontSmem<N>& S, PostTab<N>& PT, int cur, double hs, double g5, bool frames) {
     constexpr int D = 2 * N;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x ^ S.vswap;
     HullM<N>& H = S.hm;
     // H (warp 0 only; warp 1 waits at the barrier): lanes < N: W_0, W_1, G = u(1-u), Pw = w_0 w_1; lanes N..2N-2: off-diagonals of
     //    M_0, M_1; then, after a __syncwarp, lanes < N: u_2 = F(u)/2 and the diagonals of M_0, M_1 from G, Pw of the chain neighbours
@@ -822,7 +823,7 @@ __device__ __noinline__ void second_variation(FrontSmem<N>& S, PostTab<N>& PT, i
 template <int N>
 __device__ __noinline__ int set_update(FrontSmem<N>& S, PostTab<N>& PT, int cur, int nxt) {
     constexpr int D = 2 * N;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x ^ S.vswap;
     if (tid < D) S.x[nxt][tid] = __dadd_ru(S.x[cur][tid], mid_ru(S.y[tid]));          // x+ = x + mid(increment)
     // item loops are rolled and every item type appears once (code size); new values are staged in the dead table space and
     // copied back after the barrier.  Thread offsets spread the four item types over the CTA.
@@ -913,7 +914,7 @@ __device__ __noinline__ int set_update(FrontSmem<N>& S, PostTab<N>& PT, int cur,
 template <int N>
 __device__ __noinline__ void renormalise(FrontSmem<N>& S) {
     constexpr int D = 2 * N;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x ^ S.vswap;
     static_assert(D * N <= 32 && N * N + 1 <= 32, "renormalise: one item per thread");
     if (tid == 0) {
         double Q[D][N], Rt[N][N], H[N][N];
@@ -1160,7 +1161,7 @@ template <int N>
 __device__ __noinline__ void table_loop(FrontSmem<N>& S) {
     LaneC lc;
     {
-        const uint4* q = g_lanec[N][threadIdx.x];
+        const uint4* q = g_lanec[N][threadIdx.x ^ S.vswap];
         const uint4 w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2), w3 = __ldg(q + 3);
         lc.tA.ab = w0.x; lc.tA.zz = w0.y; lc.tA.ok = w0.z; lc.tB.ab = w0.w; lc.tB.zz = w1.x; lc.tB.ok = w1.y;
         lc.tC.ab = w1.z; lc.tC.zz = w1.w; lc.tC.ok = w2.x; lc.tD.ab = w2.y; lc.tD.zz = w2.z; lc.tD.ok = w2.w;
@@ -1169,7 +1170,7 @@ __device__ __noinline__ void table_loop(FrontSmem<N>& S) {
     const int p = S.cfg.p;
     constexpr int D = 2 * N, GS = TLC<N>::GS;
     constexpr int CROUNDS = PhaseCheck<N>::CROUNDS;
-    const int tid = threadIdx.x, wq = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x ^ S.vswap, wq = tid >> 5, lane = tid & 31;
     mt (*T)[KMAX] = S.T;
     const mt* const Tf = &T[0][0];
 #define cs0 lq.cs0()
@@ -1338,7 +1339,7 @@ template <int N>
 __device__ __noinline__ int step_body(FrontSmem<N>& S, const int s, const unsigned align_sm, const int align_phase) {
     using L = Lay<N>;
     constexpr int D = 2 * N;
-    const int tid = threadIdx.x, wq = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x ^ S.vswap, wq = tid >> 5, lane = tid & 31;
     mt (*T)[KMAX] = S.T;
     const mt* const Tf = &T[0][0];
     const Majorant& mj = S.mj;
@@ -1641,7 +1642,7 @@ __device__ void run_front(FrontSmem<N>& S, const ccp_front_desc* __restrict__ gd
                           ccp_series_rec* __restrict__ series, int series_cap, unsigned align_sm, int align_phase) {
     using L = Lay<N>;
     constexpr int D = 2 * N;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x ^ S.vswap;
     mt (*T)[KMAX] = S.T;
     (void)sizeof(PhaseCheck<N>);
 
@@ -1744,6 +1745,10 @@ __global__ void CCP_KERNEL_ATTR front_kernel(const ccp_front_desc* __restrict__ 
     const unsigned align_sm = ((flags & 1) && series == nullptr && count > 1) ? sm_id() : ~0u;      // single fronts (plots) run alone
     __shared__ int s_ord;
     if (threadIdx.x == 0) s_ord = align_sm != ~0u ? (int)sm_align_join(align_sm) : 0;
+    __syncthreads();
+    // The warps of a CTA sit on neighbouring SM sub-partitions (hardware warp slot mod 4), so with fixed roles every Psi warp of an SM (the heavier
+    // one in the table loop) would share two of the four FP64 pipes.  Every second CTA of a sub-partition pair exchanges the roles of its warps.
+    if (threadIdx.x == 0) { unsigned wid; asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid)); S.vswap = ((flags & 16) && ((wid >> 2) & 1u)) ? 32 : 0; }
     __syncthreads();
     const int pm = (flags >> 1) & 7;                          // experiment: which bit of the per-SM ordinal selects the half-step offset (0 = none)
     const int align_phase = pm ? (s_ord >> (pm - 1)) & 1 : 0;
