@@ -442,6 +442,28 @@ __device__ inline void pair_tasks(int P, int& idx0, int& idx1) {
         }
     }
 }
+// Lane -> pair assignment of the Psi warp.  A quarter warp (8 lanes) reads one 16-byte coefficient per lane with one LDS.128; rows r and r'
+// collide when r = r' (mod 8) (row stride 84 words).  The Psi^u rows a pair reads are 16 + 6 i' + 2 pr (+1): only the residues {0,2,4,6}
+// (resp. {1,3,5,7}) occur, so a conflict-free quarter warp holds at most four distinct rows, one per residue.  For n = 3 such an assignment of
+// the 21 pairs to three quarter warps exists (found by hand; the M-series rows 11..15 never collide); the enumeration order would put rows with
+// equal residues side by side (two-way conflicts on two of the three loads of every term of the pass).
+template <int N> __device__ inline int psi_lane_to_pair(int lane) { return lane; }
+template <> __device__ inline int psi_lane_to_pair<3>(int lane) {
+    constexpr signed char perm[21] = { 0, 9, 1, 10, 2, 11, 3, 6,   4, 7, 19, 5, 12, 15, 13, 16,   14, 17, 18, 8, 20 };
+    return lane < 21 ? perm[lane] : lane;
+}
+// Step image: which two of the NH = D + D^2 series (h < D: u, v;  h >= D: Psi entry h - D, table rows 16 + h - D for n = 3) a lane evaluates.
+// Default: neighbours 2 tt, 2 tt + 1 -- the lanes of a quarter warp then read every second row (two- and three-way bank conflicts).  n = 3:
+// rows with distinct residues mod 8 in every quarter warp for both loads (same argument as psi_lane_to_pair).
+template <int N> __device__ __forceinline__ int image_series(int tt, int which) {
+    constexpr int NH = 2 * N + 4 * N * N;
+    const int h = 2 * tt + which;
+    return h < NH ? h : NH;
+}
+__constant__ signed char c_image3[2][24] = {       // in constant memory: a table local to the function would be rebuilt on the stack at every call
+    { 0, 1, 2, 3, 4, 5, 12, 13,   6, 7, 8, 9, 10, 11, 20, 21,   14, 15, 16, 17, 18, 42, 42, 42 },
+    { 22, 23, 24, 25, 26, 27, 28, 29,   30, 31, 32, 33, 34, 35, 36, 37,   38, 39, 40, 41, 19, 42, 42, 42 } };
+template <> __device__ __forceinline__ int image_series<3>(int tt, int which) { return c_image3[which][tt]; }
 template <int N> struct PhaseCheck {
     using L = Lay<N>;
     static_assert(L::NA + L::NB <= 32, "the phi warp holds the A tasks and the B tasks side by side");
@@ -486,12 +508,17 @@ __device__ __forceinline__ TaskR make_taskr(const Task& t) {
 template <bool FAST>
 __device__ __forceinline__ void pass_early(const mt* __restrict__ Tf, const TaskR& t, int J, acc4& s0, acc4& s1) {
     if (FAST || J >= 2) {
-        const mt* pa = Tf + t.offA() + 1;
-        const mt* pb = Tf + t.offB() + J;
-        mt x = *pa, yp = *pb, y = pb[-1];                        // x = a[l], yp = b[J+1-l], y = b[J-l];  operands of the NEXT term are
-        pa++; pb -= 2;                                           // loaded one term ahead; the last prefetch reads valid, unused table slots
+        const mt* pa = Tf + t.offA() + 1;                        // a[l]
+        const mt* pb = Tf + t.offB() + J - 1;                    // b[J-l]
+        mt yp = pb[1];                                           // b[J+1-l]: the only operand carried from term to term
+        int l = 1;
 #pragma unroll 2
-        for (int l = 1; l < J; l++) { const mt xn = *pa, yn = *pb; acc_term(s1, x, yp); acc_term(s0, x, y); yp = y; x = xn; y = yn; pa++; pb--; }
+        for (; l + 1 < J; l += 2) {                              // two terms per iteration: no operand rotation through register moves
+            const mt x0 = pa[0], x1 = pa[1], y0 = pb[0], y1 = pb[-1];
+            acc_term(s1, x0, yp); acc_term(s0, x0, y0); acc_term(s1, x1, y0); acc_term(s0, x1, y1);
+            yp = y1; pa += 2; pb -= 2;
+        }
+        { const mt x0 = pa[0], y0 = pb[0]; acc_term(s1, x0, yp); acc_term(s0, x0, y0); }      // J - 1 is odd: one term is left
         acc_term(s0, Tf[t.offa0()], Tf[t.offB() + J]);
     }
 }
@@ -517,17 +544,19 @@ template <bool FAST>
 __device__ __forceinline__ void pair_early(const mt* __restrict__ Tf, const TaskR& t0, const TaskR& t1, int J,
                                            acc4& a0, acc4& a1, acc4& b0, acc4& b1) {
     if (FAST || J >= 2) {
-        const mt* pa = Tf + t0.offA() + 1; const mt* pb = Tf + t0.offB() + J; const mt* qb = Tf + t1.offB() + J;
-        mt x = *pa, yp = *pb, zp = *qb, y = pb[-1], z = qb[-1];
-        pa++; pb -= 2; qb -= 2;
+        const mt* pa = Tf + t0.offA() + 1; const mt* pb = Tf + t0.offB() + J - 1; const mt* qb = Tf + t1.offB() + J - 1;
+        mt yp = pb[1], zp = qb[1];
+        int l = 1;
 #pragma unroll 2
-        for (int l = 1; l < J; l++) {
-            const mt xn = *pa, yn = *pb, zn = *qb;
-            acc_term(a1, x, yp); acc_term(b1, x, zp); acc_term(a0, x, y); acc_term(b0, x, z);
-            yp = y; zp = z; x = xn; y = yn; z = zn; pa++; pb--; qb--;
+        for (; l + 1 < J; l += 2) {
+            const mt x0 = pa[0], x1 = pa[1], y0 = pb[0], y1 = pb[-1], z0 = qb[0], z1 = qb[-1];
+            acc_term(a1, x0, yp); acc_term(b1, x0, zp); acc_term(a0, x0, y0); acc_term(b0, x0, z0);
+            acc_term(a1, x1, y0); acc_term(b1, x1, z0); acc_term(a0, x1, y1); acc_term(b0, x1, z1);
+            yp = y1; zp = z1; pa += 2; pb -= 2; qb -= 2;
         }
-        const mt x0 = Tf[t0.offa0()];
-        acc_term(a0, x0, Tf[t0.offB() + J]); acc_term(b0, x0, Tf[t1.offB() + J]);
+        { const mt x0 = pa[0], y0 = pb[0], z0 = qb[0]; acc_term(a1, x0, yp); acc_term(b1, x0, zp); acc_term(a0, x0, y0); acc_term(b0, x0, z0); }
+        const mt x0e = Tf[t0.offa0()];
+        acc_term(a0, x0e, Tf[t0.offB() + J]); acc_term(b0, x0e, Tf[t1.offB() + J]);
     }
 }
 template <bool FAST>
@@ -1090,7 +1119,7 @@ __device__ inline LaneC make_lanec(int tid) {
     const int wq = tid >> 5, lane = tid & 31;
     LaneC c;
     int pi0, pi1, pi2, pi3;
-    pair_tasks<N>(wq == 1 ? lane : -1, pi0, pi1);
+    pair_tasks<N>(wq == 1 ? psi_lane_to_pair<N>(lane) : -1, pi0, pi1);
     pair_tasks<N>((wq == 1 && CROUNDS > 1) ? 32 + lane : -1, pi2, pi3);
     c.tA = make_taskr(wq == 0 ? (lane < L::NA ? decode_task<N>(0, lane) : decode_task<N>(1, lane - L::NA)) : decode_task<N>(2, pi0));
     c.tB = make_taskr(decode_task<N>(2, wq == 0 ? (1 << 20) : pi1));
@@ -1414,13 +1443,13 @@ __device__ __noinline__ int step_body(FrontSmem<N>& S, const int s, const unsign
         {
             constexpr int NH = D + D * D, NHT = (NH + 1) / 2;
             for (int tt = tid; tt < NHT; tt += NT) {
-                const int hA = 2 * tt, hB = 2 * tt + 1 < NH ? 2 * tt + 1 : NH - 1;
+                const int hA = image_series<N>(tt, 0), hB = image_series<N>(tt, 1);       // the two series of this lane (hB = NH: none)
                 auto row_of = [&](int h) -> const mt* {
                     if (h < D) return h < N ? T[L::U(h)] : T[L::V(h - N)];
                     const int e = h - D, row = e / D, cc = e % D, i = row % N;
                     return row < N ? T[L::PU(i, cc)] : T[L::PV(i, cc)];
                 };
-                const mt* ra = row_of(hA); const mt* rb = row_of(hB);
+                const mt* ra = row_of(hA); const mt* rb = row_of(hB < NH ? hB : NH - 1);
                 ival a = mt2iv(ra[p]), bq = mt2iv(rb[p]);
 #pragma unroll 4
                 for (int k = p - 1; k >= 1; k--) { a = horner_pt(a, hs, mt2iv(ra[k])); bq = horner_pt(bq, hs, mt2iv(rb[k])); }
@@ -1434,7 +1463,7 @@ __device__ __noinline__ int step_body(FrontSmem<N>& S, const int s, const unsign
                     }
                 };
                 put(hA, a);
-                if (2 * tt + 1 < NH) put(hB, bq);
+                if (hB < NH) put(hB, bq);
             }
             for (int e = tid - (NT - (D * N) % NT) % NT; e < D * N; e += NT) {
                 if (e < 0) continue;
