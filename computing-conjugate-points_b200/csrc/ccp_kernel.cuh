@@ -13,7 +13,21 @@
 #include <cuda/std/type_traits>
 #include "../../include/ccp.h"
 
+#ifndef CCP_UNROLL_S
+#define CCP_UNROLL_S 1      // unrolling of the two-term loops of the Cauchy passes (single tasks / pairs of tasks)
+#endif
+#ifndef CCP_UNROLL_P
+#define CCP_UNROLL_P 1      // 1 measured best at full occupancy: the step loop streams ~78 KB of code per step (L1.5 instruction cache: 32 KB), smaller is faster
+#endif
+#ifndef CCP_UNROLL_H
+#define CCP_UNROLL_H 4      // Horner chains of the step image
+#endif
+#ifndef CCP_UNROLL_G
+#define CCP_UNROLL_G 2      // Horner chains of the grid loop
+#endif
+
 namespace ccp {
+constexpr int UNROLL_S = CCP_UNROLL_S, UNROLL_P = CCP_UNROLL_P, UNROLL_H = CCP_UNROLL_H, UNROLL_G = CCP_UNROLL_G;
 
 // Optional per-phase cycle counters (make prof): block 0 adds clock64() deltas into g_prof[phase].
 #ifdef CCP_TRACE
@@ -512,7 +526,7 @@ __device__ __forceinline__ void pass_early(const mt* __restrict__ Tf, const Task
         const mt* pb = Tf + t.offB() + J - 1;                    // b[J-l]
         mt yp = pb[1];                                           // b[J+1-l]: the only operand carried from term to term
         int l = 1;
-#pragma unroll 2
+#pragma unroll UNROLL_S
         for (; l + 1 < J; l += 2) {                              // two terms per iteration: no operand rotation through register moves
             const mt x0 = pa[0], x1 = pa[1], y0 = pb[0], y1 = pb[-1];
             acc_term(s1, x0, yp); acc_term(s0, x0, y0); acc_term(s1, x1, y0); acc_term(s0, x1, y1);
@@ -547,7 +561,7 @@ __device__ __forceinline__ void pair_early(const mt* __restrict__ Tf, const Task
         const mt* pa = Tf + t0.offA() + 1; const mt* pb = Tf + t0.offB() + J - 1; const mt* qb = Tf + t1.offB() + J - 1;
         mt yp = pb[1], zp = qb[1];
         int l = 1;
-#pragma unroll 2
+#pragma unroll UNROLL_P
         for (; l + 1 < J; l += 2) {
             const mt x0 = pa[0], x1 = pa[1], y0 = pb[0], y1 = pb[-1], z0 = qb[0], z1 = qb[-1];
             acc_term(a1, x0, yp); acc_term(b1, x0, zp); acc_term(a0, x0, y0); acc_term(b0, x0, z0);
@@ -1451,7 +1465,7 @@ __device__ __noinline__ int step_body(FrontSmem<N>& S, const int s, const unsign
                 };
                 const mt* ra = row_of(hA); const mt* rb = row_of(hB < NH ? hB : NH - 1);
                 ival a = mt2iv(ra[p]), bq = mt2iv(rb[p]);
-#pragma unroll 4
+#pragma unroll UNROLL_H
                 for (int k = p - 1; k >= 1; k--) { a = horner_pt(a, hs, mt2iv(ra[k])); bq = horner_pt(bq, hs, mt2iv(rb[k])); }
                 a = mk(__dmul_rd(a.lo, hs), __dmul_ru(a.hi, hs)); bq = mk(__dmul_rd(bq.lo, hs), __dmul_ru(bq.hi, hs));     // = eval_inc
                 auto put = [&](int h, const ival& v) {
@@ -1532,7 +1546,7 @@ __device__ __noinline__ int step_body(FrontSmem<N>& S, const int s, const unsign
                     acc[j] = top; tl[j] = S.gp[ic]; th[j] = S.gp[ic + 1];
                 }
                 if (wq == 0) {
-#pragma unroll 2
+#pragma unroll UNROLL_G
                     for (int k = p - 1; k >= 0; k--) {
                         q -= NN;
                         const ival ck = *q;
@@ -1540,7 +1554,7 @@ __device__ __noinline__ int step_body(FrontSmem<N>& S, const int s, const unsign
                         for (int j = 0; j < PPL; j++) acc[j] = horner_pt(acc[j], th[j], ck);
                     }
                 } else {
-#pragma unroll 2
+#pragma unroll UNROLL_G
                     for (int k = p - 1; k >= 0; k--) {
                         q -= NN;
                         const ival ck = *q;
