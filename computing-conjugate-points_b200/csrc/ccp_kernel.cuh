@@ -13,6 +13,15 @@
 #include <cuda/std/type_traits>
 #include "../../include/ccp.h"
 
+#ifndef CCP_PASS_PREFETCH
+#define CCP_PASS_PREFETCH 0      // 1: operands of the next two terms of a Cauchy pass are loaded one iteration ahead
+#endif
+#ifndef CCP_SINGLES
+#define CCP_SINGLES 1           // 1: one variational product per lane, two columns of Psi hosted by the idle lanes of the phi warp (n <= 3)
+#endif
+#ifndef CCP_LATE_PRELOAD
+#define CCP_LATE_PRELOAD 0      // 1: operands of the late terms that are known before the pair barrier are loaded before it
+#endif
 #ifndef CCP_UNROLL_S
 #define CCP_UNROLL_S 1      // unrolling of the two-term loops of the Cauchy passes (single tasks / pairs of tasks)
 #endif
@@ -368,13 +377,11 @@ __host__ __device__ inline int step_count(double L_minus, double h) {
 
 // ------------------------------------------------------------------------------------------------
 // Cauchy tasks.  Every Taylor-table product of one order is one "task" = sum_j a(j) b(kk-j) with
-//   a(0) = T[a0r][a0c], a(j) = T[iA][j];   b(0) = T[b0r][b0c], b(m) = +-T[iB][m]  (sign flip for z = 1-u).
-// A CTA of NT = 128 threads owns one front.  Each task is split over a lane pair (j < hsplit, j >= hsplit) and
-// the two accumulators are merged with one shuffle; 64 tasks run per phase:
-//   phase 0: A(k) = g, q of order k   + C(k-1) tasks (Psi products of the previous order)
-//   phase 1: B(k) = g*w products      + remaining C(k-1) tasks            (B needs g[k] from phase 0)
-// then one combine phase turns the sums into the order-(k+1) coefficients of u, v, the order-k coefficients
-// of M and the order-k coefficients of Psi.  Same values as oracle/c1.hpp, which computes them serially.
+//   a(0) = T[a0r][a0c], a(j) = T[iA][j];   b(0) = T[b0r][b0c], b(m) = T[iB][m]     (z = 1 - u has its own rows).
+// A CTA of NT = 64 threads owns one front: warp "phi" holds the A tasks (g = u z, q = w w), the B tasks (H w) and the lanes that turn
+// g, q into the M-series and H; warp "Psi" holds the C tasks (M Psi^u), in pairs that share the M-series (or, CCP_SINGLES, one per lane
+// with two columns of Psi hosted by idle lanes of the phi warp).  table_loop<N> runs them in stages of two Taylor orders; the sums keep
+// the summation order of oracle/c1.hpp, which computes them serially.  Which lane does what is a table (LaneC, make_lanec).
 // ------------------------------------------------------------------------------------------------
 constexpr int NT = 64;                  // threads per front (one CTA): warp 0 = front tables (phi), warp 1 = variational tables (Psi)
 constexpr int NWARP = NT / 32;
@@ -526,6 +533,17 @@ __device__ __forceinline__ void pass_early(const mt* __restrict__ Tf, const Task
         const mt* pb = Tf + t.offB() + J - 1;                    // b[J-l]
         mt yp = pb[1];                                           // b[J+1-l]: the only operand carried from term to term
         int l = 1;
+#if CCP_PASS_PREFETCH
+        mt x0 = pa[0], x1 = pa[1], y0 = pb[0], y1 = pb[-1];      // operands of the next two terms are loaded one iteration ahead
+#pragma unroll UNROLL_S
+        for (; l + 1 < J; l += 2) {
+            pa += 2; pb -= 2;
+            const mt x0n = pa[0], x1n = pa[1], y0n = pb[0], y1n = pb[-1];     // the last prefetch reads valid, unused table slots
+            acc_term(s1, x0, yp); acc_term(s0, x0, y0); acc_term(s1, x1, y0); acc_term(s0, x1, y1);
+            yp = y1; x0 = x0n; x1 = x1n; y0 = y0n; y1 = y1n;
+        }
+        acc_term(s1, x0, yp); acc_term(s0, x0, y0);              // J - 1 is odd: one term is left
+#else
 #pragma unroll UNROLL_S
         for (; l + 1 < J; l += 2) {                              // two terms per iteration: no operand rotation through register moves
             const mt x0 = pa[0], x1 = pa[1], y0 = pb[0], y1 = pb[-1];
@@ -533,6 +551,7 @@ __device__ __forceinline__ void pass_early(const mt* __restrict__ Tf, const Task
             yp = y1; pa += 2; pb -= 2;
         }
         { const mt x0 = pa[0], y0 = pb[0]; acc_term(s1, x0, yp); acc_term(s0, x0, y0); }      // J - 1 is odd: one term is left
+#endif
         acc_term(s0, Tf[t.offa0()], Tf[t.offB() + J]);
     }
 }
@@ -553,6 +572,19 @@ __device__ __forceinline__ void pass_late(const mt* __restrict__ Tf, const TaskR
         if (two) { acc_term(s1, a0, Tf[t.offB() + 1]); acc_term(s1, Tf[t.offA() + 1], b0); }
     }
 }
+// The operands of the late terms that are known before the stage's barrier (FAST stages: J >= 2, so a0 = a[0] is an old coefficient)
+struct LatePre { mt a0, b0, b1, bJ1; };
+__device__ __forceinline__ LatePre late_preload(const mt* __restrict__ Tf, const TaskR& t, int J) {
+    LatePre q; q.a0 = Tf[t.offa0()]; q.b0 = Tf[t.offb0()]; q.b1 = Tf[t.offB() + 1]; q.bJ1 = Tf[t.offB() + J + 1];
+    return q;
+}
+__device__ __forceinline__ void pass_late_pre(const mt* __restrict__ Tf, const TaskR& t, int J, const LatePre& q, acc4& s0, acc4& s1) {
+    const mt aJ = Tf[t.offA() + J], aJ1 = Tf[t.offA() + J + 1];
+    acc_term(s0, aJ, q.b0);
+    acc_term(s1, aJ, q.b1);
+    acc_term(s1, q.a0, q.bJ1);
+    acc_term(s1, aJ1, q.b0);
+}
 // Two tasks that SHARE their first operand series (Psi warp: one M-series times two columns of Psi): 3 LDS.128 + 16 DFMA per term.
 template <bool FAST>
 __device__ __forceinline__ void pair_early(const mt* __restrict__ Tf, const TaskR& t0, const TaskR& t1, int J,
@@ -561,6 +593,18 @@ __device__ __forceinline__ void pair_early(const mt* __restrict__ Tf, const Task
         const mt* pa = Tf + t0.offA() + 1; const mt* pb = Tf + t0.offB() + J - 1; const mt* qb = Tf + t1.offB() + J - 1;
         mt yp = pb[1], zp = qb[1];
         int l = 1;
+#if CCP_PASS_PREFETCH
+        mt x0 = pa[0], x1 = pa[1], y0 = pb[0], y1 = pb[-1], z0 = qb[0], z1 = qb[-1];
+#pragma unroll UNROLL_P
+        for (; l + 1 < J; l += 2) {
+            pa += 2; pb -= 2; qb -= 2;
+            const mt x0n = pa[0], x1n = pa[1], y0n = pb[0], y1n = pb[-1], z0n = qb[0], z1n = qb[-1];
+            acc_term(a1, x0, yp); acc_term(b1, x0, zp); acc_term(a0, x0, y0); acc_term(b0, x0, z0);
+            acc_term(a1, x1, y0); acc_term(b1, x1, z0); acc_term(a0, x1, y1); acc_term(b0, x1, z1);
+            yp = y1; zp = z1; x0 = x0n; x1 = x1n; y0 = y0n; y1 = y1n; z0 = z0n; z1 = z1n;
+        }
+        acc_term(a1, x0, yp); acc_term(b1, x0, zp); acc_term(a0, x0, y0); acc_term(b0, x0, z0);
+#else
 #pragma unroll UNROLL_P
         for (; l + 1 < J; l += 2) {
             const mt x0 = pa[0], x1 = pa[1], y0 = pb[0], y1 = pb[-1], z0 = qb[0], z1 = qb[-1];
@@ -569,6 +613,7 @@ __device__ __forceinline__ void pair_early(const mt* __restrict__ Tf, const Task
             yp = y1; zp = z1; pa += 2; pb -= 2; qb -= 2;
         }
         { const mt x0 = pa[0], y0 = pb[0], z0 = qb[0]; acc_term(a1, x0, yp); acc_term(b1, x0, zp); acc_term(a0, x0, y0); acc_term(b0, x0, z0); }
+#endif
         const mt x0e = Tf[t0.offa0()];
         acc_term(a0, x0e, Tf[t0.offB() + J]); acc_term(b0, x0e, Tf[t1.offB() + J]);
     }
@@ -1100,7 +1145,7 @@ __device__ __noinline__ void deriv_entries(const ival* __restrict__ Fk0, const d
 struct LaneC {
     TaskR tA, tB, tC, tD;    // phi warp: tA = this lane's A or B task;  Psi warp: tA/tB and tC/tD = this lane's pairs of C tasks (rounds 0, 1)
     unsigned cs;             // cs0 | cs1 << 8 | cs2 << 16 | gslot << 24       scratch slots (combine stages); gslot 255 = none
-    unsigned ap;             // ap0 | ap1 << 6 | ap2 << 12 | mscale << 18 | mcst << 19 | (mrole + 1) << 20
+    unsigned ap;             // ap0 | ap1 << 6 | ap2 << 12 | mscale << 18 | mcst << 19 | (mrole + 1) << 20 | ccomb << 28 (lane combines the sums of one Psi entry) | cpat << 29
     unsigned rvu;            // rowV | rowU << 16       table offsets (row * KMAX)
     unsigned rz;             // rowZ
     __device__ __forceinline__ int cs0() const { return (int)(cs & 0xffu); }
@@ -1112,7 +1157,9 @@ struct LaneC {
     __device__ __forceinline__ int ap2() const { return (int)((ap >> 12) & 0x3fu); }
     __device__ __forceinline__ int mscale() const { return (int)((ap >> 18) & 1u); }
     __device__ __forceinline__ int mcst() const { return (int)((ap >> 19) & 1u); }
-    __device__ __forceinline__ int mrole() const { return (int)(ap >> 20) - 1; }
+    __device__ __forceinline__ int mrole() const { return (int)((ap >> 20) & 0xffu) - 1; }
+    __device__ __forceinline__ int ccomb() const { return (int)((ap >> 28) & 1u); }
+    __device__ __forceinline__ int cpat() const { return (int)(ap >> 29); }          // singles: 0 = first component (no w = 1 product), 1 = middle, 2 = last (no w = 2 product)
     __device__ __forceinline__ int rowV() const { return (int)(rvu & 0xffffu); }
     __device__ __forceinline__ int rowU() const { return (int)(rvu >> 16); }
     __device__ __forceinline__ int rowZ() const { return (int)rz; }
@@ -1121,8 +1168,18 @@ template <int N> struct TLC {                      // scratch layout of the tabl
     using L = Lay<N>;
     static constexpr int ZSLOT = L::NB + L::NC;      // always-zero slot (missing chain neighbours)
     static constexpr int GS = ZSLOT + 1;             // scratch slots of g_i (N) and q_e (N-1) of the newest order
-    static constexpr int MB = L::NA + L::NB;         // phi warp lanes: A tasks 0..NA-1 | B tasks NA..MB-1 | M/H lanes MB..MB+3N-2
+    static constexpr int MB = L::NA + L::NB;         // phi warp lanes: A tasks 0..NA-1 | B tasks NA..MB-1 | M/H lanes MB..MB+3N-2 | hosted C tasks HOST0..
     static_assert(MB + 3 * N - 1 <= 32, "phi warp: A, B and M/H lanes side by side");
+    // Distribution of the 2N(3N-2) variational products (C tasks).  The products of one column cc of Psi only involve that column, so
+    // whole columns can live in either warp without any exchange but the M-series.  n <= 3 ("singles"): every lane owns ONE product --
+    // the Psi warp the columns HC..2N-1, the idle lanes of the phi warp the columns 0..HC-1 -- so both warps run the single-task pass
+    // (8 DFMA per term; a pair pass costs 16 DFMA instructions per term however few lanes are busy, and at full occupancy the passes are
+    // bound by the FP64 pipes).  n = 4: pairs of products sharing the M-series, two rounds, all in the Psi warp.
+    static constexpr bool SINGLES = CCP_SINGLES && N <= 3;
+    static constexpr int PPC = 3 * N - 2;            // products per column
+    static constexpr int HOST0 = MB + 3 * N - 1;     // first hosted lane of the phi warp
+    static constexpr int HC = !SINGLES ? 0 : (2 * N - 32 / PPC > 0 ? 2 * N - 32 / PPC : 0);      // hosted columns: those the Psi warp cannot hold (n = 3: 2 of 6)
+    static_assert(!SINGLES || ((2 * N - HC) * PPC <= 32 && HOST0 + HC * PPC <= 32), "singles: one product per lane");
     static_assert(GS + 2 * N - 1 < 255, "scratch slots fit 8 bits");
 };
 template <int N>
@@ -1132,10 +1189,34 @@ __device__ inline LaneC make_lanec(int tid) {
     constexpr int CROUNDS = PhaseCheck<N>::CROUNDS;
     const int wq = tid >> 5, lane = tid & 31;
     LaneC c;
-    int pi0, pi1, pi2, pi3;
-    pair_tasks<N>(wq == 1 ? psi_lane_to_pair<N>(lane) : -1, pi0, pi1);
-    pair_tasks<N>((wq == 1 && CROUNDS > 1) ? 32 + lane : -1, pi2, pi3);
-    c.tA = make_taskr(wq == 0 ? (lane < L::NA ? decode_task<N>(0, lane) : decode_task<N>(1, lane - L::NA)) : decode_task<N>(2, pi0));
+    constexpr bool SINGLES = TLC<N>::SINGLES;
+    constexpr int PPC = TLC<N>::PPC, HOST0 = TLC<N>::HOST0, HC = TLC<N>::HC;
+    // index of the product (i, cc, w) in the enumeration of decode_task (w = 0: Md_i Pu_i, 1: Mo_{i-1} Pu_{i-1}, 2: Mo_i Pu_{i+1})
+    auto c_index = [](int i, int cc, int w) -> int {
+        const int nw = (i == 0 || i == N - 1) ? 2 : 3;
+        const int widx = (i == 0) ? (w == 0 ? 0 : 1) : w;                     // i = 0 has w in {0, 2}; the others start at w = 0, 1
+        return (i == 0 ? 0 : (3 * i - 1) * D) + cc * nw + widx;
+    };
+    // k-th product of a column, i-major: (i, w) pairs in the order (0,0) (0,2) (1,0) (1,1) (1,2) ... (N-1,0) (N-1,1)
+    auto column_product = [&](int cc, int k) -> int {
+        int cnt = 0, idx = 1 << 20;
+        for (int i = 0; i < N; i++) for (int w = 0; w < 3; w++) {
+            if ((w == 1 && i == 0) || (w == 2 && i == N - 1)) continue;
+            if (cnt == k) idx = c_index(i, cc, w);
+            cnt++;
+        }
+        return idx;
+    };
+    int pi0 = 1 << 20, pi1 = 1 << 20, pi2 = 1 << 20, pi3 = 1 << 20;
+    if (SINGLES) {
+        if (wq == 1 && lane < (D - HC) * PPC) pi0 = column_product(HC + lane / PPC, lane % PPC);                  // Psi warp: columns HC..D-1
+        if (wq == 0 && lane >= HOST0 && lane < HOST0 + HC * PPC) pi0 = column_product((lane - HOST0) / PPC, (lane - HOST0) % PPC);   // phi warp: hosted columns
+    } else {
+        pair_tasks<N>(wq == 1 ? psi_lane_to_pair<N>(lane) : -1, pi0, pi1);
+        pair_tasks<N>((wq == 1 && CROUNDS > 1) ? 32 + lane : -1, pi2, pi3);
+    }
+    const bool hosted = SINGLES && wq == 0 && lane >= HOST0;
+    c.tA = make_taskr((wq == 0 && !hosted) ? (lane < L::NA ? decode_task<N>(0, lane) : decode_task<N>(1, lane - L::NA)) : decode_task<N>(2, pi0));
     c.tB = make_taskr(decode_task<N>(2, wq == 0 ? (1 << 20) : pi1));
     c.tC = make_taskr(decode_task<N>(2, pi2)); c.tD = make_taskr(decode_task<N>(2, pi3));
     // operands of the "combine" stages.  Every stage is ONE branch-free instruction stream (missing neighbours: zero parameter, clamped slot).
@@ -1163,19 +1244,40 @@ __device__ inline LaneC make_lanec(int tid) {
             mscale = 0; rowV = L::MO(e) * KMAX;
         }
         if (lane < L::NA) gslot = GS + lane;                 // A lanes: g (task i) and q (task N+e)
-    } else if (lane < N * D) {
-        const int i = lane / D, cc = lane % D;
-        int c0 = L::NB + (i == 0 ? 0 : (3 * i - 1) * D) + cc * ((i == 0 || i == N - 1) ? 2 : 3);
-        cs0 = c0++;
-        if (i > 0)     cs1 = c0++;
-        if (i < N - 1) cs2 = c0;
-        rowV = L::PV(i, cc) * KMAX; rowU = L::PU(i, cc) * KMAX;
+    }
+    // lanes that combine the sums of one entry (i, cc) of Psi: Psi warp: the entries of its columns; phi warp (singles): the hosted columns
+    int ccomb = 0, cpat = 0;
+    {
+        int e = -1, ci = 0, ccc = 0;
+        if (SINGLES) {
+            // singles: the lane that owns the FIRST product of an entry (i, cc) combines the entry; its partners are the next one or two lanes
+            // (products of a column in the order (0,0) (0,2) | (1,0) (1,1) (1,2) | ... | (N-1,0) (N-1,1)), whose sums arrive through shuffles
+            int pl = -1, c0l = 0;
+            if (wq == 1 && lane < (D - HC) * PPC) { pl = lane % PPC; c0l = HC + lane / PPC; }
+            if (wq == 0 && lane >= HOST0 && lane < HOST0 + HC * PPC) { pl = (lane - HOST0) % PPC; c0l = (lane - HOST0) / PPC; }
+            if (pl == 0) { e = 0; ci = 0; ccc = c0l; }
+            else if (pl >= 2 && (pl - 2) % 3 == 0) { e = 0; ci = 1 + (pl - 2) / 3; ccc = c0l; }
+            cpat = ci == 0 ? 0 : (ci == N - 1 ? 2 : 1);
+        } else if (wq == 1 && lane < N * D) { e = lane; ci = e / D; ccc = e % D; }
+        if (e >= 0) {
+            const int i = ci, cc = ccc;
+            int c0 = L::NB + (i == 0 ? 0 : (3 * i - 1) * D) + cc * ((i == 0 || i == N - 1) ? 2 : 3);
+            cs0 = c0++;
+            if (i > 0)     cs1 = c0++;
+            if (i < N - 1) cs2 = c0;
+            rowV = L::PV(i, cc) * KMAX; rowU = L::PU(i, cc) * KMAX;
+            ccomb = 1;
+        }
     }
     c.cs = opaqueu((unsigned)cs0 | ((unsigned)cs1 << 8) | ((unsigned)cs2 << 16) | ((unsigned)gslot << 24));
-    c.ap = opaqueu((unsigned)ap0 | ((unsigned)ap1 << 6) | ((unsigned)ap2 << 12) | ((unsigned)mscale << 18) | ((unsigned)mcst << 19) | ((unsigned)(mrole + 1) << 20));
+    c.ap = opaqueu((unsigned)ap0 | ((unsigned)ap1 << 6) | ((unsigned)ap2 << 12) | ((unsigned)mscale << 18) | ((unsigned)mcst << 19) | ((unsigned)(mrole + 1) << 20) | ((unsigned)ccomb << 28) | ((unsigned)(ccomb ? cpat : 0) << 29));
     c.rvu = opaqueu((unsigned)rowV | ((unsigned)rowU << 16));
     c.rz = opaqueu((unsigned)rowZ);
     return c;
+}
+
+__device__ __forceinline__ ival shfl_down_ival(const ival& a, int d) {
+    return mk(__shfl_down_sync(0xffffffffu, a.lo, d), __shfl_down_sync(0xffffffffu, a.hi, d));
 }
 
 // The lane constants are the same for every front of one n: a table in global memory, filled once per device (lanec_table_kernel, launched
@@ -1213,6 +1315,8 @@ __device__ __noinline__ void table_loop(FrontSmem<N>& S) {
     const int p = S.cfg.p;
     constexpr int D = 2 * N, GS = TLC<N>::GS;
     constexpr int CROUNDS = PhaseCheck<N>::CROUNDS;
+    constexpr bool SINGLES = TLC<N>::SINGLES;
+    constexpr int HC = TLC<N>::HC;
     const int tid = threadIdx.x ^ S.vswap, wq = tid >> 5, lane = tid & 31;
     mt (*T)[KMAX] = S.T;
     const mt* const Tf = &T[0][0];
@@ -1229,6 +1333,8 @@ __device__ __noinline__ void table_loop(FrontSmem<N>& S) {
 #define mscale lq.mscale()
 #define mcst lq.mcst()
 #define mrole lq.mrole()
+#define ccomb lq.ccomb()
+#define cpat lq.cpat()
 #undef PROF
 #undef TRC
 #define PROF(i) do {} while (0)
@@ -1253,6 +1359,26 @@ __device__ __noinline__ void table_loop(FrontSmem<N>& S) {
             }
             lq.cs = opaqueu(lq.cs); lq.ap = opaqueu(lq.ap); lq.rvu = opaqueu(lq.rvu); lq.rz = opaqueu(lq.rz);
             const TaskR tA = lq.tA, tB = lq.tB, tC = lq.tC, tD = lq.tD;
+            // the lanes that own an entry (i, cc) of Psi: scratch sums of order kc -> Pv[kc+1];  Pu[kc+2] = Pv[kc+1]/(kc+2)   (Pu[1] = Pv[0] comes with the order-0 data)
+            auto combine_c = [&]() {
+                if (ccomb) {
+                    const mt i1 = inv[J + 1], i2 = inv[J + 2], i3 = inv[J + 3];
+                    const ival x0 = scr0[cs0], x1 = scr0[cs1], x2 = scr0[cs2], y0 = scr1[cs0], y1 = scr1[cs1], y2 = scr1[cs2];
+                    const mt pv1 = mt_scale(iv2mt(iadd(iadd(x0, x1), x2)), i1.m, i1.t), pv2 = mt_scale(iv2mt(iadd(iadd(y0, y1), y2)), i2.m, i2.t);
+                    const mt pu2 = mt_scale(pv1, i2.m, i2.t), pu3 = mt_scale(pv2, i3.m, i3.t);
+                    T[0][rowV + J + 1] = pv1;
+                    (two ? &T[0][rowV + J + 2] : dummy)[0] = pv2;
+                    (two ? &T[0][rowU + J + 2] : dummy)[0] = pu2;
+                    (three ? &T[0][rowU + J + 3] : dummy)[0] = pu3;
+                }
+            };
+            // singles: the sums of the one or two partner lanes arrive through shuffles (every lane of the warp executes them); the leader of an
+            // entry forms (w0 + w1) + w2 with an exact zero for the product a boundary component does not have -- the additions of combine_c
+            auto entry_sum = [&](const ival& f) -> ival {
+                const ival t1 = shfl_down_ival(f, 1), t2 = shfl_down_ival(f, 2);
+                const ival b = cpat == 0 ? pt(0.0) : t1, c = cpat == 0 ? t1 : (cpat == 1 ? t2 : pt(0.0));
+                return iadd(iadd(f, b), c);
+            };
             if (wq == 0) {
                 PROF(12);
                 TRC(100 + J);
@@ -1286,12 +1412,40 @@ __device__ __noinline__ void table_loop(FrontSmem<N>& S) {
                 }
                 __syncwarp();
                 TRC(400 + J);
+#if CCP_LATE_PRELOAD
+                LatePre lp;
+                if (FAST && kind >= 1) lp = late_preload(Tf, tA, J);      // operands of the late terms that do not depend on this stage
+                else { lp.a0 = lp.b0 = lp.b1 = lp.bJ1 = ptm(0.0); }
+#define LATE_TERMS(acc0, acc1) do { if (FAST) pass_late_pre(Tf, tA, J, lp, acc0, acc1); else pass_late<FAST>(Tf, tA, J, two, acc0, acc1); } while (0)
+#else
+#define LATE_TERMS(acc0, acc1) pass_late<FAST>(Tf, tA, J, two, acc0, acc1)
+#endif
                 bar_pair();                                       // Md, Mo of orders J, J+1 are in the tables
                 TRC(500 + J);
-                if (kind == 1) {                                  // B lanes: (H w)[kc] is v'[kc]:  v[kc+1] = sum/(kc+1), u[kc+2] = v[kc+1]/(kc+2), z = -u
+                ival f0 = pt(0.0), f1 = pt(0.0);
+                if (kind == 1 || (SINGLES && HC > 0 && kind == 2)) {      // B lanes and hosted C lanes: the same late terms in one instruction stream
+                    LATE_TERMS(s0, s1);
+                    f0 = acc_finish(s0); f1 = acc_finish(s1);
+                }
+                if (SINGLES && HC > 0) {
+                    // B lanes and the leaders of the hosted entries of Psi share ONE epilogue: sum -> (mid,t) -> /(kc+1) -> /(kc+2) -> rows V, U (B: and Z)
+                    const ival e0 = entry_sum(f0), e1 = entry_sum(f1);
+                    if (kind == 1 || ccomb) {
+                        const ival g0 = kind == 1 ? f0 : e0, g1 = kind == 1 ? f1 : e1;
+                        const mt i1 = inv[J + 1], i2 = inv[J + 2], i3 = inv[J + 3];
+                        const mt v1 = mt_scale(iv2mt(g0), i1.m, i1.t), v2 = mt_scale(iv2mt(g1), i2.m, i2.t);
+                        const mt u2 = mt_scale(v1, i2.m, i2.t), u3 = mt_scale(v2, i3.m, i3.t);
+                        mt z2, z3; z2.m = -u2.m; z2.t = u2.t; z3.m = -u3.m; z3.t = u3.t;
+                        T[0][rowV + J + 1] = v1;
+                        (two ? &T[0][rowV + J + 2] : dummy)[0] = v2;
+                        (two ? &T[0][rowU + J + 2] : dummy)[0] = u2;
+                        (three ? &T[0][rowU + J + 3] : dummy)[0] = u3;
+                        ((two && kind == 1) ? &T[0][rowZ + J + 2] : dummy)[0] = z2;
+                        ((three && kind == 1) ? &T[0][rowZ + J + 3] : dummy)[0] = z3;
+                    }
+                } else if (kind == 1) {                           // B lanes: (H w)[kc] is v'[kc]:  v[kc+1] = sum/(kc+1), u[kc+2] = v[kc+1]/(kc+2), z = -u
                     const mt i1 = inv[J + 1], i2 = inv[J + 2], i3 = inv[J + 3];
-                    pass_late<FAST>(Tf, tA, J, two, s0, s1);
-                    const mt v1 = mt_scale(iv2mt(acc_finish(s0)), i1.m, i1.t), v2 = mt_scale(iv2mt(acc_finish(s1)), i2.m, i2.t);
+                    const mt v1 = mt_scale(iv2mt(f0), i1.m, i1.t), v2 = mt_scale(iv2mt(f1), i2.m, i2.t);
                     const mt u2 = mt_scale(v1, i2.m, i2.t), u3 = mt_scale(v2, i3.m, i3.t);
                     mt z2, z3; z2.m = -u2.m; z2.t = u2.t; z3.m = -u3.m; z3.t = u3.t;
                     T[0][rowV + J + 1] = v1;
@@ -1300,10 +1454,45 @@ __device__ __noinline__ void table_loop(FrontSmem<N>& S) {
                     (three ? &T[0][rowU + J + 3] : dummy)[0] = u3; (three ? &T[0][rowZ + J + 3] : dummy)[0] = z3;
                 }
                 __syncwarp();
+#undef LATE_TERMS
                 PROF(9);
             } else {
                 TRC(700 + J);
                 // variational tables: products M * Psi^u of orders J, J+1 (pairs of tasks sharing the M-series)
+                if constexpr (SINGLES) {
+                    // one product per lane: the single-task pass of the phi warp
+                    const bool r0 = tA.kind() == 2;
+                    acc4 s0 = acc_zero(), s1 = acc_zero();        // defined on every path (see the phi warp)
+                    if (r0) pass_early<FAST>(Tf, tA, J, s0, s1);
+                    TRC(400 + J);
+#if CCP_LATE_PRELOAD
+                    LatePre lp;
+                    if (FAST && r0) lp = late_preload(Tf, tA, J);
+                    else { lp.a0 = lp.b0 = lp.b1 = lp.bJ1 = ptm(0.0); }
+#endif
+                    bar_pair();
+                    TRC(500 + J);
+                    ival f0 = pt(0.0), f1 = pt(0.0);
+                    if (r0) {
+#if CCP_LATE_PRELOAD
+                        if (FAST) pass_late_pre(Tf, tA, J, lp, s0, s1); else
+#endif
+                        pass_late<FAST>(Tf, tA, J, two, s0, s1);
+                        f0 = acc_finish(s0); f1 = acc_finish(s1);
+                    }
+                    TRC(800 + J);
+                    const ival e0 = entry_sum(f0), e1 = entry_sum(f1);
+                    if (ccomb) {                                  // Pv[kc+1] = sum/(kc+1);  Pu[kc+2] = Pv[kc+1]/(kc+2)   (Pu[1] = Pv[0] comes with the order-0 data)
+                        const mt i1 = inv[J + 1], i2 = inv[J + 2], i3 = inv[J + 3];
+                        const mt pv1 = mt_scale(iv2mt(e0), i1.m, i1.t), pv2 = mt_scale(iv2mt(e1), i2.m, i2.t);
+                        const mt pu2 = mt_scale(pv1, i2.m, i2.t), pu3 = mt_scale(pv2, i3.m, i3.t);
+                        T[0][rowV + J + 1] = pv1;
+                        (two ? &T[0][rowV + J + 2] : dummy)[0] = pv2;
+                        (two ? &T[0][rowU + J + 2] : dummy)[0] = pu2;
+                        (three ? &T[0][rowU + J + 3] : dummy)[0] = pu3;
+                    }
+                    __syncwarp();
+                } else {
                 acc4 a0, a1, b0, b1, c0, c1, d0, d1;
                 const bool r0 = tA.kind() == 2, r1 = CROUNDS > 1 && tC.kind() == 2;
                 // every lane runs the passes (lanes without a task: on row 0, results dropped into the dummy slot) -- no divergence, and the
@@ -1329,17 +1518,9 @@ __device__ __noinline__ void table_loop(FrontSmem<N>& S) {
                 }
                 __syncwarp();
                 TRC(800 + J);
-                if (lane < N * D) {                               // scratch sums of order kc -> Pv[kc+1];  Pu[kc+2] = Pv[kc+1]/(kc+2)   (Pu[1] = Pv[0] comes with the order-0 data)
-                    const mt i1 = inv[J + 1], i2 = inv[J + 2], i3 = inv[J + 3];
-                    const ival x0 = scr0[cs0], x1 = scr0[cs1], x2 = scr0[cs2], y0 = scr1[cs0], y1 = scr1[cs1], y2 = scr1[cs2];
-                    const mt pv1 = mt_scale(iv2mt(iadd(iadd(x0, x1), x2)), i1.m, i1.t), pv2 = mt_scale(iv2mt(iadd(iadd(y0, y1), y2)), i2.m, i2.t);
-                    const mt pu2 = mt_scale(pv1, i2.m, i2.t), pu3 = mt_scale(pv2, i3.m, i3.t);
-                    T[0][rowV + J + 1] = pv1;
-                    (two ? &T[0][rowV + J + 2] : dummy)[0] = pv2;
-                    (two ? &T[0][rowU + J + 2] : dummy)[0] = pu2;
-                    (three ? &T[0][rowU + J + 3] : dummy)[0] = pu3;
-                }
+                combine_c();
                 __syncwarp();
+                }
             }
         };
 
@@ -1360,6 +1541,8 @@ __device__ __noinline__ void table_loop(FrontSmem<N>& S) {
 #undef mscale
 #undef mcst
 #undef mrole
+#undef ccomb
+#undef cpat
 #undef PROF
 #undef TRC
 }
