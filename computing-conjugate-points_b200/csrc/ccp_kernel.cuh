@@ -13,14 +13,8 @@
 #include <cuda/std/type_traits>
 #include "../../include/ccp.h"
 
-#ifndef CCP_PASS_PREFETCH
-#define CCP_PASS_PREFETCH 0      // 1: operands of the next two terms of a Cauchy pass are loaded one iteration ahead
-#endif
 #ifndef CCP_SINGLES
 #define CCP_SINGLES 1           // 1: one variational product per lane, two columns of Psi hosted by the idle lanes of the phi warp (n <= 3)
-#endif
-#ifndef CCP_LATE_PRELOAD
-#define CCP_LATE_PRELOAD 0      // 1: operands of the late terms that are known before the pair barrier are loaded before it
 #endif
 #ifndef CCP_UNROLL_S
 #define CCP_UNROLL_S 1      // unrolling of the two-term loops of the Cauchy passes (single tasks / pairs of tasks)
@@ -533,17 +527,6 @@ __device__ __forceinline__ void pass_early(const mt* __restrict__ Tf, const Task
         const mt* pb = Tf + t.offB() + J - 1;                    // b[J-l]
         mt yp = pb[1];                                           // b[J+1-l]: the only operand carried from term to term
         int l = 1;
-#if CCP_PASS_PREFETCH
-        mt x0 = pa[0], x1 = pa[1], y0 = pb[0], y1 = pb[-1];      // operands of the next two terms are loaded one iteration ahead
-#pragma unroll UNROLL_S
-        for (; l + 1 < J; l += 2) {
-            pa += 2; pb -= 2;
-            const mt x0n = pa[0], x1n = pa[1], y0n = pb[0], y1n = pb[-1];     // the last prefetch reads valid, unused table slots
-            acc_term(s1, x0, yp); acc_term(s0, x0, y0); acc_term(s1, x1, y0); acc_term(s0, x1, y1);
-            yp = y1; x0 = x0n; x1 = x1n; y0 = y0n; y1 = y1n;
-        }
-        acc_term(s1, x0, yp); acc_term(s0, x0, y0);              // J - 1 is odd: one term is left
-#else
 #pragma unroll UNROLL_S
         for (; l + 1 < J; l += 2) {                              // two terms per iteration: no operand rotation through register moves
             const mt x0 = pa[0], x1 = pa[1], y0 = pb[0], y1 = pb[-1];
@@ -551,7 +534,6 @@ __device__ __forceinline__ void pass_early(const mt* __restrict__ Tf, const Task
             yp = y1; pa += 2; pb -= 2;
         }
         { const mt x0 = pa[0], y0 = pb[0]; acc_term(s1, x0, yp); acc_term(s0, x0, y0); }      // J - 1 is odd: one term is left
-#endif
         acc_term(s0, Tf[t.offa0()], Tf[t.offB() + J]);
     }
 }
@@ -572,19 +554,6 @@ __device__ __forceinline__ void pass_late(const mt* __restrict__ Tf, const TaskR
         if (two) { acc_term(s1, a0, Tf[t.offB() + 1]); acc_term(s1, Tf[t.offA() + 1], b0); }
     }
 }
-// The operands of the late terms that are known before the stage's barrier (FAST stages: J >= 2, so a0 = a[0] is an old coefficient)
-struct LatePre { mt a0, b0, b1, bJ1; };
-__device__ __forceinline__ LatePre late_preload(const mt* __restrict__ Tf, const TaskR& t, int J) {
-    LatePre q; q.a0 = Tf[t.offa0()]; q.b0 = Tf[t.offb0()]; q.b1 = Tf[t.offB() + 1]; q.bJ1 = Tf[t.offB() + J + 1];
-    return q;
-}
-__device__ __forceinline__ void pass_late_pre(const mt* __restrict__ Tf, const TaskR& t, int J, const LatePre& q, acc4& s0, acc4& s1) {
-    const mt aJ = Tf[t.offA() + J], aJ1 = Tf[t.offA() + J + 1];
-    acc_term(s0, aJ, q.b0);
-    acc_term(s1, aJ, q.b1);
-    acc_term(s1, q.a0, q.bJ1);
-    acc_term(s1, aJ1, q.b0);
-}
 // Two tasks that SHARE their first operand series (Psi warp: one M-series times two columns of Psi): 3 LDS.128 + 16 DFMA per term.
 template <bool FAST>
 __device__ __forceinline__ void pair_early(const mt* __restrict__ Tf, const TaskR& t0, const TaskR& t1, int J,
@@ -593,18 +562,6 @@ __device__ __forceinline__ void pair_early(const mt* __restrict__ Tf, const Task
         const mt* pa = Tf + t0.offA() + 1; const mt* pb = Tf + t0.offB() + J - 1; const mt* qb = Tf + t1.offB() + J - 1;
         mt yp = pb[1], zp = qb[1];
         int l = 1;
-#if CCP_PASS_PREFETCH
-        mt x0 = pa[0], x1 = pa[1], y0 = pb[0], y1 = pb[-1], z0 = qb[0], z1 = qb[-1];
-#pragma unroll UNROLL_P
-        for (; l + 1 < J; l += 2) {
-            pa += 2; pb -= 2; qb -= 2;
-            const mt x0n = pa[0], x1n = pa[1], y0n = pb[0], y1n = pb[-1], z0n = qb[0], z1n = qb[-1];
-            acc_term(a1, x0, yp); acc_term(b1, x0, zp); acc_term(a0, x0, y0); acc_term(b0, x0, z0);
-            acc_term(a1, x1, y0); acc_term(b1, x1, z0); acc_term(a0, x1, y1); acc_term(b0, x1, z1);
-            yp = y1; zp = z1; x0 = x0n; x1 = x1n; y0 = y0n; y1 = y1n; z0 = z0n; z1 = z1n;
-        }
-        acc_term(a1, x0, yp); acc_term(b1, x0, zp); acc_term(a0, x0, y0); acc_term(b0, x0, z0);
-#else
 #pragma unroll UNROLL_P
         for (; l + 1 < J; l += 2) {
             const mt x0 = pa[0], x1 = pa[1], y0 = pb[0], y1 = pb[-1], z0 = qb[0], z1 = qb[-1];
@@ -613,7 +570,6 @@ __device__ __forceinline__ void pair_early(const mt* __restrict__ Tf, const Task
             yp = y1; zp = z1; pa += 2; pb -= 2; qb -= 2;
         }
         { const mt x0 = pa[0], y0 = pb[0], z0 = qb[0]; acc_term(a1, x0, yp); acc_term(b1, x0, zp); acc_term(a0, x0, y0); acc_term(b0, x0, z0); }
-#endif
         const mt x0e = Tf[t0.offa0()];
         acc_term(a0, x0e, Tf[t0.offB() + J]); acc_term(b0, x0e, Tf[t1.offB() + J]);
     }
@@ -1261,10 +1217,12 @@ __device__ inline LaneC make_lanec(int tid) {
         } else if (wq == 1 && lane < N * D) { e = lane; ci = e / D; ccc = e % D; }
         if (e >= 0) {
             const int i = ci, cc = ccc;
-            int c0 = L::NB + (i == 0 ? 0 : (3 * i - 1) * D) + cc * ((i == 0 || i == N - 1) ? 2 : 3);
-            cs0 = c0++;
-            if (i > 0)     cs1 = c0++;
-            if (i < N - 1) cs2 = c0;
+            if (!SINGLES) {
+                int c0 = L::NB + (i == 0 ? 0 : (3 * i - 1) * D) + cc * ((i == 0 || i == N - 1) ? 2 : 3);
+                cs0 = c0++;
+                if (i > 0)     cs1 = c0++;
+                if (i < N - 1) cs2 = c0;
+            }
             rowV = L::PV(i, cc) * KMAX; rowU = L::PU(i, cc) * KMAX;
             ccomb = 1;
         }
@@ -1313,11 +1271,11 @@ __device__ __noinline__ void table_loop(FrontSmem<N>& S) {
         lc.cs = w3.x; lc.ap = w3.y; lc.rvu = w3.z; lc.rz = w3.w;
     }
     const int p = S.cfg.p;
-    constexpr int D = 2 * N, GS = TLC<N>::GS;
+    constexpr int GS = TLC<N>::GS;
     constexpr int CROUNDS = PhaseCheck<N>::CROUNDS;
     constexpr bool SINGLES = TLC<N>::SINGLES;
     constexpr int HC = TLC<N>::HC;
-    const int tid = threadIdx.x ^ S.vswap, wq = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x ^ S.vswap, wq = tid >> 5;
     mt (*T)[KMAX] = S.T;
     const mt* const Tf = &T[0][0];
 #define cs0 lq.cs0()
@@ -1359,6 +1317,7 @@ __device__ __noinline__ void table_loop(FrontSmem<N>& S) {
             }
             lq.cs = opaqueu(lq.cs); lq.ap = opaqueu(lq.ap); lq.rvu = opaqueu(lq.rvu); lq.rz = opaqueu(lq.rz);
             const TaskR tA = lq.tA, tB = lq.tB, tC = lq.tC, tD = lq.tD;
+            (void)tB; (void)tC; (void)tD;                         // pairs only
             // the lanes that own an entry (i, cc) of Psi: scratch sums of order kc -> Pv[kc+1];  Pu[kc+2] = Pv[kc+1]/(kc+2)   (Pu[1] = Pv[0] comes with the order-0 data)
             auto combine_c = [&]() {
                 if (ccomb) {
@@ -1396,6 +1355,7 @@ __device__ __noinline__ void table_loop(FrontSmem<N>& S) {
                 __syncwarp();
                 PROF(8);
                 TRC(300 + J);
+                ival f0 = pt(0.0), f1 = pt(0.0);
                 if (mrole >= 0) {                                 // M/H lanes: one (mid,t) dot product per order: parameter * g (or q), three slots
                     const mt* const pmt = &S.pm.B[0];             // B | B3 | B6 | Cm | Cp | C2m | C2p | C2, N entries each
                     const mt p0 = pmt[ap0], p1 = pmt[ap1], p2 = pmt[ap2];
@@ -1412,19 +1372,10 @@ __device__ __noinline__ void table_loop(FrontSmem<N>& S) {
                 }
                 __syncwarp();
                 TRC(400 + J);
-#if CCP_LATE_PRELOAD
-                LatePre lp;
-                if (FAST && kind >= 1) lp = late_preload(Tf, tA, J);      // operands of the late terms that do not depend on this stage
-                else { lp.a0 = lp.b0 = lp.b1 = lp.bJ1 = ptm(0.0); }
-#define LATE_TERMS(acc0, acc1) do { if (FAST) pass_late_pre(Tf, tA, J, lp, acc0, acc1); else pass_late<FAST>(Tf, tA, J, two, acc0, acc1); } while (0)
-#else
-#define LATE_TERMS(acc0, acc1) pass_late<FAST>(Tf, tA, J, two, acc0, acc1)
-#endif
                 bar_pair();                                       // Md, Mo of orders J, J+1 are in the tables
                 TRC(500 + J);
-                ival f0 = pt(0.0), f1 = pt(0.0);
                 if (kind == 1 || (SINGLES && HC > 0 && kind == 2)) {      // B lanes and hosted C lanes: the same late terms in one instruction stream
-                    LATE_TERMS(s0, s1);
+                    pass_late<FAST>(Tf, tA, J, two, s0, s1);
                     f0 = acc_finish(s0); f1 = acc_finish(s1);
                 }
                 if (SINGLES && HC > 0) {
@@ -1454,7 +1405,6 @@ __device__ __noinline__ void table_loop(FrontSmem<N>& S) {
                     (three ? &T[0][rowU + J + 3] : dummy)[0] = u3; (three ? &T[0][rowZ + J + 3] : dummy)[0] = z3;
                 }
                 __syncwarp();
-#undef LATE_TERMS
                 PROF(9);
             } else {
                 TRC(700 + J);
@@ -1465,18 +1415,10 @@ __device__ __noinline__ void table_loop(FrontSmem<N>& S) {
                     acc4 s0 = acc_zero(), s1 = acc_zero();        // defined on every path (see the phi warp)
                     if (r0) pass_early<FAST>(Tf, tA, J, s0, s1);
                     TRC(400 + J);
-#if CCP_LATE_PRELOAD
-                    LatePre lp;
-                    if (FAST && r0) lp = late_preload(Tf, tA, J);
-                    else { lp.a0 = lp.b0 = lp.b1 = lp.bJ1 = ptm(0.0); }
-#endif
                     bar_pair();
                     TRC(500 + J);
                     ival f0 = pt(0.0), f1 = pt(0.0);
                     if (r0) {
-#if CCP_LATE_PRELOAD
-                        if (FAST) pass_late_pre(Tf, tA, J, lp, s0, s1); else
-#endif
                         pass_late<FAST>(Tf, tA, J, two, s0, s1);
                         f0 = acc_finish(s0); f1 = acc_finish(s1);
                     }
