@@ -13,6 +13,9 @@
 #include <cuda/std/type_traits>
 #include "../../include/ccp.h"
 
+#ifndef CCP_STAGE0
+#define CCP_STAGE0 2            // 2: the first stage (J = 0) has its own compact instantiation; 0: it runs through the general one
+#endif
 #ifndef CCP_SINGLES
 #define CCP_SINGLES 1           // 1: one variational product per lane, two columns of Psi hosted by the idle lanes of the phi warp (n <= 3)
 #endif
@@ -518,11 +521,12 @@ __device__ __forceinline__ TaskR make_taskr(const Task& t) {
 // a(0), b(0) live at their own offsets (w0 = u0 - 1/2 and z0 = 1 - u0 differ from u only in order 0).
 // pass_early: everything that does not involve a[J], a[J+1] (for the products H*w and M*Psi^u these are the coefficients the stage is
 // waiting for) and precedes them in the summation order: 2 LDS.128 + 8 DFMA per term, 8 independent FMA chains.
-// FAST = the stage is known to have J >= 2 and a second order (every stage of an even-order run but the first): no branches, so that
+// MODE 1 ("FAST") = the stage is known to have J >= 2 and a second order, MODE 2 = J == 0 and a second order (every stage of an even-order
+// run is one of the two; MODE 0 = anything, decided at run time): no branches, so that
 // the two orders' dependent chains end up in one basic block and the scheduler interleaves them (a warp issues in order).
-template <bool FAST>
+template <int MODE>
 __device__ __forceinline__ void pass_early(const mt* __restrict__ Tf, const TaskR& t, int J, acc4& s0, acc4& s1) {
-    if (FAST || J >= 2) {
+    if (MODE == 1 || (MODE == 0 && J >= 2)) {
         const mt* pa = Tf + t.offA() + 1;                        // a[l]
         const mt* pb = Tf + t.offB() + J - 1;                    // b[J-l]
         mt yp = pb[1];                                           // b[J+1-l]: the only operand carried from term to term
@@ -538,27 +542,27 @@ __device__ __forceinline__ void pass_early(const mt* __restrict__ Tf, const Task
     }
 }
 // pass_late: the remaining terms, in order.  two = the stage has a second order.
-template <bool FAST>
+template <int MODE>
 __device__ __forceinline__ void pass_late(const mt* __restrict__ Tf, const TaskR& t, int J, bool two, acc4& s0, acc4& s1) {
     const mt a0 = Tf[t.offa0()], b0 = Tf[t.offb0()];
-    if (FAST || J >= 2) {
+    if (MODE == 1 || (MODE == 0 && J >= 2)) {
         const mt aJ = Tf[t.offA() + J];
         acc_term(s0, aJ, b0);
-        if (FAST || two) {
+        if (MODE == 1 || two) {
             acc_term(s1, aJ, Tf[t.offB() + 1]);
             acc_term(s1, a0, Tf[t.offB() + J + 1]);
             acc_term(s1, Tf[t.offA() + J + 1], b0);
         }
     } else {
         acc_term(s0, a0, b0);
-        if (two) { acc_term(s1, a0, Tf[t.offB() + 1]); acc_term(s1, Tf[t.offA() + 1], b0); }
+        if (MODE == 2 || two) { acc_term(s1, a0, Tf[t.offB() + 1]); acc_term(s1, Tf[t.offA() + 1], b0); }
     }
 }
 // Two tasks that SHARE their first operand series (Psi warp: one M-series times two columns of Psi): 3 LDS.128 + 16 DFMA per term.
-template <bool FAST>
+template <int MODE>
 __device__ __forceinline__ void pair_early(const mt* __restrict__ Tf, const TaskR& t0, const TaskR& t1, int J,
                                            acc4& a0, acc4& a1, acc4& b0, acc4& b1) {
-    if (FAST || J >= 2) {
+    if (MODE == 1 || (MODE == 0 && J >= 2)) {
         const mt* pa = Tf + t0.offA() + 1; const mt* pb = Tf + t0.offB() + J - 1; const mt* qb = Tf + t1.offB() + J - 1;
         mt yp = pb[1], zp = qb[1];
         int l = 1;
@@ -574,14 +578,14 @@ __device__ __forceinline__ void pair_early(const mt* __restrict__ Tf, const Task
         acc_term(a0, x0e, Tf[t0.offB() + J]); acc_term(b0, x0e, Tf[t1.offB() + J]);
     }
 }
-template <bool FAST>
+template <int MODE>
 __device__ __forceinline__ void pair_late(const mt* __restrict__ Tf, const TaskR& t0, const TaskR& t1, int J, bool two,
                                           acc4& a0, acc4& a1, acc4& b0, acc4& b1) {
     const mt x0 = Tf[t0.offa0()], y0 = Tf[t0.offb0()], z0 = Tf[t1.offb0()];
-    if (FAST || J >= 2) {
+    if (MODE == 1 || (MODE == 0 && J >= 2)) {
         const mt xJ = Tf[t0.offA() + J];
         acc_term(a0, xJ, y0); acc_term(b0, xJ, z0);
-        if (FAST || two) {
+        if (MODE == 1 || two) {
             acc_term(a1, xJ, Tf[t0.offB() + 1]);     acc_term(b1, xJ, Tf[t1.offB() + 1]);
             acc_term(a1, x0, Tf[t0.offB() + J + 1]); acc_term(b1, x0, Tf[t1.offB() + J + 1]);
             const mt xJ1 = Tf[t0.offA() + J + 1];
@@ -589,7 +593,7 @@ __device__ __forceinline__ void pair_late(const mt* __restrict__ Tf, const TaskR
         }
     } else {
         acc_term(a0, x0, y0); acc_term(b0, x0, z0);
-        if (two) {
+        if (MODE == 2 || two) {
             acc_term(a1, x0, Tf[t0.offB() + 1]); acc_term(b1, x0, Tf[t1.offB() + 1]);
             const mt x1 = Tf[t0.offA() + 1];
             acc_term(a1, x1, y0); acc_term(b1, x1, z0);
@@ -1303,8 +1307,8 @@ __device__ __noinline__ void table_loop(FrontSmem<N>& S) {
         const mt* const inv = reinterpret_cast<const mt*>(scr1) + FrontSmem<N>::INV_OFF;   // (RU(1/k), RU(RU(1/k)(1 + 2^-50))), refilled every step (Jc, Kc, J are dead here)
         static_assert(FrontSmem<N>::INV_OFF >= GS + 2 * N, "second scratch set + dummy slot, then the reciprocal table");
         auto stage = [&](auto fast_tag, const int J) {
-            constexpr bool FAST = decltype(fast_tag)::value;
-            const bool two = FAST || (J + 1 < p);                 // uniform: the stage has a second order
+            constexpr int MODE = decltype(fast_tag)::value;     // 1: J >= 2 and two orders, 2: J == 0 and two orders, 0: decided at run time
+            const bool two = MODE != 0 || (J + 1 < p);            // uniform: the stage has a second order
             const bool three = J + 3 <= p;                        // u, z, Pu of order J+3 exist
             // the packed lane constants are laundered once per stage: everything derived from them (table addresses, scratch slots) is
             // recomputed here with a few ALU operations instead of being hoisted out of the stage loop into registers that spill
@@ -1344,10 +1348,10 @@ __device__ __noinline__ void table_loop(FrontSmem<N>& S) {
                 const int kind = tA.kind();
                 acc4 s0, s1;
                 s0 = acc_zero(); s1 = acc_zero();                 // defined on every path (lanes without a task keep the zeros): accumulators that are only
-                if (kind >= 0) pass_early<FAST>(Tf, tA, J, s0, s1);      // defined inside a divergent branch get spilled across the barrier below
+                if (kind >= 0) pass_early<MODE>(Tf, tA, J, s0, s1);      // defined inside a divergent branch get spilled across the barrier below
                 if (kind == 0) {
                     acc4 t0 = s0, t1 = s1;                        // A lanes: g, q of both orders -> scratch (they only travel to the M/H lanes)
-                    pass_late<FAST>(Tf, tA, J, two, t0, t1);
+                    pass_late<MODE>(Tf, tA, J, two, t0, t1);
                     const mt g0 = iv2mt(acc_finish(t0)), g1 = iv2mt(acc_finish(t1));
                     reinterpret_cast<mt*>(scr0)[gslot] = g0;
                     (two ? reinterpret_cast<mt*>(scr1) + gslot : dummy)[0] = g1;
@@ -1366,7 +1370,7 @@ __device__ __noinline__ void table_loop(FrontSmem<N>& S) {
                     acc_term(c0, p2, gq0[cs2]); acc_term(c1, p2, gq1[cs2]);
                     ival d0 = acc_finish(c0), d1 = acc_finish(c1);
                     if (mscale) { d0 = ineg(d0); d1 = ineg(d1); }
-                    if (!FAST && J == 0 && mcst) d0 = iadd(S.pm.halfB[mrole], d0);      // Md_i[0] = b_i/2 - (...)
+                    if ((MODE == 2 || (MODE == 0 && J == 0)) && mcst) d0 = iadd(S.pm.halfB[mrole], d0);      // Md_i[0] = b_i/2 - (...)
                     T[0][rowV + J] = iv2mt(d0);
                     (two ? &T[0][rowV + J + 1] : dummy)[0] = iv2mt(d1);
                 }
@@ -1375,7 +1379,7 @@ __device__ __noinline__ void table_loop(FrontSmem<N>& S) {
                 bar_pair();                                       // Md, Mo of orders J, J+1 are in the tables
                 TRC(500 + J);
                 if (kind == 1 || (SINGLES && HC > 0 && kind == 2)) {      // B lanes and hosted C lanes: the same late terms in one instruction stream
-                    pass_late<FAST>(Tf, tA, J, two, s0, s1);
+                    pass_late<MODE>(Tf, tA, J, two, s0, s1);
                     f0 = acc_finish(s0); f1 = acc_finish(s1);
                 }
                 if (SINGLES && HC > 0) {
@@ -1413,13 +1417,13 @@ __device__ __noinline__ void table_loop(FrontSmem<N>& S) {
                     // one product per lane: the single-task pass of the phi warp
                     const bool r0 = tA.kind() == 2;
                     acc4 s0 = acc_zero(), s1 = acc_zero();        // defined on every path (see the phi warp)
-                    if (r0) pass_early<FAST>(Tf, tA, J, s0, s1);
+                    if (r0) pass_early<MODE>(Tf, tA, J, s0, s1);
                     TRC(400 + J);
                     bar_pair();
                     TRC(500 + J);
                     ival f0 = pt(0.0), f1 = pt(0.0);
                     if (r0) {
-                        pass_late<FAST>(Tf, tA, J, two, s0, s1);
+                        pass_late<MODE>(Tf, tA, J, two, s0, s1);
                         f0 = acc_finish(s0); f1 = acc_finish(s1);
                     }
                     TRC(800 + J);
@@ -1441,19 +1445,19 @@ __device__ __noinline__ void table_loop(FrontSmem<N>& S) {
                 // accumulators that live across the barrier are defined unconditionally
                 ival* const dmy = reinterpret_cast<ival*>(dummy);
                 a0 = acc_zero(); a1 = acc_zero(); b0 = acc_zero(); b1 = acc_zero(); c0 = acc_zero(); c1 = acc_zero(); d0 = acc_zero(); d1 = acc_zero();
-                if (r0) pair_early<FAST>(Tf, tA, tB, J, a0, a1, b0, b1);
-                if (r1) pair_early<FAST>(Tf, tC, tD, J, c0, c1, d0, d1);
+                if (r0) pair_early<MODE>(Tf, tA, tB, J, a0, a1, b0, b1);
+                if (r1) pair_early<MODE>(Tf, tC, tD, J, c0, c1, d0, d1);
                 TRC(400 + J);
                 bar_pair();
                 TRC(500 + J);
                 if (r0) {
-                    pair_late<FAST>(Tf, tA, tB, J, two, a0, a1, b0, b1);
+                    pair_late<MODE>(Tf, tA, tB, J, two, a0, a1, b0, b1);
                     const ival fa0 = acc_finish(a0), fb0 = acc_finish(b0), fa1 = acc_finish(a1), fb1 = acc_finish(b1);
                     (r0 ? scr0 + tA.out() : dmy)[0] = fa0; (r0 ? scr0 + tB.out() : dmy)[0] = fb0;
                     (r0 ? scr1 + tA.out() : dmy)[0] = fa1; (r0 ? scr1 + tB.out() : dmy)[0] = fb1;      // scr1 sums of a missing order are never used
                 }
                 if (r1) {
-                    pair_late<FAST>(Tf, tC, tD, J, two, c0, c1, d0, d1);
+                    pair_late<MODE>(Tf, tC, tD, J, two, c0, c1, d0, d1);
                     const ival fc0 = acc_finish(c0), fd0 = acc_finish(d0), fc1 = acc_finish(c1), fd1 = acc_finish(d1);
                     (r1 ? scr0 + tC.out() : dmy)[0] = fc0; (r1 ? scr0 + tD.out() : dmy)[0] = fd0;
                     (r1 ? scr1 + tC.out() : dmy)[0] = fc1; (r1 ? scr1 + tD.out() : dmy)[0] = fd1;
@@ -1467,8 +1471,8 @@ __device__ __noinline__ void table_loop(FrontSmem<N>& S) {
         };
 
         for (int J = 0; J < p; J += 2) {
-            if (J >= 2 && J + 1 < p) stage(cuda::std::true_type{}, J);
-            else stage(cuda::std::false_type{}, J);
+            if (J + 1 < p) { if (J >= 2) stage(cuda::std::integral_constant<int, 1>{}, J); else stage(cuda::std::integral_constant<int, CCP_STAGE0>{}, 0); }
+            else stage(cuda::std::integral_constant<int, 0>{}, J);
         }
 #undef cs0
 #undef cs1
