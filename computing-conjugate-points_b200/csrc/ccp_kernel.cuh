@@ -1800,6 +1800,9 @@ __device__ __noinline__ int step_body(FrontSmem<N>& S, const int s, const unsign
                 ival a = pt(S.x[nxt][tid]);                       // nxt: the set after the update
                 for (int j = 0; j < D; j++) ipfma(a, S.r0[j], S.C[nxt][tid][j]);          // fused: one rounding per bound and term
                 gres->last_frame[tid * ld + N + 1] = toc(iadd(a, S.r[nxt][tid]));
+                // flow mode: image of the CENTRE of the set (rho = 0 in x + C rho + r, valid for every rho in r0 pointwise): with flow_P it gives
+                // the image of any sub-box of Uxy by the mean-value form (host/ccp_bvp.hpp: G at the point from the integration over the box)
+                if (g == 0) gres->last_frame[tid * ld + N] = toc(iadd(pt(S.x[nxt][tid]), S.r[nxt][tid]));
             }
         }
     }

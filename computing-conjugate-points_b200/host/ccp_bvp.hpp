@@ -20,6 +20,8 @@
 #include "ccp_frame_det.hpp"
 #include <algorithm>
 #include <cmath>
+#include <mutex>
+#include <string>
 #include <thread>
 
 namespace ccp_host {
@@ -79,6 +81,7 @@ class boundaryValueProblem {
         : n_(n), params_(params), order_(order), step_(step_size), finest_(finest_step < step_size ? step_size : finest_step) {
         if (n < 2 || n > CCP_MAX_N) throw std::invalid_argument("n out of range");
     }
+    void share_integrations(bool on) { share_ = on; }     // Krawczyk phase: point image from the integration over the box (default on)
     int launches() const { return launches_; }            // launches of validated integrations so far (all rungs)
     double kernel_ms() const { return kernel_ms_; }       // device time of those launches (slowest device per launch)
     // enclosure of the time-T image of the set (Gxy)
@@ -86,7 +89,7 @@ class boundaryValueProblem {
     // enclosure of [D Phi_T] * A_i over the set (DGxy before the factor DW)
     IMatrix DGxyA(const FlowSet& s, double T) { return run({s}, {T})[0].deriv_A; }
 
-    struct Out { int status; IVector image; IMatrix deriv_A; };
+    struct Out { int status; IVector image, centre; IMatrix deriv_A; };      // centre: image of p_i alone (rho = 0), see ccp.h last_frame column n
     // all integrations of a Newton step (or of a whole sweep) in ONE launch
     std::vector<Out> run(const std::vector<FlowSet>& sets, const std::vector<double>& T) {
         const int D = 2 * n_;
@@ -107,8 +110,11 @@ class boundaryValueProblem {
                 for (int j = 0; j < D; j++) e.A_u[i * CCP_MAX_DIM + j] = sg * s.A_i[i][j];
             }
         });
-        if (ccp_frame_count_batch_multi(d.data(), d.size(), r.data()) != 0) throw std::runtime_error(std::string("ccp: ") + ccp_last_error());
-        launches_++; kernel_ms_ += ccp_last_kernel_ms();
+        {
+            std::lock_guard<std::mutex> lk(dev_mu_);
+            if (ccp_frame_count_batch_multi(d.data(), d.size(), r.data()) != 0) throw std::runtime_error(std::string("ccp: ") + ccp_last_error());
+            launches_++; kernel_ms_ += ccp_last_kernel_ms();
+        }
         // step ladder: integrations whose a-priori enclosure failed with the coarse step are re-run with the next finer one
         for (int st = step_ + 1; st <= finest_; st++) {
             std::vector<size_t> redo;
@@ -116,19 +122,23 @@ class boundaryValueProblem {
             if (redo.empty()) break;
             std::vector<ccp_front_desc> d2(redo.size()); std::vector<ccp_front_result> r2(redo.size());
             for (size_t k = 0; k < redo.size(); k++) { d2[k] = d[redo[k]]; d2[k].step_log2 = st; }
-            if (ccp_frame_count_batch_multi(d2.data(), d2.size(), r2.data()) != 0) throw std::runtime_error(std::string("ccp: ") + ccp_last_error());
-            launches_++; kernel_ms_ += ccp_last_kernel_ms();
+            {
+                std::lock_guard<std::mutex> lk(dev_mu_);
+                if (ccp_frame_count_batch_multi(d2.data(), d2.size(), r2.data()) != 0) throw std::runtime_error(std::string("ccp: ") + ccp_last_error());
+                launches_++; kernel_ms_ += ccp_last_kernel_ms();
+            }
             for (size_t k = 0; k < redo.size(); k++) r[redo[k]] = r2[k];
         }
         std::vector<Out> out(sets.size());
         parallel_for(sets.size(), [&](size_t q) {
             Out& o = out[q];
             o.status = r[q].status;
-            o.image.resize(D); o.deriv_A.assign(D, IVector(D));
+            o.image.resize(D); o.centre.resize(D); o.deriv_A.assign(D, IVector(D));
             for (int i = 0; i < D; i++) {
                 const bool flip = sets[q].stable && i >= n_;
                 auto m = [&](const ccp_interval& a) { return flip ? interval(-a.hi, -a.lo) : from_c(a); };
                 o.image[i] = m(r[q].last_frame[i * (CCP_MAX_N + 2) + n_ + 1]);
+                o.centre[i] = m(r[q].last_frame[i * (CCP_MAX_N + 2) + n_]);
                 for (int j = 0; j < D; j++) o.deriv_A[i][j] = m(r[q].flow_P[i * CCP_MAX_DIM + j]);
             }
         });
@@ -178,30 +188,75 @@ class boundaryValueProblem {
     // boundaryValueProblem::NewtonStep (boundaryValueProblem.cpp:237-317) for many fronts (a parameter sweep): the image of
     // XY_pt + XY_nbd under the interval Krawczyk operator of G(x,y) = Phi_T(x) - Phi_{-T}(y) (last row: |x|^2 - r_u^2).
     // The validated integrations of every front -- 4 * in.size(), 2 * in.size() while XY_nbd = 0 -- are ONE launch (per rung of the step ladder).
+    // Large batches are cut into chunks that run as concurrent host pipelines (marshalling -> launch -> Krawczyk algebra): the engine
+    // serialises the launches, so the host algebra of one chunk overlaps the integrations of the next.  A chunk keeps >= ~1,000
+    // integrations (one wave of the front kernel), otherwise the launches themselves would get slower.  pipeline_chunks(1) = off.
+    void pipeline_chunks(int k, size_t min_fronts = 512) { chunks_ = k < 1 ? 1 : k; chunk_min_ = min_fronts < 1 ? 1 : min_fronts; }
     std::vector<StepOut> NewtonStepBatch(const std::vector<StepIn>& in) {
+        size_t K = std::min<size_t>((size_t)chunks_, in.size() / chunk_min_);
+        if (K <= 1) return NewtonStepChunk(in.data(), in.size());
+        std::vector<std::vector<StepOut>> part(K);
+        std::vector<std::thread> th;
+        std::vector<std::string> err(K);
+        const size_t per = (in.size() + K - 1) / K;
+        for (size_t c = 0; c < K; c++) {
+            const size_t lo = c * per, hi = std::min(in.size(), lo + per);
+            th.emplace_back([&, c, lo, hi] { try { part[c] = NewtonStepChunk(in.data() + lo, hi - lo); } catch (const std::exception& e) { err[c] = e.what(); if (err[c].empty()) err[c] = "error"; } });
+        }
+        for (auto& t : th) t.join();
+        for (size_t c = 0; c < K; c++) if (!err[c].empty()) throw std::runtime_error(err[c]);
+        std::vector<StepOut> res; res.reserve(in.size());
+        for (size_t c = 0; c < K; c++) for (auto& r : part[c]) res.push_back(std::move(r));
+        return res;
+    }
+    std::vector<StepOut> NewtonStepChunk(const StepIn* inp, size_t in_size) {
+        struct View { const StepIn* p; size_t n; size_t size() const { return n; } const StepIn& operator[](size_t i) const { return p[i]; } } in{inp, in_size};
         const int n = n_, D = 2 * n;
         const IVector zero(n, interval(0.0));
         // The operator needs G at the POINT (C^0 images of XY_pt, sets 0 and 1) and DG over the BOX (C^1 maps of XY_pt + XY_nbd, sets 2
         // and 3).  In the Newton phase of the driver (heteroclinic.cpp:186-191: 20 steps with XY_nbd = 0) box and point coincide, and
         // since one integration delivers image and derivative alike only two of the four are launched.
+        // Krawczyk phase (XY_nbd != 0): the point set p_i + A_i U_pt and the box set p_i + A_i U_box share p_i, and U_pt is a sub-box of
+        // U_box (the neighbourhood and the cone error +-L|x| both only grow with XY_nbd).  The integration over the box returns the image of
+        // p_i alone (Out::centre) and [D Phi_T(box set)] A_i (Out::deriv_A), hence by the mean-value form along the segment p_i .. p_i + A_i rho
+        //     Phi_T(p_i + A_i rho)  in  centre + deriv_A rho      for every rho in U_pt,
+        // a valid enclosure of the point image G(x) -- the same two integrations per front as in the Newton phase instead of four
+        // (share_integrations(false) restores the reference's four; a front whose sets do not nest falls back to four on its own).
         std::vector<size_t> slot(4 * in.size()), first(in.size() + 1, 0);
-        std::vector<char> thin(in.size(), 1);
-        for (size_t fi = 0; fi < in.size(); fi++) {
-            for (const interval& e : in[fi].XY_nbd) thin[fi] = thin[fi] && e.lo == 0.0 && e.hi == 0.0;
-            first[fi + 1] = first[fi] + (thin[fi] ? 2 : 4);
-        }
-        std::vector<FlowSet> sets(first[in.size()]); std::vector<double> times(first[in.size()]);
+        std::vector<char> thin(in.size(), 1), shared(in.size(), 0);
+        std::vector<FlowSet> four(4 * in.size());
         parallel_for(in.size(), [&](size_t fi) {
             const StepIn& q = in[fi];
+            for (const interval& e : q.XY_nbd) thin[fi] = thin[fi] && e.lo == 0.0 && e.hi == 0.0;
             IVector X_pt(q.XY_pt.begin(), q.XY_pt.begin() + n), Y_pt(q.XY_pt.begin() + n, q.XY_pt.end());
             IVector X_nbd(q.XY_nbd.begin(), q.XY_nbd.begin() + n), Y_nbd(q.XY_nbd.begin() + n, q.XY_nbd.end());
-            const int nk = thin[fi] ? 2 : 4;
+            bool nest = share_ && !thin[fi];
             for (int k = 0; k < 4; k++) {
-                if (k >= nk) { slot[4 * fi + k] = slot[4 * fi + k - 2]; continue; }
+                if (thin[fi] && k >= 2) continue;
                 FlowSet fs = getPointNbd(k % 2 ? q.stable : q.unstable, k % 2 ? Y_pt : X_pt, k < 2 ? zero : (k % 2 ? Y_nbd : X_nbd));
                 fs.params = q.params;
-                slot[4 * fi + k] = first[fi] + k; sets[first[fi] + k] = std::move(fs); times[first[fi] + k] = q.T;
+                four[4 * fi + k] = std::move(fs);
             }
+            for (int k = 0; k < 2 && nest; k++) {
+                const FlowSet &pt = four[4 * fi + k], &bx = four[4 * fi + 2 + k];
+                for (int i = 0; i < D && nest; i++)
+                    nest = pt.p_i[i].lo == bx.p_i[i].lo && pt.p_i[i].hi == bx.p_i[i].hi && bx.Uxy[i].lo <= pt.Uxy[i].lo && pt.Uxy[i].hi <= bx.Uxy[i].hi &&
+                           bx.Uxy[i].lo <= 0.0 && 0.0 <= bx.Uxy[i].hi;
+            }
+            shared[fi] = nest ? 1 : 0;
+        });
+        for (size_t fi = 0; fi < in.size(); fi++) first[fi + 1] = first[fi] + ((thin[fi] || shared[fi]) ? 2 : 4);
+        std::vector<FlowSet> sets(first[in.size()]); std::vector<double> times(first[in.size()]);
+        for (size_t fi = 0; fi < in.size(); fi++) {
+            if (thin[fi]) for (int k = 0; k < 4; k++) slot[4 * fi + k] = first[fi] + k % 2;
+            else if (shared[fi]) for (int k = 0; k < 4; k++) slot[4 * fi + k] = first[fi] + k % 2;       // the box sets only
+            else for (int k = 0; k < 4; k++) slot[4 * fi + k] = first[fi] + k;
+            const int nk = (thin[fi] || shared[fi]) ? 2 : 4;
+            for (int k = 0; k < nk; k++) times[first[fi] + k] = in[fi].T;
+        }
+        parallel_for(in.size(), [&](size_t fi) {                     // the sets that are launched move out of `four`; the point sets of shared fronts stay (their Uxy is U_pt)
+            const int nk = (thin[fi] || shared[fi]) ? 2 : 4;
+            for (int k = 0; k < nk; k++) sets[first[fi] + k] = std::move(four[4 * fi + (shared[fi] ? 2 + k : k)]);
         });
         const std::vector<Out> all = run(sets, times);
         std::vector<StepOut> res(in.size());
@@ -212,7 +267,18 @@ class boundaryValueProblem {
             bool okflow = true; for (int k = 0; k < 4; k++) okflow = okflow && o[k].status == CCP_OK;
             if (!okflow) return;                                     // like a CAPD exception inside one parameter value: this front fails, the sweep goes on
             IVector X_pt(q.XY_pt.begin(), q.XY_pt.begin() + n), X_nbd(q.XY_nbd.begin(), q.XY_nbd.begin() + n);
-            const IVector& G_x = o[0].image; const IVector& G_y = o[1].image;
+            IVector G_x = o[0].image, G_y = o[1].image;
+            if (shared[f]) {                                         // point images from the integrations over the boxes (mean-value form, see above)
+                for (int s2 = 0; s2 < 2; s2++) {
+                    const Out& ob = o[2 + s2]; const IVector& rho = four[4 * f + s2].Uxy;
+                    IVector& Gp = s2 ? G_y : G_x;
+                    for (int i = 0; i < D; i++) {
+                        interval a = ob.centre[i];
+                        for (int k = 0; k < D; k++) a = ia::add(a, ia::mul(ob.deriv_A[i][k], rho[k]));
+                        Gp[i] = a;
+                    }
+                }
+            }
             IVector G(D);
             for (int i = 0; i < D; i++) G[i] = ia::sub(G_x[i], G_y[i]);
             interval x_radius_sqr(0.0);
@@ -335,7 +401,7 @@ class boundaryValueProblem {
     }
 
   private:
-    int n_; IVector params_; int order_, step_, finest_; int launches_ = 0; double kernel_ms_ = 0.0;
+    int n_; IVector params_; int order_, step_, finest_; int launches_ = 0; double kernel_ms_ = 0.0; bool share_ = true; int chunks_ = 2; size_t chunk_min_ = 512; std::mutex dev_mu_;
 };
 
 } // namespace ccp_host

@@ -93,6 +93,9 @@ typedef struct {
        flow_P = [D Phi_T(set)] * A_u, rows/cols 0..2n-1, row-major ld = CCP_MAX_DIM.  This is `XY_deriv*A_i` of
        boundaryValueProblem::DGxy (boundaryValueProblem.cpp:61-115, C1Rect2Set(p_i,A_i,Uxy)); the C^0 image
        Phi_T(set) of boundaryValueProblem::Gxy (:9-59, C0Rect2Set(p_i,A_i,Uxy)) is last_frame column n+1.
+       With grid = 0 (flow mode) last_frame column n holds the image of the CENTRE of the set, Phi_T(p_i): together with flow_P it
+       encloses the image of every sub-box U' of Uxy (0 in U') by the mean-value form  Phi_T(p_i) + flow_P U'  -- the point
+       image and the box derivative of a Krawczyk step then come from ONE integration (host/ccp_bvp.hpp).
        Does not depend on Eu_err.  The backward maps (STABLE = true, field f_minus) follow from the time-reversal
        symmetry Phi_{-T} = S Phi_T S, S = diag(I,-I) (host/ccp_bvp.hpp).                                        */
     ccp_interval flow_P[CCP_MAX_DIM * CCP_MAX_DIM];

@@ -556,6 +556,7 @@ static inline void run_front(const ccp_front_desc& d, ccp_front_result& res, std
                 ival a(x[i]);
                 for (int j = 0; j < D; j++) ipfma(a, r0[j], C[i][j]);
                 res.last_frame[i * ld + n + 1] = toc(a + r[i]);
+                if (g == 0) res.last_frame[i * ld + n] = toc(ival(x[i]) + r[i]);      // flow mode: image of the centre of the set (rho = 0)
             }
         }
     }

@@ -170,3 +170,27 @@ def test_batch_driver_reference_sweep_on_gpu(pkg):
     r = subprocess.run([exe, "24", "4"], capture_output=True, text=True)          # the reference's own 96-point sweep
     assert r.returncode == 0, r.stdout + r.stderr
     assert "batch == single-front driver on the probed fronts" in r.stdout
+
+
+def test_krawczyk_step_with_shared_integrations_against_oracle_backend(pkg, orc):
+    """host/ccp_bvp.hpp: in the Krawczyk phase the point image G(x) comes from the integration over the box (image of the centre +
+    flow_P * U_pt, mean-value form) -- two validated integrations per front instead of the reference's four
+    (boundaryValueProblem.cpp:237-317).  Against the oracle twins: on the same inputs, step by step, the Krawczyk images of both
+    arrangements intersect, the shared one is at most marginally wider, the verdicts agree."""
+    exe = os.path.join(ROOT, "tests", "cpp", "bvp_share_dry")
+    _build_with_oracle_backend(pkg, "bvp_share.cpp", exe)
+    r = subprocess.run([exe, "3", "2"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "0 disagreements" in r.stdout
+
+
+@pytest.mark.gpu
+def test_krawczyk_step_with_shared_integrations_on_gpu(pkg):
+    exe = os.path.join(ROOT, "tests", "cpp", "bvp_share")
+    cmd = ["g++", "-std=c++17", "-O1", "-o", exe, os.path.join(ROOT, "tests", "cpp", "bvp_share.cpp"),
+           "-L", pkg.PKG_DIR, "-lccp_b200", "-lccp_setup", "-Wl,-rpath," + pkg.PKG_DIR]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe, "24", "4"], capture_output=True, text=True)          # the reference's own 96-point sweep
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "0 disagreements" in r.stdout and "verified 96 (shared) / 96 (four integrations)" in r.stdout
