@@ -46,11 +46,11 @@ __device__ __forceinline__ ival imulk(const ival& a, int k) { return mk(__dmul_r
 __device__ __forceinline__ double mid_ru(const ival& a) { return __dadd_ru(0.5 * a.lo, 0.5 * a.hi); }
 
 __device__ __forceinline__ ival mt2iv(const mt& a) { double r = __dadd_ru(a.t, -fabs(a.m)); return mk(__dadd_rd(a.m, -r), __dadd_ru(a.m, r)); }
-// m = RU(lo/2 + hi/2) is never below the exact midpoint (the halvings are exact, or rounded up for subnormals), hence
+// m = RU(lo/2 + hi/2) is never below the exact midpoint (hi/2 is exact, or rounded up for subnormals; lo/2 enters the FMA unrounded), hence
 // m - lo >= hi - m and r = RU(m - lo) alone bounds both distances: no comparison on the critical chains.  (For normal numbers this is
 // bit-identical to max(RU(hi - m), RU(m - lo)): rounding is monotone.)
 __device__ __forceinline__ mt iv2mt(const ival& a) {
-    mt o; o.m = __dadd_ru(__dmul_ru(0.5, a.lo), __dmul_ru(0.5, a.hi));
+    mt o; o.m = __fma_ru(0.5, a.lo, __dmul_ru(0.5, a.hi));       // one instruction less than RU(RU(lo/2) + RU(hi/2)); the same bits whenever lo/2 is exact (always, but for subnormals)
     const double r = __dadd_ru(o.m, -a.lo);
     o.t = __dadd_ru(fabs(o.m), r);
     return o;

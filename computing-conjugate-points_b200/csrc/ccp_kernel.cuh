@@ -755,32 +755,41 @@ __device__ __noinline__ void second_variation(FrontSmem<N>& S, PostTab<N>& PT, i
         PT.u.x.DD[j][3][m] = iv2mt(idivk_tab(acc_finish(a3), c_invlo, c_invhi, 6));
     }
     __syncthreads();
-    // X2a: product series (w_i d_m)_k, k <= 3, all N x N pairs
-    constexpr int NWD = (D + 1) * 4 * N * N;
-#pragma unroll 1                                                // rolled: the step loop must stay inside the instruction cache
-    for (int t = tid; t < NWD; t += NT) {
-        const int j = t / (4 * N * N), k = (t / (N * N)) % 4, i = (t / N) % N, m = t % N;
-        acc4 a = acc_zero();
-#pragma unroll
-        for (int q = 0; q < 4; q++) if (q <= k) acc_term(a, H.W[q][i], PT.u.x.DD[j][k - q][m]);
-        PT.u.x.WD[j][k][i][m] = iv2mt(acc_finish(a));
+    // X2a: product series (w_i d_m)_k, k <= 3, all N x N pairs.  One thread per (direction j, i, m): the four orders are independent
+    //      chains over the same eight operands (loaded once); same sums in the same order as an item per (j, k, i, m)
+    constexpr int NJM = (D + 1) * N * N;
+    for (int t = tid; t < NJM; t += NT) {
+        const int j = t / (N * N), i = (t / N) % N, m = t % N;
+        const mt w0 = H.W[0][i], w1 = H.W[1][i], w2 = H.W[2][i], w3 = H.W[3][i];
+        const mt e0 = PT.u.x.DD[j][0][m], e1 = PT.u.x.DD[j][1][m], e2 = PT.u.x.DD[j][2][m], e3 = PT.u.x.DD[j][3][m];
+        acc4 a0 = acc_zero(), a1 = acc_zero(), a2 = acc_zero(), a3 = acc_zero();
+        acc_term(a0, w0, e0);
+        acc_term(a1, w0, e1); acc_term(a1, w1, e0);
+        acc_term(a2, w0, e2); acc_term(a2, w1, e1); acc_term(a2, w2, e0);
+        acc_term(a3, w0, e3); acc_term(a3, w1, e2); acc_term(a3, w2, e1); acc_term(a3, w3, e0);
+        PT.u.x.WD[j][0][i][m] = iv2mt(acc_finish(a0)); PT.u.x.WD[j][1][i][m] = iv2mt(acc_finish(a1));
+        PT.u.x.WD[j][2][i][m] = iv2mt(acc_finish(a2)); PT.u.x.WD[j][3][i][m] = iv2mt(acc_finish(a3));
     }
     __syncthreads();
-    // X2b: Taylor coefficients N_k of DM(u)[Psi^u c_j] (dense): three parameter * product-series slots per entry
-#pragma unroll 1
-    for (int t = tid; t < NWD; t += NT) {
-        const int j = t / (4 * N * N), k = (t / (N * N)) % 4, i = (t / N) % N, l = t % N;
+    // X2b: Taylor coefficients N_k of DM(u)[Psi^u c_j] (dense): three parameter * product-series slots per entry; one thread per (j, i, l),
+    //      the four orders share the parameters and the slot indices
+    for (int t = tid; t < NJM; t += NT) {
+        const int j = t / (N * N), i = (t / N) % N, l = t % N;
         // slots: diagonal (i,i): 6 b_i (w_i d_i), 2 c_{i-1} (w_{i-1} d_{i-1}), 2 c_i (w_{i+1} d_{i+1});  off-diagonal e = min(i,l): 2 c_e (w_{e+1} d_e + w_e d_{e+1})
         const int e = i < l ? i : l, e1 = e + 1 < N ? e + 1 : N - 1;
         const int a0 = i == l ? i : e1, b0 = i == l ? i : e;
         const int a1 = i == l ? (i > 0 ? i - 1 : 0) : e, b1 = i == l ? a1 : e1;
         const int a2 = i == l ? (i < N - 1 ? i + 1 : N - 1) : e, b2 = i == l ? a2 : e1;
-        const mt (*WDk)[N] = PT.u.x.WD[j][k];
-        acc4 a = acc_zero();
-        acc_term(a, S.pm.PN[i][l][0], WDk[a0][b0]);
-        acc_term(a, S.pm.PN[i][l][1], WDk[a1][b1]);
-        acc_term(a, S.pm.PN[i][l][2], WDk[a2][b2]);
-        PT.u.x.NN[j][k][i][l] = iv2mt(acc_finish(a));          // NN overlays DD (dead since X2a)
+        const mt p0 = S.pm.PN[i][l][0], p1 = S.pm.PN[i][l][1], p2 = S.pm.PN[i][l][2];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const mt (*WDk)[N] = PT.u.x.WD[j][k];
+            acc4 a = acc_zero();
+            acc_term(a, p0, WDk[a0][b0]);
+            acc_term(a, p1, WDk[a1][b1]);
+            acc_term(a, p2, WDk[a2][b2]);
+            PT.u.x.NN[j][k][i][l] = iv2mt(acc_finish(a));      // NN overlays DD (dead since X2a)
+        }
     }
     __syncthreads();
     // X3: the four n x n blocks of Xi_j(hs) = sum_{k<=4} Xi_k hs^k + remainder, one (j, i, k) entry of each block per item
@@ -1139,7 +1148,7 @@ template <int N> struct TLC {                      // scratch layout of the tabl
     static constexpr int PPC = 3 * N - 2;            // products per column
     static constexpr int HOST0 = MB + 3 * N - 1;     // first hosted lane of the phi warp
     static constexpr int HC = !SINGLES ? 0 : (2 * N - 32 / PPC > 0 ? 2 * N - 32 / PPC : 0);      // hosted columns: those the Psi warp cannot hold (n = 3: 2 of 6)
-    static_assert(!SINGLES || ((2 * N - HC) * PPC <= 32 && HOST0 + HC * PPC <= 32), "singles: one product per lane");
+    static_assert(!SINGLES || ((2 * N - HC) * PPC <= 31 && HOST0 + HC * PPC <= 32), "singles: one product per lane; lane 31 of the Psi warp stays idle (exact zero for entry_sum)");
     static_assert(GS + 2 * N - 1 < 255, "scratch slots fit 8 bits");
 };
 template <int N>
@@ -1218,6 +1227,13 @@ __device__ inline LaneC make_lanec(int tid) {
             if (pl == 0) { e = 0; ci = 0; ccc = c0l; }
             else if (pl >= 2 && (pl - 2) % 3 == 0) { e = 0; ci = 1 + (pl - 2) / 3; ccc = c0l; }
             cpat = ci == 0 ? 0 : (ci == N - 1 ? 2 : 1);
+            if (e >= 0) {
+                // source lanes of the two partner sums (entry_sum): a product a boundary component does not have is read from a lane whose sum is
+                // an exact zero -- lane 31 of the Psi warp (never owns a product), lane 0 of the phi warp (an A lane) -- instead of being selected
+                const int zl = wq == 1 ? 31 : 0;
+                const int sb = cpat == 0 ? zl : lane + 1, sc = cpat == 0 ? lane + 1 : (cpat == 1 ? lane + 2 : zl);
+                rowZ = sb | (sc << 8);                        // combiner lanes have no z rows: the word is free
+            }
         } else if (wq == 1 && lane < N * D) { e = lane; ci = e / D; ccc = e % D; }
         if (e >= 0) {
             const int i = ci, cc = ccc;
@@ -1238,8 +1254,8 @@ __device__ inline LaneC make_lanec(int tid) {
     return c;
 }
 
-__device__ __forceinline__ ival shfl_down_ival(const ival& a, int d) {
-    return mk(__shfl_down_sync(0xffffffffu, a.lo, d), __shfl_down_sync(0xffffffffu, a.hi, d));
+__device__ __forceinline__ ival shfl_ival(const ival& a, int src) {
+    return mk(__shfl_sync(0xffffffffu, a.lo, src), __shfl_sync(0xffffffffu, a.hi, src));
 }
 
 // The lane constants are the same for every front of one n: a table in global memory, filled once per device (lanec_table_kernel, launched
@@ -1338,8 +1354,8 @@ __device__ __noinline__ void table_loop(FrontSmem<N>& S) {
             // singles: the sums of the one or two partner lanes arrive through shuffles (every lane of the warp executes them); the leader of an
             // entry forms (w0 + w1) + w2 with an exact zero for the product a boundary component does not have -- the additions of combine_c
             auto entry_sum = [&](const ival& f) -> ival {
-                const ival t1 = shfl_down_ival(f, 1), t2 = shfl_down_ival(f, 2);
-                const ival b = cpat == 0 ? pt(0.0) : t1, c = cpat == 0 ? t1 : (cpat == 1 ? t2 : pt(0.0));
+                const int sb = rowZ & 31, sc = (rowZ >> 8) & 31;      // make_lanec: partner lanes, or a lane holding an exact zero (B lanes: any lane, their result is not used)
+                const ival b = shfl_ival(f, sb), c = shfl_ival(f, sc);
                 return iadd(iadd(f, b), c);
             };
             if (wq == 0) {

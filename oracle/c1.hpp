@@ -35,7 +35,7 @@ static inline double mid_ru(const ival& a) { return add_ru(0.5 * a.lo, 0.5 * a.h
 // m = RU(lo/2 + hi/2) is never below the exact midpoint, hence m - lo >= hi - m and r = RU(m - lo) bounds both distances
 // (bit-identical to max(RU(hi - m), RU(m - lo)) for normal numbers; see csrc/ccp_interval.cuh)
 static inline mt iv2mt(const ival& a) {
-    mt o; o.m = add_ru(mul_ru(0.5, a.lo), mul_ru(0.5, a.hi));
+    mt o; o.m = fma_ru(0.5, a.lo, mul_ru(0.5, a.hi));            // = RU(lo/2 + hi/2) with lo/2 unrounded: the kernel's instruction sequence
     const double r = sub_ru(o.m, a.lo);
     o.t = add_ru(std::fabs(o.m), r);
     return o;
