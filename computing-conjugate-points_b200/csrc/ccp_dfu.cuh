@@ -11,6 +11,10 @@
 namespace ccp {
 
 constexpr int DFU_NT = 256;
+#ifndef CCP_DFU_MINB
+#define CCP_DFU_MINB 2
+#endif
+constexpr int DFU_MINB = CCP_DFU_MINB;      // resident CTAs per SM the register allocation aims at
 
 __device__ __forceinline__ void dfu_ipfma(ival& a, const ival& x, double p) {
     const double l = p >= 0 ? x.lo : x.hi, h = p >= 0 ? x.hi : x.lo;
@@ -57,7 +61,7 @@ struct DfuSmem {
 // lane j then forms column j of M A[:n,:] and of Ainv Df A and keeps the running hull of its column in registers.  The partial hulls of
 // the groups meet in shared memory at the end (min / max: independent of the order, hence bit-identical to the serial oracle).
 template <int N>
-__global__ void __launch_bounds__(DFU_NT) dfu_kernel(const ccp_dfu_desc* __restrict__ descs, ccp_dfu_result* __restrict__ results, int count) {
+__global__ void __launch_bounds__(DFU_NT, DFU_MINB) dfu_kernel(const ccp_dfu_desc* __restrict__ descs, ccp_dfu_result* __restrict__ results, int count) {
     constexpr int D = 2 * N, G = DfuSmem<N>::G, P = DfuSmem<N>::P;
     extern __shared__ __align__(16) unsigned char dfu_raw[];
     DfuSmem<N>& S = *reinterpret_cast<DfuSmem<N>*>(dfu_raw);

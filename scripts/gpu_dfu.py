@@ -4,6 +4,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import __graft_entry__ as ge
 pkg = ge.load_package(); orc = ge.load_oracle(); abi = pkg.abi; orc.lib(abi)
+if os.environ.get("CCP_LIB"):                      # experiment builds (e.g. libccp_b200_x.so)
+    import ctypes as C
+    pkg._lib = abi.bind(C.CDLL(os.path.join(pkg.PKG_DIR, os.environ["CCP_LIB"])))
 eng = pkg.Engine(0)
 m = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 n, params, N = 3, [1.0, .98, .96, .04, .02], 15
