@@ -46,23 +46,6 @@ inline interval sqr(const interval& a) {
 inline interval sqrt(const interval& a) { return interval(a.lo > 0 ? std::max(0.0, dn(std::sqrt(a.lo))) : 0.0, up(std::sqrt(std::max(a.hi, 0.0)))); }
 }
 
-// The per-front host algebra of a batched step (descriptor marshalling, Krawczyk operator, 6x6 interval products) is independent
-// between fronts: with 1,024 fronts it is longer than the launch itself when run on one host thread, so the loops over fronts are
-// split over the host cores.  Exceptions must not escape f.
-template <class F> inline void parallel_for(size_t n, F f) {
-    const size_t hw = std::max(1u, std::thread::hardware_concurrency());
-    const size_t nt = std::min(hw, n / 16);                 // below 32 fronts a thread costs more than it saves
-    if (nt <= 1) { for (size_t i = 0; i < n; i++) f(i); return; }
-    std::vector<std::thread> th;
-    const size_t chunk = (n + nt - 1) / nt;
-    for (size_t t = 0; t < nt; t++) {
-        const size_t lo = t * chunk, hi = std::min(n, lo + chunk);
-        if (lo >= hi) break;
-        th.emplace_back([=] { for (size_t i = lo; i < hi; i++) f(i); });
-    }
-    for (auto& x : th) x.join();
-}
-
 struct FlowSet {                 // what getPointNbd / (*pF).A hand to C0Rect2Set / C1Rect2Set
     IVector p_i, Uxy;            // 2n each
     DMatrix A_i;                 // 2n x 2n point matrix

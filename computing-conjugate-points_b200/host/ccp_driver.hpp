@@ -12,6 +12,7 @@
 // float shooting of ccp_setup_front.  Return values are the reference's: count >= 0, -1 manifolds / end points, -2 connecting orbit,
 // -3 count failed, -4 L_+, -5 below L_-.
 #pragma once
+#include <chrono>
 #include "ccp_l_plus.hpp"
 #include "../../include/ccp_setup.h"
 
@@ -139,8 +140,13 @@ inline int computeFrontAndConjugatePoints(int dimension, const std::vector<doubl
 // about 65 launches per front.  Per front the operations and results are those of computeFrontAndConjugatePoints above; a front that
 // fails a stage keeps the reference's code for that stage, an exception inside its host algebra gives -10 (or the thrown int) as in
 // SampleParameters' try / catch (heteroclinic.cpp:456-467).
+// wall-clock seconds of the stages of the last computeFrontAndConjugatePointsBatch call (stage name, seconds), for the timing reports
+inline std::vector<std::pair<std::string, double>>& driverStageTimes() { static std::vector<std::pair<std::string, double>> t; return t; }
 inline std::vector<int> computeFrontAndConjugatePointsBatch(int dimension, const std::vector<std::vector<double>>& P, const std::vector<IVector>& PI,
                                                            std::vector<DriverReport>* reports = nullptr) {
+    auto& stage_times = driverStageTimes(); stage_times.clear();
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char* name) { const auto now = std::chrono::steady_clock::now(); stage_times.emplace_back(name, std::chrono::duration<double>(now - t_last).count()); t_last = now; };
     const int n = dimension / 2;
     const size_t m = P.size();
     const int order = 20, manifold_subdivision = 15, newton_steps = 20, grid = 14, stepsize = 5;
@@ -167,6 +173,7 @@ inline std::vector<int> computeFrontAndConjugatePointsBatch(int dimension, const
     ccp_setup_opts o{}; o.xy_nbd = -1; o.cone_L = -1; o.eig_err = -1; o.scale = -1; o.L_minus_percent = -1; o.L_minus_override = -1;
     if (ccp_setup_sweep(n, flat.data(), m, &o, d0.data(), info.data(), 0) != 0) throw std::runtime_error(std::string("ccp: ") + ccp_last_error());
 
+    lap("float preparation (ccp_setup_sweep)");
     const IVector U_flat(n, ia::mul(scale, interval(-1.0, 1.0)));
     for (size_t q = 0; q < m; q++) guarded(q, [&] {
         Front& f = F[q];
@@ -190,7 +197,9 @@ inline std::vector<int> computeFrontAndConjugatePointsBatch(int dimension, const
         const std::vector<char> ok = checkConditionsBatch(ms);
         for (size_t k = 0; k < who.size(); k++) { rep[who[k]].*flag = ok[2 * k] && ok[2 * k + 1]; if (!(rep[who[k]].*flag)) code[who[k]] = -1; }
     };
+    lap("front set-up");
     checkBoth(&DriverReport::conditions_first);
+    lap("manifold conditions, first");
 
     boundaryValueProblem BVP(n, PI.empty() ? IVector(2 * n - 1, interval(0.0)) : PI[0], order);
     {   // FindTime
@@ -213,7 +222,9 @@ inline std::vector<int> computeFrontAndConjugatePointsBatch(int dimension, const
             else { const IVector mid = midVector(out[k].kraw_image); for (int i = 0; i < dimension; i++) f.XY_nbd[i] = ia::sub(out[k].kraw_image[i], mid[i]); f.XY_pt = mid; }
         }
     };
+    lap("FindTime");
     for (int i = 0; i < newton_steps; i++) newtonRound(true);
+    lap("Newton steps");
 
     for (size_t q = 0; q < m; q++) if (alive(q)) guarded(q, [&] {
         Front& f = F[q];
@@ -227,7 +238,9 @@ inline std::vector<int> computeFrontAndConjugatePointsBatch(int dimension, const
         f.U.U_flat_global = f.U_new; f.S.U_flat_global = f.S_new;
         f.XY_nbd.assign(dimension, ia::mul(scale, initial_box));
     });
+    lap("resizing");
     checkBoth(&DriverReport::conditions_resized);
+    lap("manifold conditions, resized");
 
     for (int i = 0; i < newton_steps; i++) newtonRound(false);
     for (size_t q = 0; q < m; q++) if (alive(q)) for (int k = 0; k < dimension; k++) F[q].XY_nbd[k] = ia::mul(F[q].XY_nbd[k], interval(1.5));
@@ -248,8 +261,9 @@ inline std::vector<int> computeFrontAndConjugatePointsBatch(int dimension, const
         if (!inside) code[q] = -1; else if (!f.success) code[q] = -2;
     }
 
+    lap("Krawczyk steps and proof");
     // (ii) eigenfunction error and the L_- test; end points phi(L_+)
-    for (size_t q = 0; q < m; q++) if (alive(q)) guarded(q, [&] {
+    parallel_for(m, [&](size_t q) { if (alive(q)) guarded(q, [&] {        // per-front interval algebra: independent between fronts
         Front& f = F[q];
         f.eig = localManifold_Eig(f.U);
         f.eig.computeEigenError_minus_infty();
@@ -259,7 +273,7 @@ inline std::vector<int> computeFrontAndConjugatePointsBatch(int dimension, const
         f.start = boundaryValueProblem::getPointNbd(f.Mu, X, Xn);
         f.L_minus = interval(ia::mul(ia::mul(interval(2.0), interval(f.T)), interval(L_minus_percent)).hi);
         rep[q].L_minus = f.L_minus;
-    });
+    }); });
     {
         std::vector<FlowSet> sets; std::vector<double> times; std::vector<size_t> who;
         for (size_t q = 0; q < m; q++) if (alive(q)) {
@@ -278,6 +292,7 @@ inline std::vector<int> computeFrontAndConjugatePointsBatch(int dimension, const
             }
         }
     }
+    lap("eigenfunction error, L_- test, end points");
     // manifolds at L_+ for all fronts (rounds of one boundDFU launch), then (iii)-(v): one launch of the hot path
     std::vector<size_t> who;
     for (size_t q = 0; q < m; q++) if (alive(q)) who.push_back(q);
@@ -286,6 +301,7 @@ inline std::vector<int> computeFrontAndConjugatePointsBatch(int dimension, const
     std::vector<char> verified;
     std::vector<localManifold_Eig> big;
     if (!who.empty()) big = constructManifoldsAtLPlusBatch(st, ends, verified);
+    lap("manifolds at L_+");
     std::vector<propagateManifold> fronts; std::vector<interval> Lm; std::vector<int> thrown(who.size(), 0);
     for (size_t k = 0; k < who.size(); k++) {
         const Front& f = F[who[k]];
@@ -300,7 +316,7 @@ inline std::vector<int> computeFrontAndConjugatePointsBatch(int dimension, const
         };
     }
     if (!who.empty()) {
-        const std::vector<int> out = propagateManifold::frameDetBatch(fronts, Lm, grid, ends);
+        const std::vector<int> out = propagateManifold::frameDetBatch(fronts, Lm, grid, ends, /*parallel_hooks=*/true);    // the hooks above only touch slot k
         for (size_t k = 0; k < who.size(); k++) {
             code[who[k]] = thrown[k] != 0 ? thrown[k] : out[k];
             const ccp_front_result& fr = fronts[k].frame().result();
@@ -308,6 +324,7 @@ inline std::vector<int> computeFrontAndConjugatePointsBatch(int dimension, const
             r.zero_count = fr.zero_count; r.failure_count = fr.failure_count; r.first_failure = fr.first_failure; r.series_length = fr.series_length;
         }
     }
+    lap("frame count and L_+ test");
     for (size_t q = 0; q < m; q++) rep[q].result = code[q];
     if (reports) *reports = rep;
     return code;

@@ -15,7 +15,9 @@
 #include <cstdio>
 #include <functional>
 #include <stdexcept>
+#include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace ccp_host {
@@ -31,6 +33,23 @@ struct interval {
 typedef std::vector<interval> IVector;
 typedef std::vector<std::vector<interval>> IMatrix;      // row-major
 typedef std::vector<std::vector<double>> DMatrix;
+
+// The per-front host algebra of a batched stage (descriptor marshalling, Krawczyk operator, 6x6 interval products, the L_+ test) is independent
+// between fronts: with 1,024 fronts it is longer than the launch itself when run on one host thread, so the loops over fronts are
+// split over the host cores.  Exceptions must not escape f.
+template <class F> inline void parallel_for(size_t n, F f) {
+    const size_t hw = std::max(1u, std::thread::hardware_concurrency());
+    const size_t nt = std::min(hw, n / 16);                 // below 32 fronts a thread costs more than it saves
+    if (nt <= 1) { for (size_t i = 0; i < n; i++) f(i); return; }
+    std::vector<std::thread> th;
+    const size_t chunk = (n + nt - 1) / nt;
+    for (size_t t = 0; t < nt; t++) {
+        const size_t lo = t * chunk, hi = std::min(n, lo + chunk);
+        if (lo >= hi) break;
+        th.emplace_back([=] { for (size_t i = lo; i < hi; i++) f(i); });
+    }
+    for (auto& x : th) x.join();
+}
 
 inline ccp_interval to_c(const interval& a) { ccp_interval o; o.lo = a.lo; o.hi = a.hi; return o; }
 inline interval from_c(const ccp_interval& a) { return interval(a.lo, a.hi); }
@@ -132,8 +151,10 @@ class propagateManifold {
     }
 
     // The sweep of SampleParameters in one launch: all fronts go to the GPU together.
+    // `parallel_hooks`: the below-L_- and L_+ hooks of different fronts may run concurrently (they must then only touch per-front state;
+    // the L_+ test is an interval eigen-computation per front and dominates this call for a large sweep)
     static std::vector<int> frameDetBatch(std::vector<propagateManifold>& fronts, const std::vector<interval>& L_minus, int grid,
-                                          const std::vector<IVector>& endPoints) {
+                                          const std::vector<IVector>& endPoints, bool parallel_hooks = false) {
         std::vector<ccp_front_desc> d(fronts.size());
         std::vector<ccp_front_result> r(fronts.size());
         std::vector<int> out(fronts.size(), -10);
@@ -141,10 +162,11 @@ class propagateManifold {
         for (size_t i = 0; i < fronts.size(); i++) { fronts[i].desc_.L_minus = L_minus[i].hi; fronts[i].desc_.grid = grid; d[i] = fronts[i].desc_; }
         // every GPU bound by ccp_init_multi takes part (front f on device f mod n_devices); with ccp_init it is one device
         check(ccp_frame_count_batch_multi(d.data(), d.size(), r.data()));
-        for (size_t i = 0; i < fronts.size(); i++) {
-            if (!fronts[i].below_Lminus()) { out[i] = -5; continue; }
+        auto one = [&](size_t i) {
+            if (!fronts[i].below_Lminus()) { out[i] = -5; return; }
             try { out[i] = fronts[i].finish(r[i], {}, endPoints[i]); } catch (const std::exception&) { out[i] = -10; }
-        }
+        };
+        if (parallel_hooks) parallel_for(fronts.size(), one); else for (size_t i = 0; i < fronts.size(); i++) one(i);
         return out;
     }
     static std::vector<int> frameDetBatchUnchecked(std::vector<propagateManifold>& fronts, const std::vector<interval>& L_minus, int grid) {

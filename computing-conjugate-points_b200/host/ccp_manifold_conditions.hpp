@@ -235,7 +235,7 @@ inline std::vector<char> checkConditionsBatch(const std::vector<localManifold*>&
     std::vector<char> ok(Ms.size());
     if (Ms.empty()) return ok;
     const std::vector<IMatrix> DF = boundDFUBatch(d);
-    for (size_t q = 0; q < Ms.size(); q++) ok[q] = Ms[q]->checkConditionsOn(DF[q], Us[q]) ? 1 : 0;
+    parallel_for(Ms.size(), [&](size_t q) { ok[q] = Ms[q]->checkConditionsOn(DF[q], Us[q]) ? 1 : 0; });      // per-manifold interval algebra (the pointers are distinct objects)
     return ok;
 }
 inline std::vector<char> checkConditionsBatch(std::vector<localManifold>& Ms) {

@@ -39,6 +39,7 @@ int main(int argc, char** argv) {
     for (int q = 0; q < m; q++) { if (code[q] >= 0 && code[q] < 8) hist[code[q]]++; proven += rep[q].proof ? 1 : 0; }
     std::printf("sweep %d x %d: %d fronts, %d connecting orbits proven, counts 0/1/2: %d/%d/%d, failed: %d, %.2f s\n", N_c, N_r, m, proven, hist[0], hist[1], hist[2],
                 m - hist[0] - hist[1] - hist[2], sec);
+    for (const auto& st : driverStageTimes()) std::printf("  stage %-44s %8.3f s\n", st.first.c_str(), st.second);
     for (int q = 0; q < m; q++) std::printf("%s%d", q ? " " : "codes: ", code[q]);
     std::printf("\n");
     int bad = 0;
