@@ -62,6 +62,11 @@ static void hess(const Sys& s, const double* u, double M[MAXN][MAXN]) {
 }
 
 // One Taylor step of phi (2n) and optionally Psi (2n x 2n, row-major ld 2n) of size h (may be < 0).
+// Built for AVX2 too where the host has it (function multi-versioning, resolved at load time).  The AVX2 target has no fused
+// multiply-add, and nothing here may be contracted or re-associated: the descriptors must not depend on the host.
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+__attribute__((target_clones("avx2", "default")))
+#endif
 static void taylor_step(const Sys& s, double* phi, double* Psi, double h) {
     const int n = s.n, D = 2 * n;
     static thread_local double u[ORD + 2][MAXN], v[ORD + 2][MAXN], w[ORD + 2][MAXN], g[ORD + 2][MAXN], q[ORD + 2][MAXN];
@@ -73,21 +78,34 @@ static void taylor_step(const Sys& s, double* phi, double* Psi, double h) {
     }
     for (int k = 0; k <= ORD; k++) {
         for (int i = 0; i < n; i++) w[k][i] = u[k][i] - (k == 0 ? 0.5 : 0.0);
-        for (int i = 0; i < n; i++) {
-            double a = 0; for (int j = 0; j <= k; j++) a += w[j][i] * w[k - j][i];
-            g[k][i] = (k == 0 ? 0.25 : 0.0) - a;
-        }
-        for (int i = 0; i + 1 < n; i++) {
-            double a = 0; for (int j = 0; j <= k; j++) a += w[j][i] * w[k - j][i + 1];
-            q[k][i] = a;
-        }
-        for (int i = 0; i < n; i++) {
-            double sgw = 0; for (int j = 0; j <= k; j++) sgw += g[j][i] * w[k - j][i];
-            double f = -s.b[i] * sgw;
-            if (i > 0)     { double x = 0; for (int j = 0; j <= k; j++) x += g[j][i - 1] * w[k - j][i]; f -= s.c[i - 1] * x; }
-            if (i < n - 1) { double x = 0; for (int j = 0; j <= k; j++) x += g[j][i + 1] * w[k - j][i]; f -= s.c[i] * x; }
-            u[k + 1][i] = v[k][i] / (k + 1);
-            v[k + 1][i] = f / (k + 1);
+        // The Cauchy sums of one order side by side (full MAXN-wide rows; components >= n are never written and only feed sums nobody
+        // reads): every sum sees its terms in the same order as a sum-by-sum loop -- the same bits --, but the chains are independent
+        // of each other instead of one latency-bound chain after the other
+        {
+            double ag[MAXN], aq[MAXN];
+            for (int i = 0; i < MAXN; i++) { ag[i] = 0; aq[i] = 0; }
+            for (int j = 0; j <= k; j++) {
+                const double* wj = w[j]; const double* wr = w[k - j];
+                for (int i = 0; i < MAXN; i++) ag[i] += wj[i] * wr[i];
+                for (int i = 0; i + 1 < MAXN; i++) aq[i] += wj[i] * wr[i + 1];
+            }
+            for (int i = 0; i < n; i++) g[k][i] = (k == 0 ? 0.25 : 0.0) - ag[i];
+            for (int i = 0; i + 1 < n; i++) q[k][i] = aq[i];
+            double sg[MAXN], xm[MAXN], xp[MAXN];
+            for (int i = 0; i < MAXN; i++) { sg[i] = 0; xm[i] = 0; xp[i] = 0; }
+            for (int j = 0; j <= k; j++) {
+                const double* gj = g[j]; const double* wr = w[k - j];
+                for (int i = 0; i < MAXN; i++) sg[i] += gj[i] * wr[i];
+                for (int i = 1; i < MAXN; i++) xm[i] += gj[i - 1] * wr[i];
+                for (int i = 0; i + 1 < MAXN; i++) xp[i] += gj[i + 1] * wr[i];
+            }
+            for (int i = 0; i < n; i++) {
+                double f = -s.b[i] * sg[i];
+                if (i > 0)     f -= s.c[i - 1] * xm[i];
+                if (i < n - 1) f -= s.c[i] * xp[i];
+                u[k + 1][i] = v[k][i] / (k + 1);
+                v[k + 1][i] = f / (k + 1);
+            }
         }
         if (Psi) {
             for (int i = 0; i < n; i++) {
@@ -97,15 +115,20 @@ static void taylor_step(const Sys& s, double* phi, double* Psi, double h) {
                 Md[k][i] = d;
                 if (i < n - 1) Mo[k][i] = 2.0 * s.c[i] * q[k][i];
             }
-            for (int i = 0; i < n; i++) for (int cidx = 0; cidx < D; cidx++) {
-                double a = 0;
+            // all MAXD columns of a row at once (the columns >= D stay zero): every element sees the same operations in the same order as
+            // a column-by-column loop -- the same bits --, but the inner loops have a fixed length and vectorise
+            for (int i = 0; i < n; i++) {
+                double a[MAXD];
+                for (int cidx = 0; cidx < MAXD; cidx++) a[cidx] = 0;
                 for (int j = 0; j <= k; j++) {
-                    a += Md[j][i] * Pu[k - j][i][cidx];
-                    if (i > 0)     a += Mo[j][i - 1] * Pu[k - j][i - 1][cidx];
-                    if (i < n - 1) a += Mo[j][i] * Pu[k - j][i + 1][cidx];
+                    const double md = Md[j][i];
+                    const double* p0 = Pu[k - j][i];
+                    for (int cidx = 0; cidx < MAXD; cidx++) a[cidx] += md * p0[cidx];
+                    if (i > 0)     { const double mo = Mo[j][i - 1]; const double* p1 = Pu[k - j][i - 1]; for (int cidx = 0; cidx < MAXD; cidx++) a[cidx] += mo * p1[cidx]; }
+                    if (i < n - 1) { const double mo = Mo[j][i];     const double* p2 = Pu[k - j][i + 1]; for (int cidx = 0; cidx < MAXD; cidx++) a[cidx] += mo * p2[cidx]; }
                 }
-                Pu[k + 1][i][cidx] = Pv[k][i][cidx] / (k + 1);
-                Pv[k + 1][i][cidx] = a / (k + 1);
+                const double kk = k + 1;
+                for (int cidx = 0; cidx < MAXD; cidx++) { Pu[k + 1][i][cidx] = Pv[k][i][cidx] / kk; Pv[k + 1][i][cidx] = a[cidx] / kk; }
             }
         }
     }
@@ -114,10 +137,11 @@ static void taylor_step(const Sys& s, double* phi, double* Psi, double h) {
         for (int k = ORD; k >= 0; k--) { su = su * h + u[k][i]; sv = sv * h + v[k][i]; }
         phi[i] = su; phi[n + i] = sv;
     }
-    if (Psi) for (int i = 0; i < n; i++) for (int cidx = 0; cidx < D; cidx++) {
-        double su = 0, sv = 0;
-        for (int k = ORD; k >= 0; k--) { su = su * h + Pu[k][i][cidx]; sv = sv * h + Pv[k][i][cidx]; }
-        Psi[i * D + cidx] = su; Psi[(n + i) * D + cidx] = sv;
+    if (Psi) for (int i = 0; i < n; i++) {
+        double su[MAXD], sv[MAXD];
+        for (int cidx = 0; cidx < MAXD; cidx++) { su[cidx] = 0; sv[cidx] = 0; }
+        for (int k = ORD; k >= 0; k--) for (int cidx = 0; cidx < MAXD; cidx++) { su[cidx] = su[cidx] * h + Pu[k][i][cidx]; sv[cidx] = sv[cidx] * h + Pv[k][i][cidx]; }
+        for (int cidx = 0; cidx < D; cidx++) { Psi[i * D + cidx] = su[cidx]; Psi[(n + i) * D + cidx] = sv[cidx]; }
     }
 }
 
