@@ -29,7 +29,7 @@
 #define CCP_UNROLL_H 4      // Horner chains of the step image
 #endif
 #ifndef CCP_UNROLL_G
-#define CCP_UNROLL_G 2      // Horner chains of the grid loop
+#define CCP_UNROLL_G 4      // Horner chains of the grid loop (4: -1 % against 2 with the v26 code, 1 and 8 are slower; profiles/r2_v26_unroll_experiments.txt)
 #endif
 
 namespace ccp {
@@ -1227,13 +1227,14 @@ __device__ inline LaneC make_lanec(int tid) {
             if (pl == 0) { e = 0; ci = 0; ccc = c0l; }
             else if (pl >= 2 && (pl - 2) % 3 == 0) { e = 0; ci = 1 + (pl - 2) / 3; ccc = c0l; }
             cpat = ci == 0 ? 0 : (ci == N - 1 ? 2 : 1);
-            if (e >= 0) {
-                // source lanes of the two partner sums (entry_sum): a product a boundary component does not have is read from a lane whose sum is
-                // an exact zero -- lane 31 of the Psi warp (never owns a product), lane 0 of the phi warp (an A lane) -- instead of being selected
-                const int zl = wq == 1 ? 31 : 0;
-                const int sb = cpat == 0 ? zl : lane + 1, sc = cpat == 0 ? lane + 1 : (cpat == 1 ? lane + 2 : zl);
-                rowZ = sb | (sc << 8);                        // combiner lanes have no z rows: the word is free
-            }
+            // source lanes of the two partner sums (entry_sum): a product a boundary component does not have is read from a lane whose sum is
+            // an exact zero -- lane 31 of the Psi warp (never owns a product), lane 0 of the phi warp (an A lane) -- instead of being selected.
+            // The B lanes read two zeros: their "entry sum" is their own sum (x + 0 is exact and keeps the sign of a zero bound: the upper
+            // bound of a finished sum is never -0), so B lanes and entry leaders share the epilogue without a select.  The lanes that use
+            // scratch slots (M/H lanes) are neither: cs0, cs1 carry the two source lanes.
+            const int zl = wq == 1 ? 31 : 0;
+            if (e >= 0) { cs0 = cpat == 0 ? zl : lane + 1; cs1 = cpat == 0 ? lane + 1 : (cpat == 1 ? lane + 2 : zl); }
+            else if (wq == 0 && lane >= L::NA && lane < MB) { cs0 = zl; cs1 = zl; }
         } else if (wq == 1 && lane < N * D) { e = lane; ci = e / D; ccc = e % D; }
         if (e >= 0) {
             const int i = ci, cc = ccc;
@@ -1354,7 +1355,7 @@ __device__ __noinline__ void table_loop(FrontSmem<N>& S) {
             // singles: the sums of the one or two partner lanes arrive through shuffles (every lane of the warp executes them); the leader of an
             // entry forms (w0 + w1) + w2 with an exact zero for the product a boundary component does not have -- the additions of combine_c
             auto entry_sum = [&](const ival& f) -> ival {
-                const int sb = rowZ & 31, sc = (rowZ >> 8) & 31;      // make_lanec: partner lanes, or a lane holding an exact zero (B lanes: any lane, their result is not used)
+                const int sb = cs0 & 31, sc = cs1 & 31;               // make_lanec: partner lanes, or a lane holding an exact zero (M/H and A lanes: any lane, their result is not used)
                 const ival b = shfl_ival(f, sb), c = shfl_ival(f, sc);
                 return iadd(iadd(f, b), c);
             };
@@ -1402,7 +1403,7 @@ __device__ __noinline__ void table_loop(FrontSmem<N>& S) {
                     // B lanes and the leaders of the hosted entries of Psi share ONE epilogue: sum -> (mid,t) -> /(kc+1) -> /(kc+2) -> rows V, U (B: and Z)
                     const ival e0 = entry_sum(f0), e1 = entry_sum(f1);
                     if (kind == 1 || ccomb) {
-                        const ival g0 = kind == 1 ? f0 : e0, g1 = kind == 1 ? f1 : e1;
+                        const ival g0 = e0, g1 = e1;                  // B lanes: e = f + 0 + 0 = f
                         const mt i1 = inv[J + 1], i2 = inv[J + 2], i3 = inv[J + 3];
                         const mt v1 = mt_scale(iv2mt(g0), i1.m, i1.t), v2 = mt_scale(iv2mt(g1), i2.m, i2.t);
                         const mt u2 = mt_scale(v1, i2.m, i2.t), u3 = mt_scale(v2, i3.m, i3.t);
