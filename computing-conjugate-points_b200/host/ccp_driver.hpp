@@ -225,6 +225,8 @@ inline std::vector<int> computeFrontAndConjugatePointsBatch(int dimension, const
     lap("FindTime");
     for (int i = 0; i < newton_steps; i++) newtonRound(true);
     lap("Newton steps");
+    stage_times.emplace_back("  (validated-integration launches so far)", (double)BVP.launches());
+    stage_times.emplace_back("  (device time of those launches, s)", BVP.kernel_ms() * 1e-3);
 
     for (size_t q = 0; q < m; q++) if (alive(q)) guarded(q, [&] {
         Front& f = F[q];
@@ -262,6 +264,8 @@ inline std::vector<int> computeFrontAndConjugatePointsBatch(int dimension, const
     }
 
     lap("Krawczyk steps and proof");
+    stage_times.emplace_back("  (validated-integration launches so far)", (double)BVP.launches());
+    stage_times.emplace_back("  (device time of those launches, s)", BVP.kernel_ms() * 1e-3);
     // (ii) eigenfunction error and the L_- test; end points phi(L_+)
     parallel_for(m, [&](size_t q) { if (alive(q)) guarded(q, [&] {        // per-front interval algebra: independent between fronts
         Front& f = F[q];
