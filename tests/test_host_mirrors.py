@@ -154,6 +154,11 @@ def test_batch_driver_against_oracle_backend(pkg, orc):
     assert r.returncode == 0, r.stdout + r.stderr
     assert "batch == single-front driver on the probed fronts" in r.stdout
     assert "codes: 2 -2 1 0 -2 1" in r.stdout
+    # 36 fronts: enough for the per-front host stages to run on several host threads (parallel_for needs >= 32 items); the batch must still
+    # reproduce the single-front driver on the probed fronts
+    r = subprocess.run([exe, "12", "3"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "batch == single-front driver on the probed fronts" in r.stdout and "36 fronts, 36 connecting orbits proven" in r.stdout
     # the two-component system: a front with one conjugate point, a stable front (0, proven end to end), another with one
     r = subprocess.run([exe, "n2"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
